@@ -1,0 +1,197 @@
+"""ctypes binding of libb200stencil.so — the C-ABI drop-in boundary (include/b200stencil.h).
+
+The reference reaches its generated kernel the same way: `ctypes` load of a shared object,
+`argtypes` from each parameter's `_C_ctype`, one blocking call per `Operator.apply`
+(devito/operator/operator.py:857-869, :1029-1032).  There is NO fallback: if the library or a
+GPU is missing, `lib()` raises `BackendUnavailable`.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_ulong, c_ulonglong,
+                    c_void_p)
+
+import numpy as np
+
+from .exceptions import BackendUnavailable
+
+__all__ = ['lib', 'have_lib', 'have_gpu', 'Dataobj', 'Profiler', 'Sparse', 'IsoArgs', 'TtiArgs',
+           'make_dataobj', 'nccl_library_path', 'LIB_PATH']
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libb200stencil.so')
+
+
+class Dataobj(Structure):
+    """`struct dataobj` (devito/types/dense.py:737-746)."""
+    _fields_ = [('data', c_void_p), ('size', POINTER(c_int)), ('nbytes', c_ulong),
+                ('npsize', POINTER(c_ulong)), ('dsize', POINTER(c_ulong)),
+                ('hsize', POINTER(c_int)), ('hofs', POINTER(c_int)), ('oofs', POINTER(c_int)),
+                ('dmap', c_void_p)]
+
+
+class Profiler(Structure):
+    _fields_ = [('section0', c_double), ('section1', c_double), ('section2', c_double),
+                ('haloupdate0', c_double)]
+
+
+class Sparse(Structure):
+    _fields_ = [('data', POINTER(Dataobj)), ('gp', POINTER(Dataobj)),
+                ('w', POINTER(Dataobj) * 3), ('p_m', c_int), ('p_M', c_int), ('r', c_int)]
+
+
+class IsoArgs(Structure):
+    _fields_ = [('ndim', c_int), ('space_order', c_int), ('radius', c_int),
+                ('w', POINTER(c_float) * 3),
+                ('u', POINTER(Dataobj)), ('damp', POINTER(Dataobj)),
+                ('param_kind', c_int), ('param', POINTER(Dataobj)), ('vp', c_float),
+                ('dt', c_float),
+                ('x_m', c_int), ('x_M', c_int), ('y_m', c_int), ('y_M', c_int),
+                ('z_m', c_int), ('z_M', c_int), ('time_m', c_int), ('time_M', c_int),
+                ('src', POINTER(Sparse)), ('rec', POINTER(Sparse)), ('rec_toff', c_int),
+                ('errctl', c_int), ('deviceid', c_int), ('kernel', c_int),
+                ('halo', c_void_p), ('timers', POINTER(Profiler))]
+
+
+class TtiArgs(Structure):
+    _fields_ = [('space_order', c_int), ('radius', c_int),
+                ('w2', POINTER(c_float) * 3), ('w1', POINTER(c_float) * 3),
+                ('u', POINTER(Dataobj)), ('v', POINTER(Dataobj)), ('damp', POINTER(Dataobj)),
+                ('vp', c_float), ('epsilon', c_float), ('delta', c_float), ('theta', c_float),
+                ('phi', c_float), ('dt', c_float),
+                ('x_m', c_int), ('x_M', c_int), ('y_m', c_int), ('y_M', c_int),
+                ('z_m', c_int), ('z_M', c_int), ('time_m', c_int), ('time_M', c_int),
+                ('src', POINTER(Sparse)), ('rec', POINTER(Sparse)), ('rec_toff', c_int),
+                ('errctl', c_int), ('deviceid', c_int), ('kernel', c_int),
+                ('halo', c_void_p), ('timers', POINTER(Profiler))]
+
+
+_lib = None
+
+# every symbol include/b200stencil.h declares
+SYMBOLS = ['b2_iso_forward', 'b2_tti_forward', 'b2_nccl_unique_id', 'b2_halo_create',
+           'b2_halo_destroy', 'b2_halo_update', 'b2_device_count', 'b2_last_error', 'b2_version',
+           'b2_launch_count', 'b2_kernel_timing_reset', 'b2_kernel_timing_ms',
+           'b2_kernel_timing_enable', 'b2_malloc_device', 'b2_free_device', 'b2_memcpy_h2d',
+           'b2_memcpy_d2h', 'b2_memset_device', 'b2_synchronize', 'b2_set_stream']
+
+
+def have_lib():
+    return os.path.exists(LIB_PATH)
+
+
+def load_library():
+    """Load the shared object and declare signatures (no GPU needed for this)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not have_lib():
+        raise BackendUnavailable(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C devito_b200/csrc`). The wave-propagation path has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    L.b2_iso_forward.argtypes = [POINTER(IsoArgs)]
+    L.b2_iso_forward.restype = c_int
+    L.b2_tti_forward.argtypes = [POINTER(TtiArgs)]
+    L.b2_tti_forward.restype = c_int
+    L.b2_nccl_unique_id.argtypes = [c_char_p, c_char_p]
+    L.b2_nccl_unique_id.restype = c_int
+    L.b2_halo_create.argtypes = [c_char_p, c_char_p, c_int, c_int, c_int]
+    L.b2_halo_create.restype = c_void_p
+    L.b2_halo_destroy.argtypes = [c_void_p]
+    L.b2_halo_destroy.restype = None
+    L.b2_halo_update.argtypes = [c_void_p, POINTER(Dataobj), c_int, c_int]
+    L.b2_halo_update.restype = c_int
+    L.b2_device_count.restype = c_int
+    L.b2_last_error.restype = c_char_p
+    L.b2_version.restype = c_char_p
+    L.b2_launch_count.restype = c_ulonglong
+    L.b2_kernel_timing_reset.restype = None
+    L.b2_kernel_timing_ms.argtypes = [POINTER(c_int)]
+    L.b2_kernel_timing_ms.restype = c_double
+    L.b2_kernel_timing_enable.argtypes = [c_int]
+    L.b2_kernel_timing_enable.restype = None
+    L.b2_malloc_device.argtypes = [c_ulong, c_int]
+    L.b2_malloc_device.restype = c_void_p
+    L.b2_free_device.argtypes = [c_void_p, c_int]
+    L.b2_free_device.restype = None
+    L.b2_memcpy_h2d.argtypes = [c_void_p, c_void_p, c_ulong, c_int]
+    L.b2_memcpy_h2d.restype = c_int
+    L.b2_memcpy_d2h.argtypes = [c_void_p, c_void_p, c_ulong, c_int]
+    L.b2_memcpy_d2h.restype = c_int
+    L.b2_memset_device.argtypes = [c_void_p, c_int, c_ulong, c_int]
+    L.b2_memset_device.restype = c_int
+    L.b2_synchronize.argtypes = [c_int]
+    L.b2_synchronize.restype = c_int
+    L.b2_set_stream.argtypes = [c_void_p]
+    L.b2_set_stream.restype = None
+    _lib = L
+    return L
+
+
+_gpu_checked = None
+
+
+def have_gpu():
+    global _gpu_checked
+    if _gpu_checked is None:
+        try:
+            _gpu_checked = load_library().b2_device_count() > 0
+        except BackendUnavailable:
+            _gpu_checked = False
+    return _gpu_checked
+
+
+def lib():
+    """The library, ready to compute. Raises BackendUnavailable without a B200-class GPU."""
+    L = load_library()
+    if not have_gpu():
+        raise BackendUnavailable("no CUDA device visible: the wave-propagation path runs only on the "
+                                 "GPU (there is deliberately no CPU fallback)")
+    return L
+
+
+def nccl_library_path():
+    try:
+        import nvidia.nccl as n
+        p = os.path.join(list(n.__path__)[0], 'lib', 'libnccl.so.2')
+        if os.path.exists(p):
+            return p.encode()
+    except Exception:
+        pass
+    return b'libnccl.so.2'
+
+
+class DataobjHolder:
+    """Keeps the ctypes arrays (and the ndarray) alive next to the struct, like the reference
+    stashes the ndarray on the ctypes object (devito/types/dense.py:774-776)."""
+
+    def __init__(self, host=None, dev_ptr=None, shape=None, halo=None, itemsize=4):
+        if host is not None:
+            assert host.flags['C_CONTIGUOUS']
+            shape = host.shape
+            itemsize = host.dtype.itemsize
+        self.host = host
+        nd = len(shape)
+        self._size = (c_int * nd)(*[int(s) for s in shape])
+        halo = halo or tuple((0, 0) for _ in shape)
+        flat = [int(v) for pair in halo for v in pair]
+        self._hsize = (c_int * (2 * nd))(*flat)
+        self._hofs = (c_int * (2 * nd))(*[0] * (2 * nd))
+        self._oofs = (c_int * (2 * nd))(*[0] * (2 * nd))
+        self.obj = Dataobj()
+        self.obj.data = host.ctypes.data if host is not None else None
+        self.obj.size = ctypes.cast(self._size, POINTER(c_int))
+        self.obj.nbytes = int(np.prod(shape)) * itemsize
+        self.obj.npsize = None
+        self.obj.dsize = None
+        self.obj.hsize = ctypes.cast(self._hsize, POINTER(c_int))
+        self.obj.hofs = ctypes.cast(self._hofs, POINTER(c_int))
+        self.obj.oofs = ctypes.cast(self._oofs, POINTER(c_int))
+        self.obj.dmap = dev_ptr
+
+    @property
+    def ptr(self):
+        return ctypes.pointer(self.obj)
+
+
+def make_dataobj(host=None, dev_ptr=None, shape=None, halo=None):
+    return DataobjHolder(host=host, dev_ptr=dev_ptr, shape=shape, halo=halo)

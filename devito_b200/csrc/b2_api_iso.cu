@@ -1,0 +1,221 @@
+// C-ABI entry point b2_iso_forward: the whole time loop of the reference's generated
+// `Forward` function (examples/seismic/acoustic/operators.py:113-150 builds it; loop shape
+// printed in examples/seismic/tutorials/08_snapshotting.ipynb:473-505):
+//
+//   for time in [time_m, time_M]:  t0 = time % T, t1 = (time+1) % T, t2 = (time+T-1) % T
+//       [haloupdate u[t0]]            (devito/mpi/routines.py:457-510; here NCCL, b2_halo.cu)
+//       section0: u[t1] = stencil(u[t0], u[t2], m, damp)
+//       section1: u[t1] += inject(src[time])
+//       section2: rec[time] = interpolate(u[t0] | u[t1])
+#include "b2_iso.cuh"
+#include "b2_sparse.cuh"
+#include "b2_halo.cuh"
+#include <vector>
+
+using namespace b2;
+
+namespace b2 {
+
+// NaN/Inf check (reference: errctl='max' checks every 100 steps, passes/iet/errors.py:59-85)
+__global__ void k_check_finite(const float *__restrict__ f, size_t n, int *flag) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= !isfinite(f[i]);
+    if (bad) atomicOr(flag, 1);
+}
+
+int check_finite(const float *f, size_t n, bool &bad) {
+    static int *d_flag = nullptr;
+    if (!d_flag) B2_CUDA(cudaMalloc(&d_flag, sizeof(int)), B2_ERR_MEMORY);
+    B2_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), stream()), B2_ERR_MEMORY);
+    k_check_finite<<<148 * 4, 256, 0, stream()>>>(f, n, d_flag);
+    count_launch();
+    int h = 0;
+    B2_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream()), B2_ERR_MEMORY);
+    B2_CUDA(cudaStreamSynchronize(stream()), B2_ERR_DEVICE);
+    bad = h != 0;
+    return B2_OK;
+}
+
+// Section timing with a reusable pool of CUDA events: 4 events per time step.
+struct StepEvents {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    bool on = false;
+    cudaEvent_t next() {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        cudaEvent_t e = ev[used++];
+        cudaEventRecord(e, stream());
+        return e;
+    }
+};
+static StepEvents g_step_events;
+
+}  // namespace b2
+
+extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
+    if (!a || !a->u) { set_error("b2_iso_forward: NULL args"); return B2_ERR_INVALID; }
+    if (a->ndim != 2 && a->ndim != 3) { set_error("b2_iso_forward: ndim must be 2 or 3"); return B2_ERR_INVALID; }
+    if (a->radius < 1 || a->radius > B2_MAX_RADIUS || a->radius > a->space_order) {
+        set_error("b2_iso_forward: unsupported radius %d (space_order %d)", a->radius, a->space_order);
+        return B2_ERR_INVALID;
+    }
+    if (a->time_M < a->time_m) return B2_OK;
+    B2_CUDA(cudaSetDevice(a->deviceid), B2_ERR_DEVICE);
+
+    const int nd = a->ndim;
+    const int so = a->space_order;
+    int rc = B2_OK;
+
+    DevArray u, damp, param;
+    SparseDev src, rec;
+    IsoPlan p;
+    FieldGeom g;
+    bool staged_u = false, staged_damp = false, staged_param = false;
+
+    auto cleanup = [&](int code) {
+        // copy back what the reference would copy back (u and rec), free staged copies
+        int r1 = staged_u ? stage_out(u, code == B2_OK || code == B2_ERR_NAN) : B2_OK;
+        if (staged_damp) stage_out(damp, false);
+        if (staged_param) stage_out(param, false);
+        sparse_stage_out(src, false);
+        int r2 = sparse_stage_out(rec, code == B2_OK || code == B2_ERR_NAN);
+        if (code != B2_OK) return code;
+        return r1 ? r1 : r2;
+    };
+
+    if ((rc = stage_in(a->u, nd + 1, u, true))) return cleanup(rc);
+    staged_u = true;
+    if (a->damp) {
+        if ((rc = stage_in(a->damp, nd, damp, true))) return cleanup(rc);
+        staged_damp = true;
+    }
+    if (a->param_kind != B2_PARAM_SCALAR) {
+        if (!a->param) { set_error("b2_iso_forward: param array missing"); return cleanup(B2_ERR_INVALID); }
+        if ((rc = stage_in(a->param, nd, param, true))) return cleanup(rc);
+        staged_param = true;
+    }
+    if ((rc = sparse_stage_in(a->src, nd, src, true))) return cleanup(rc);
+    if ((rc = sparse_stage_in(a->rec, nd, rec, true))) return cleanup(rc);
+
+    // ---- geometry in the internal 3-dim convention ----
+    const int lo_in[3] = {a->x_m, a->y_m, a->z_m};
+    const int hi_in[3] = {a->x_M, a->y_M, a->z_M};
+    p.tsize = u.size[0];
+    p.so = so;
+    if (nd == 3) {
+        for (int d = 0; d < 3; ++d) {
+            p.a[d] = u.size[d + 1];
+            p.n[d] = hi_in[d] - lo_in[d] + 1;
+            p.o[d] = lo_in[d] + so;
+            p.radius[d] = a->radius;
+        }
+    } else {
+        p.a[0] = 1; p.n[0] = 1; p.o[0] = 0; p.radius[0] = 0;
+        for (int d = 0; d < 2; ++d) {
+            p.a[d + 1] = u.size[d + 1];
+            p.n[d + 1] = hi_in[d] - lo_in[d] + 1;
+            p.o[d + 1] = lo_in[d] + so;
+            p.radius[d + 1] = a->radius;
+        }
+    }
+    for (int d = 0; d < 3; ++d) {
+        if (p.n[d] <= 0) return cleanup(B2_OK);
+        const int rd = p.radius[d];
+        if (p.o[d] - rd < 0 || p.o[d] + p.n[d] - 1 + rd >= p.a[d]) {
+            set_error("b2_iso_forward: iteration range [%d,%d] + radius %d leaves the allocated "
+                      "array (extent %d) on dim %d", lo_in[nd == 3 ? d : d - 1], hi_in[nd == 3 ? d : d - 1],
+                      rd, p.a[d], d);
+            return cleanup(B2_ERR_INVALID);
+        }
+    }
+    p.sy = p.a[2];
+    p.sx = (long long)p.a[1] * p.a[2];
+    p.slot_elems = (size_t)p.a[0] * p.a[1] * p.a[2];
+    p.u = (float *)u.d;
+    p.damp = a->damp ? (const float *)damp.d : nullptr;
+    p.param = a->param_kind != B2_PARAM_SCALAR ? (const float *)param.d : nullptr;
+    p.param_kind = a->param_kind;
+    p.vp = a->vp;
+    p.dt = a->dt;
+    for (int d = 0; d < nd; ++d) {
+        const int di = nd == 3 ? d : d + 1;
+        if (!a->w[d]) { set_error("b2_iso_forward: weights for dim %d missing", d); return cleanup(B2_ERR_INVALID); }
+        for (int i = 0; i <= a->radius; ++i) p.w[di][i] = a->w[d][i];
+    }
+    if ((rc = iso_plan_init(p, a->kernel))) return cleanup(rc);
+
+    g.sx = p.sx;
+    g.sy = p.sy;
+    g.slot_elems = p.slot_elems;
+    g.so = so;
+    g.ndim = nd;
+    for (int d = 0; d < nd; ++d) { g.lo[d] = lo_in[d]; g.hi[d] = hi_in[d]; }
+
+    const float dt2 = a->dt * a->dt;
+    const float scalar_scale = dt2 * a->vp * a->vp;
+    const int T = p.tsize;
+    const bool timing = a->timers != nullptr;
+    StepEvents &se = g_step_events;
+    se.used = 0;
+    const int nsteps = a->time_M - a->time_m + 1;
+    const bool per_step_events = timing && nsteps <= 4096;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (timing && !per_step_events) ev_begin = se.next();
+
+    for (int time = a->time_m; time <= a->time_M; ++time) {
+        const int t0 = ((time % T) + T) % T;
+        const int t1 = (((time + 1) % T) + T) % T;
+        const int t2 = (((time - 1) % T) + T) % T;
+        if (per_step_events) se.next();
+        if (a->halo) {
+            if ((rc = halo_exchange_and_step_iso(a->halo, p, t0, t2, t1))) return cleanup(rc);
+        } else {
+            if ((rc = iso_step(p, t0, t2, t1, 0, p.n[0]))) return cleanup(rc);
+        }
+        if (per_step_events) se.next();
+        float *f1 = p.u + (size_t)t1 * p.slot_elems;
+        if ((rc = launch_inject(src, g, f1, nullptr, time, p.param_kind, p.param, scalar_scale, dt2)))
+            return cleanup(rc);
+        if (per_step_events) se.next();
+        const float *fr = p.u + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
+        if ((rc = launch_interp(rec, g, fr, nullptr, time))) return cleanup(rc);
+        if (per_step_events) se.next();
+        if (a->errctl && ((time - a->time_m) % 100 == 99 || time == a->time_M)) {
+            bool bad = false;
+            if ((rc = check_finite(f1, p.slot_elems, bad))) return cleanup(rc);
+            if (bad) { set_error("NaN/Inf detected in u at time=%d", time); return cleanup(B2_ERR_NAN); }
+        }
+    }
+    if (timing && !per_step_events) ev_end = se.next();
+
+    cudaError_t e = cudaStreamSynchronize(stream());
+    if (e != cudaSuccess) {
+        set_error("b2_iso_forward: device error: %s", cudaGetErrorString(e));
+        return cleanup(B2_ERR_LAUNCH);
+    }
+    if (timing) {
+        if (per_step_events) {
+            double s0 = 0, s1 = 0, s2 = 0;
+            for (size_t i = 0; i + 3 < se.used; i += 4) {
+                float ms;
+                cudaEventElapsedTime(&ms, se.ev[i], se.ev[i + 1]); s0 += ms;
+                cudaEventElapsedTime(&ms, se.ev[i + 1], se.ev[i + 2]); s1 += ms;
+                cudaEventElapsedTime(&ms, se.ev[i + 2], se.ev[i + 3]); s2 += ms;
+            }
+            a->timers->section0 += s0 * 1e-3;
+            a->timers->section1 += s1 * 1e-3;
+            a->timers->section2 += s2 * 1e-3;
+        } else {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev_begin, ev_end);
+            a->timers->section0 += ms * 1e-3;
+        }
+    }
+    return cleanup(B2_OK);
+}

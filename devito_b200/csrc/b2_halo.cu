@@ -1,0 +1,208 @@
+// NCCL point-to-point halo exchange for x-slab decomposition, one process per GPU.
+//
+// Replaces the reference's generated MPI routines `haloupdate0/sendrecv0/gather0/scatter0`
+// (devito/mpi/routines.py:285-552; printed in examples/mpi/overview.ipynb:503-560). Because
+// the decomposed dimension x is the slowest-varying one of the (t, x, y, z) row-major
+// layout, a face of `width` yz-planes is one contiguous block: no pack/unpack kernels
+// (`gather0/scatter0`) are needed and NCCL sends/receives straight from/to field memory.
+// Only `radius` planes are exchanged (the reference ships the full `space_order`-wide halo,
+// devito/types/dense.py:1256-1259). Neighbours at the physical boundary are skipped
+// (MPI_PROC_NULL in the reference, routines.py:429-433).
+#include "b2_halo.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+    void *dl = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+int load_nccl(const char *path) {
+    if (g_nccl.dl) return B2_OK;
+    const char *cands[] = {path, "libnccl.so.2", "libnccl.so"};
+    void *dl = nullptr;
+    for (const char *c : cands) {
+        if (!c || !*c) continue;
+        dl = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (dl) break;
+    }
+    if (!dl) { b2::set_error("cannot dlopen NCCL (%s)", dlerror()); return B2_ERR_COMM; }
+#define LOAD(field, sym)                                                              \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(dl, sym));          \
+    if (!g_nccl.field) { b2::set_error("NCCL symbol %s missing", sym); return B2_ERR_COMM; }
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(Send, "ncclSend")
+    LOAD(Recv, "ncclRecv")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    g_nccl.dl = dl;
+    return B2_OK;
+}
+
+#define B2_NCCL(call)                                                                   \
+    do {                                                                                \
+        ncclResult_t _r = (call);                                                       \
+        if (_r != ncclSuccess) {                                                        \
+            b2::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                  \
+                          g_nccl.GetErrorString(_r));                                   \
+            return B2_ERR_COMM;                                                         \
+        }                                                                               \
+    } while (0)
+
+}  // namespace
+
+namespace b2 {
+
+int halo_enqueue(b2_halo_ctx *ctx, float *base, size_t plane_elems, int lo, int n, int width) {
+    const int left = ctx->rank - 1, right = ctx->rank + 1;
+    const bool has_l = left >= 0, has_r = right < ctx->nranks;
+    if (!has_l && !has_r) return B2_OK;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const size_t cnt = plane_elems * (size_t)width;
+    B2_NCCL(g_nccl.GroupStart());
+    if (has_l) {
+        B2_NCCL(g_nccl.Send(base + (size_t)lo * plane_elems, cnt, ncclFloat, left, comm, ctx->comm_stream));
+        B2_NCCL(g_nccl.Recv(base + (size_t)(lo - width) * plane_elems, cnt, ncclFloat, left, comm,
+                            ctx->comm_stream));
+    }
+    if (has_r) {
+        B2_NCCL(g_nccl.Send(base + (size_t)(lo + n - width) * plane_elems, cnt, ncclFloat, right, comm,
+                            ctx->comm_stream));
+        B2_NCCL(g_nccl.Recv(base + (size_t)(lo + n) * plane_elems, cnt, ncclFloat, right, comm,
+                            ctx->comm_stream));
+    }
+    B2_NCCL(g_nccl.GroupEnd());
+    return B2_OK;
+}
+
+int halo_exchange_and_step_iso(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1) {
+    const int R = p.radius[0];
+    const int n = p.n[0];
+    if (n < 2 * R) {
+        set_error("halo: local slab of %d planes is thinner than 2*radius=%d", n, 2 * R);
+        return B2_ERR_INVALID;
+    }
+    cudaStream_t main = stream();
+    B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
+    B2_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0), B2_ERR_COMM);
+    float *base = p.u + (size_t)t0 * p.slot_elems;
+    int rc = halo_enqueue(ctx, base, (size_t)p.sx, p.o[0], n, R);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream), B2_ERR_COMM);
+    if ((rc = iso_step(p, t0, t2, t1, R, n - 2 * R))) return rc;
+    B2_CUDA(cudaStreamWaitEvent(main, ctx->ev_comm, 0), B2_ERR_COMM);
+    if ((rc = iso_step(p, t0, t2, t1, 0, R))) return rc;
+    if ((rc = iso_step(p, t0, t2, t1, n - R, R))) return rc;
+    return B2_OK;
+}
+
+int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t2, int t1) {
+    // TTI footprint: Laplacian star of radius R (the rotated derivatives stay within R-1)
+    const int R = p.R;
+    const int n = p.n[0];
+    if (n < 2 * R) {
+        set_error("halo: local slab of %d planes is thinner than 2*radius=%d", n, 2 * R);
+        return B2_ERR_INVALID;
+    }
+    cudaStream_t main = stream();
+    B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
+    B2_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0), B2_ERR_COMM);
+    int rc;
+    if ((rc = halo_enqueue(ctx, p.u + (size_t)t0 * p.slot_elems, (size_t)p.sx, p.o[0], n, R))) return rc;
+    if ((rc = halo_enqueue(ctx, p.v + (size_t)t0 * p.slot_elems, (size_t)p.sx, p.o[0], n, R))) return rc;
+    B2_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream), B2_ERR_COMM);
+    if ((rc = tti_step(p, t0, t2, t1, R, n - 2 * R))) return rc;
+    B2_CUDA(cudaStreamWaitEvent(main, ctx->ev_comm, 0), B2_ERR_COMM);
+    if ((rc = tti_step(p, t0, t2, t1, 0, R))) return rc;
+    if ((rc = tti_step(p, t0, t2, t1, n - R, R))) return rc;
+    return B2_OK;
+}
+
+}  // namespace b2
+
+extern "C" {
+
+int b2_nccl_unique_id(const char *nccl_lib, char id_out[128]) {
+    int rc = load_nccl(nccl_lib);
+    if (rc) return rc;
+    ncclUniqueId id;
+    B2_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id_out, &id, 128);
+    return B2_OK;
+}
+
+b2_halo_ctx *b2_halo_create(const char *nccl_lib, const char id_in[128], int rank, int nranks,
+                            int deviceid) {
+    if (load_nccl(nccl_lib)) return nullptr;
+    if (cudaSetDevice(deviceid) != cudaSuccess) { b2::set_error("cudaSetDevice(%d) failed", deviceid); return nullptr; }
+    b2_halo_ctx *ctx = new b2_halo_ctx();
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    ctx->deviceid = deviceid;
+    ncclUniqueId id;
+    memcpy(&id, id_in, 128);
+    ncclComm_t comm;
+    ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        b2::set_error("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+        delete ctx;
+        return nullptr;
+    }
+    ctx->comm = comm;
+    cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming);
+    return ctx;
+}
+
+void b2_halo_destroy(b2_halo_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->deviceid);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    if (ctx->comm) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    delete ctx;
+}
+
+int b2_halo_update(b2_halo_ctx *ctx, struct b2_dataobj *f, int slot, int width) {
+    if (!ctx || !f || !f->dmap) { b2::set_error("b2_halo_update: needs a device-resident field"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaSetDevice(ctx->deviceid), B2_ERR_DEVICE);
+    // f is (t, x, y, z) or (x, y, z) when slot < 0
+    const int nd = slot < 0 ? 3 : 4;
+    const int *sz = f->size;
+    const int ax = sz[nd - 3], ay = sz[nd - 2], az = sz[nd - 1];
+    const size_t plane = (size_t)ay * az;
+    const int so_l = f->hsize ? f->hsize[2 * (nd - 3)] : width;
+    const int so_r = f->hsize ? f->hsize[2 * (nd - 3) + 1] : width;
+    if (width > so_l || width > so_r) { b2::set_error("b2_halo_update: width %d exceeds halo", width); return B2_ERR_INVALID; }
+    float *base = (float *)f->dmap + (slot < 0 ? 0 : (size_t)slot * ax * plane);
+    cudaStream_t main = b2::stream();
+    B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
+    B2_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0), B2_ERR_COMM);
+    int rc = b2::halo_enqueue(ctx, base, plane, so_l, ax - so_l - so_r, width);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream), B2_ERR_COMM);
+    B2_CUDA(cudaStreamWaitEvent(main, ctx->ev_comm, 0), B2_ERR_COMM);
+    B2_CUDA(cudaStreamSynchronize(main), B2_ERR_COMM);
+    return B2_OK;
+}
+
+}  // extern "C"

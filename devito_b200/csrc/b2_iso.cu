@@ -1,0 +1,498 @@
+// Isotropic acoustic time-update kernels for sm_100a.
+//
+// Numerical spec (reference: examples/seismic/acoustic/operators.py:71-107 `iso_stencil`,
+// `laplacian` :50-68; generated form printed by the reference's own code generator):
+//
+//   u[t+1] = ( m/dt^2 (2 u[t] - u[t-1]) + damp/dt u[t] + sum_d sum_k w_d[k] u[t][..+k..] )
+//            / ( m/dt^2 + damp/dt )
+//
+// with w_d[k] = finite_diff_weights(2, ...)/h_d^2 (devito/finite_differences/tools.py:231-236).
+//
+// Two kernels:
+//   k_iso_generic : one thread per point, any radius <= 8, 2-D or 3-D, any alignment.
+//   k_iso_tma     : 2.5-D sweep. A CTA owns a (TY x TZ) yz-tile and marches along x.
+//                   A producer warp streams haloed yz-planes of u[t] (and the matching tiles
+//                   of u[t-1], damp, vp|m) into shared-memory rings with TMA
+//                   (cp.async.bulk.tensor) signalled on mbarriers; consumer threads own four
+//                   consecutive z points (float4), keep the x-direction neighbours in a
+//                   register queue, read y/z neighbours from the shared plane, and write
+//                   u[t+1] with 16-byte coalesced stores. No tensor cores: the update is
+//                   HBM-bandwidth bound (16 B/point).
+#include "b2_iso.cuh"
+#include "b2_ptx.cuh"
+#include <cstdlib>
+#include <algorithm>
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------
+// generic kernel
+// ------------------------------------------------------------------------------------------
+struct IsoGK {
+    const float *__restrict__ u0;
+    const float *__restrict__ um;
+    float *__restrict__ u1;
+    const float *__restrict__ damp;
+    const float *__restrict__ param;
+    long long sx, sy;
+    int n0, n1, n2;          // extents of this launch (dim0 count is xcount)
+    int o0, o1, o2;          // array index of first point (o0 already includes xlo)
+    int r0, r1, r2;          // radius per dim
+    int param_kind;
+    float m_dt2, inv_dt, inv_dt2;
+    float w[3][B2_MAX_RADIUS + 1];
+};
+
+__global__ void __launch_bounds__(256) k_iso_generic(IsoGK k) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (z >= k.n2 || y >= k.n1) return;
+    for (int x = blockIdx.z; x < k.n0; x += gridDim.z) {
+        const long long idx = (long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z);
+        const float c = k.u0[idx];
+        float acc = (k.w[0][0] + k.w[1][0] + k.w[2][0]) * c;
+        for (int i = 1; i <= k.r0; ++i)
+            acc += k.w[0][i] * (k.u0[idx - i * k.sx] + k.u0[idx + i * k.sx]);
+        for (int i = 1; i <= k.r1; ++i)
+            acc += k.w[1][i] * (k.u0[idx - i * k.sy] + k.u0[idx + i * k.sy]);
+        for (int i = 1; i <= k.r2; ++i)
+            acc += k.w[2][i] * (k.u0[idx - i] + k.u0[idx + i]);
+        float m_dt2 = k.m_dt2;
+        if (k.param_kind == B2_PARAM_VP) {
+            const float v = k.param[idx];
+            m_dt2 = k.inv_dt2 / (v * v);
+        } else if (k.param_kind == B2_PARAM_M) {
+            m_dt2 = k.param[idx] * k.inv_dt2;
+        }
+        const float d = k.damp ? k.damp[idx] * k.inv_dt : 0.f;
+        const float num = m_dt2 * (2.f * c - k.um[idx]) + d * c + acc;
+        k.u1[idx] = num / (m_dt2 + d);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA 2.5-D kernel
+// ------------------------------------------------------------------------------------------
+template <int R>
+struct IsoTK {
+    float *__restrict__ u1;      // base of the output time slot
+    long long sx, sy;
+    int ny, nz;                  // iteration extents (for masking)
+    int ox, oy, oz;
+    int xlo, xcount, lx;
+    int ntz, nty;
+    int slot0, slotm;
+    float m_dt2, inv_dt, inv_dt2;
+    float wx[R + 1], wy[R + 1], wz[R + 1];
+};
+
+constexpr int ceil4(int v) { return (v + 3) / 4 * 4; }
+constexpr int align32f(int v) { return (v + 31) / 32 * 32; }   // 128-byte multiples in floats
+
+template <int R, int TY, int TZ4, int PF, int PK>
+struct IsoTmaCfg {
+    static constexpr int RZ = ceil4(R);
+    static constexpr int TZ = 4 * TZ4;
+    static constexpr int BY = TY + 2 * R;
+    static constexpr int BZ = TZ + 2 * RZ;
+    static constexpr int NU = R + 1 + PF;
+    static constexpr int NS = PF + 1;
+    static constexpr int Q = 2 * R + 1;
+    static constexpr int PLANE = align32f(BY * BZ);
+    static constexpr int TILE = TY * TZ;
+    static constexpr int NCW = TY * TZ4 / 32;          // consumer warps
+    static constexpr int NTILES = 2 + (PK != B2_PARAM_SCALAR ? 1 : 0);   // prev, damp, [param]
+    static constexpr size_t SMEM =
+        (size_t)(NU * PLANE + NS * TILE * NTILES) * 4 + 2 * NU * 8 + 128;
+};
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ void f4fma(float4 &acc, float w, float4 v) {
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+}
+
+template <int R, int TY, int TZ4, int PF, int PK>
+__global__ void __launch_bounds__(TY *TZ4 + 32, 1)
+k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUtensorMap tm_uc,
+          const __grid_constant__ CUtensorMap tm_damp, const __grid_constant__ CUtensorMap tm_par,
+          const IsoTK<R> k) {
+    using C = IsoTmaCfg<R, TY, TZ4, PF, PK>;
+    constexpr int RZ = C::RZ, TZ = C::TZ, BZ = C::BZ, NU = C::NU, NS = C::NS, Q = C::Q;
+    constexpr int PLANE = C::PLANE, TILE = C::TILE, NCW = C::NCW;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_u = reinterpret_cast<float *>(smem_raw);
+    float *s_prev = s_u + NU * PLANE;
+    float *s_damp = s_prev + NS * TILE;
+    float *s_par = s_damp + NS * TILE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_par + (PK != B2_PARAM_SCALAR ? NS * TILE : 0));
+    uint64_t *empty = full + NU;
+
+    int b = blockIdx.x;
+    const int iz = b % k.ntz;
+    b /= k.ntz;
+    const int iy = b % k.nty;
+    const int ix = b / k.nty;
+    const int z0 = iz * TZ, y0 = iy * C::BY - iy * 2 * R;   // = iy * TY
+    const int xs = k.xlo + ix * k.lx;
+    const int xe = min(xs + k.lx, k.xlo + k.xcount);
+    const int NP = (xe - xs) + 2 * R;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < NU; ++i) {
+            b2ptx::mbar_init(&full[i], 1);
+            b2ptx::mbar_init(&empty[i], NCW);
+        }
+        b2ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ---------------- producer warp: one lane drives the TMA engine ----------------
+        if (lane == 0) {
+            b2ptx::tma_prefetch_desc(&tm_uh);
+            b2ptx::tma_prefetch_desc(&tm_uc);
+            b2ptx::tma_prefetch_desc(&tm_damp);
+            if (PK != B2_PARAM_SCALAR) b2ptx::tma_prefetch_desc(&tm_par);
+            int slot = 0, round = 0, ss = 0;
+            for (int j = 0; j < NP; ++j) {
+                if (round > 0) b2ptx::mbar_wait(&empty[slot], (round - 1) & 1);
+                const int s = j - 2 * R;
+                uint32_t bytes = C::BY * BZ * 4;
+                if (s >= 0) bytes += TILE * 4 * C::NTILES;
+                b2ptx::mbar_arrive_expect_tx(&full[slot], bytes);
+                b2ptx::tma_load_4d(s_u + slot * PLANE, &tm_uh, &full[slot], k.oz + z0 - RZ,
+                                   k.oy + y0 - R, k.ox + xs - R + j, k.slot0);
+                if (s >= 0) {
+                    b2ptx::tma_load_4d(s_prev + ss * TILE, &tm_uc, &full[slot], k.oz + z0,
+                                       k.oy + y0, k.ox + xs + s, k.slotm);
+                    b2ptx::tma_load_3d(s_damp + ss * TILE, &tm_damp, &full[slot], k.oz + z0,
+                                       k.oy + y0, k.ox + xs + s);
+                    if (PK != B2_PARAM_SCALAR)
+                        b2ptx::tma_load_3d(s_par + ss * TILE, &tm_par, &full[slot], k.oz + z0,
+                                           k.oy + y0, k.ox + xs + s);
+                    if (++ss == NS) ss = 0;
+                }
+                if (++slot == NU) { slot = 0; ++round; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int ty = tid / TZ4, tz4 = tid % TZ4;
+    const int gy = y0 + ty, gz = z0 + 4 * tz4;
+    const bool yok = gy < k.ny;
+    const int zcnt = yok ? min(max(k.nz - gz, 0), 4) : 0;
+    const float *my_col = s_u + (ty + R) * BZ + RZ + 4 * tz4;
+    const int tile_off = ty * TZ + 4 * tz4;
+    float *outp = k.u1 + (long long)(k.ox + xs) * k.sx + (long long)(k.oy + gy) * k.sy + (k.oz + gz);
+
+    float4 q[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const float wc = k.wx[0] + k.wy[0] + k.wz[0];
+    int slot_h = 0, par_h = 0;      // ring slot / parity of the newest plane j
+    int slot_c = 0;                 // ring slot of plane j-R (valid once j >= R)
+    int ss = 0;                     // prev/damp ring slot of output step j-2R
+
+    for (int jb = 0; jb < NP; jb += Q) {
+#pragma unroll
+        for (int p = 0; p < Q; ++p) {
+            const int j = jb + p;
+            if (j >= NP) break;
+            b2ptx::mbar_wait(&full[slot_h], par_h);
+            q[p] = b2ptx::lds128(my_col + slot_h * PLANE);
+
+            if (j >= 2 * R) {
+                const float *cp = my_col + slot_c * PLANE;
+                const float4 c = q[(p - R + Q) % Q];
+                // z direction: gather the row segment [-RZ, 4+RZ) around my 4 points
+                float zr[4 + 2 * RZ];
+#pragma unroll
+                for (int m = 0; m < RZ / 4; ++m) {
+                    const float4 l = b2ptx::lds128(cp - RZ + 4 * m);
+                    zr[4 * m + 0] = l.x; zr[4 * m + 1] = l.y; zr[4 * m + 2] = l.z; zr[4 * m + 3] = l.w;
+                    const float4 r = b2ptx::lds128(cp + 4 + 4 * m);
+                    zr[RZ + 4 + 4 * m + 0] = r.x; zr[RZ + 4 + 4 * m + 1] = r.y;
+                    zr[RZ + 4 + 4 * m + 2] = r.z; zr[RZ + 4 + 4 * m + 3] = r.w;
+                }
+                zr[RZ + 0] = c.x; zr[RZ + 1] = c.y; zr[RZ + 2] = c.z; zr[RZ + 3] = c.w;
+                float4 acc = make_float4(wc * c.x, wc * c.y, wc * c.z, wc * c.w);
+#pragma unroll
+                for (int i = 1; i <= R; ++i) {
+                    acc.x = fmaf(k.wz[i], zr[RZ + 0 - i] + zr[RZ + 0 + i], acc.x);
+                    acc.y = fmaf(k.wz[i], zr[RZ + 1 - i] + zr[RZ + 1 + i], acc.y);
+                    acc.z = fmaf(k.wz[i], zr[RZ + 2 - i] + zr[RZ + 2 + i], acc.z);
+                    acc.w = fmaf(k.wz[i], zr[RZ + 3 - i] + zr[RZ + 3 + i], acc.w);
+                }
+#pragma unroll
+                for (int i = 1; i <= R; ++i) {
+                    const float4 a = b2ptx::lds128(cp - i * BZ);
+                    const float4 bb = b2ptx::lds128(cp + i * BZ);
+                    f4fma(acc, k.wy[i], f4add(a, bb));
+                }
+#pragma unroll
+                for (int i = 1; i <= R; ++i)
+                    f4fma(acc, k.wx[i], f4add(q[(p - R - i + 2 * Q) % Q], q[(p - R + i + Q) % Q]));
+
+                const float4 pv = b2ptx::lds128(s_prev + ss * TILE + tile_off);
+                const float4 dm = b2ptx::lds128(s_damp + ss * TILE + tile_off);
+                float4 md = make_float4(k.m_dt2, k.m_dt2, k.m_dt2, k.m_dt2);
+                if (PK == B2_PARAM_VP) {
+                    const float4 v = b2ptx::lds128(s_par + ss * TILE + tile_off);
+                    md = make_float4(k.inv_dt2 / (v.x * v.x), k.inv_dt2 / (v.y * v.y),
+                                     k.inv_dt2 / (v.z * v.z), k.inv_dt2 / (v.w * v.w));
+                } else if (PK == B2_PARAM_M) {
+                    const float4 v = b2ptx::lds128(s_par + ss * TILE + tile_off);
+                    md = make_float4(v.x * k.inv_dt2, v.y * k.inv_dt2, v.z * k.inv_dt2, v.w * k.inv_dt2);
+                }
+                float4 o;
+                {
+                    const float d0 = dm.x * k.inv_dt, d1 = dm.y * k.inv_dt, d2 = dm.z * k.inv_dt,
+                                d3 = dm.w * k.inv_dt;
+                    o.x = (fmaf(md.x, 2.f * c.x - pv.x, fmaf(d0, c.x, acc.x))) / (md.x + d0);
+                    o.y = (fmaf(md.y, 2.f * c.y - pv.y, fmaf(d1, c.y, acc.y))) / (md.y + d1);
+                    o.z = (fmaf(md.z, 2.f * c.z - pv.z, fmaf(d2, c.z, acc.z))) / (md.z + d2);
+                    o.w = (fmaf(md.w, 2.f * c.w - pv.w, fmaf(d3, c.w, acc.w))) / (md.w + d3);
+                }
+                float *dst = outp + (long long)(j - 2 * R) * k.sx;
+                if (zcnt == 4) {
+                    *reinterpret_cast<float4 *>(dst) = o;
+                } else if (zcnt > 0) {
+                    dst[0] = o.x;
+                    if (zcnt > 1) dst[1] = o.y;
+                    if (zcnt > 2) dst[2] = o.z;
+                }
+                if (++ss == NS) ss = 0;
+            }
+            if (j >= R) {
+                __syncwarp();
+                if (lane == 0) b2ptx::mbar_arrive(&empty[slot_c]);
+                if (++slot_c == NU) slot_c = 0;
+            }
+            if (++slot_h == NU) { slot_h = 0; par_h ^= 1; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+// tensor map over a (t?, x, y, z) f32 array; box = (bz, by, 1[, 1])
+static int make_tmap(CUtensorMap *tm, const void *base, int rank, const int *dims_zyxt,
+                     int bz, int by) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return B2_ERR_DEVICE; }
+    cuuint64_t gdim[4];
+    cuuint64_t gstr[3];
+    cuuint32_t box[4] = {(cuuint32_t)bz, (cuuint32_t)by, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint64_t stride = 4;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = (cuuint64_t)dims_zyxt[i];
+        stride *= gdim[i];
+        if (i < rank - 1) gstr[i] = stride;
+    }
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base),
+                     gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rank=%d box=(%d,%d)", (int)r, rank, bz, by);
+        return B2_ERR_DEVICE;
+    }
+    return B2_OK;
+}
+
+// tile configuration per radius (TY, TZ4, PF); tuned on B200 (see profiles/)
+template <int R> struct TileOf;
+template <> struct TileOf<2> { static constexpr int TY = 32, TZ4 = 16, PF = 3; };
+template <> struct TileOf<4> { static constexpr int TY = 32, TZ4 = 16, PF = 3; };
+template <> struct TileOf<6> { static constexpr int TY = 32, TZ4 = 16, PF = 3; };
+template <> struct TileOf<8> { static constexpr int TY = 32, TZ4 = 16, PF = 2; };
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int R>
+static int plan_tma(IsoPlan &p) {
+    using T = TileOf<R>;
+    constexpr int RZ = ceil4(R);
+    const int dims4[4] = {p.a[2], p.a[1], p.a[0], p.tsize};
+    const int dims3[3] = {p.a[2], p.a[1], p.a[0]};
+    int rc;
+    if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T::TZ4 + 2 * RZ, T::TY + 2 * R))) return rc;
+    if ((rc = make_tmap(&p.tm_uc, p.u, 4, dims4, 4 * T::TZ4, T::TY))) return rc;
+    if ((rc = make_tmap(&p.tm_damp, p.damp, 3, dims3, 4 * T::TZ4, T::TY))) return rc;
+    if (p.param_kind != B2_PARAM_SCALAR) {
+        if ((rc = make_tmap(&p.tm_par, p.param, 3, dims3, 4 * T::TZ4, T::TY))) return rc;
+    } else {
+        p.tm_par = p.tm_damp;
+    }
+    return B2_OK;
+}
+
+int iso_plan_init(IsoPlan &p, int kernel) {
+    const int R = p.radius[2];
+    bool ok = (p.radius[0] == R && p.radius[1] == R) && (R == 2 || R == 4 || R == 6 || R == 8);
+    ok = ok && p.damp != nullptr;
+    ok = ok && (p.a[2] % 4 == 0) && (p.o[2] % 4 == 0);
+    ok = ok && ((uintptr_t)p.u % 16 == 0) && ((uintptr_t)p.damp % 16 == 0);
+    ok = ok && (p.param_kind == B2_PARAM_SCALAR || (uintptr_t)p.param % 16 == 0);
+    ok = ok && (p.slot_elems % 4 == 0);
+    // tiny grids gain nothing from the pipelined kernel
+    ok = ok && (p.n[1] >= 8 && p.n[2] >= 16);
+    if (kernel == 1) ok = false;
+    if (kernel == 2 && !ok) {
+        set_error("iso: TMA kernel forced but layout does not qualify (radius=%d a2=%d o2=%d)", R,
+                  p.a[2], p.o[2]);
+        return B2_ERR_INVALID;
+    }
+    p.use_tma = ok;
+    if (!ok) return B2_OK;
+    switch (R) {
+        case 2: return plan_tma<2>(p);
+        case 4: return plan_tma<4>(p);
+        case 6: return plan_tma<6>(p);
+        case 8: return plan_tma<8>(p);
+    }
+    return B2_ERR_INVALID;
+}
+
+template <int R, int PK>
+static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
+    using T = TileOf<R>;
+    using C = IsoTmaCfg<R, T::TY, T::TZ4, T::PF, PK>;
+    auto kern = k_iso_tma<R, T::TY, T::TZ4, T::PF, PK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),
+                B2_ERR_LAUNCH);
+        attr_set = true;
+    }
+    IsoTK<R> k;
+    k.u1 = p.u + (size_t)slot1 * p.slot_elems;
+    k.sx = p.sx;
+    k.sy = p.sy;
+    k.ny = p.n[1];
+    k.nz = p.n[2];
+    k.ox = p.o[0];
+    k.oy = p.o[1];
+    k.oz = p.o[2];
+    k.xlo = xlo;
+    k.xcount = xcount;
+    k.ntz = (p.n[2] + C::TZ - 1) / C::TZ;
+    k.nty = (p.n[1] + T::TY - 1) / T::TY;
+    // x-chunk length: enough CTAs for ~16 waves of 148 SMs, but chunks of at least 32 planes
+    int lx = env_int("B2_ISO_LX", 0);
+    if (lx <= 0) {
+        const int tiles = k.ntz * k.nty;
+        const int want = 148 * 16;
+        int nchunks = std::max(1, want / std::max(1, tiles));
+        lx = std::max(32, (xcount + nchunks - 1) / nchunks);
+        lx = std::min(lx, xcount);
+    }
+    k.lx = lx;
+    const int ntx = (xcount + lx - 1) / lx;
+    k.slot0 = slot0;
+    k.slotm = slotm;
+    const float inv_dt = 1.0f / p.dt;
+    k.inv_dt = inv_dt;
+    k.inv_dt2 = 1.0f / (p.dt * p.dt);
+    k.m_dt2 = (1.0f / (p.vp * p.vp)) * k.inv_dt2;
+    for (int i = 0; i <= R; ++i) {
+        k.wx[i] = p.w[0][i];
+        k.wy[i] = p.w[1][i];
+        k.wz[i] = p.w[2][i];
+    }
+    const unsigned grid = (unsigned)(k.ntz * k.nty * ntx);
+    timing_begin();
+    kern<<<grid, T::TY * T::TZ4 + 32, C::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
+    timing_end();
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
+template <int R>
+static int launch_tma_pk(const IsoPlan &p, int s0, int sm, int s1, int xlo, int xcount) {
+    switch (p.param_kind) {
+        case B2_PARAM_SCALAR: return launch_tma<R, B2_PARAM_SCALAR>(p, s0, sm, s1, xlo, xcount);
+        case B2_PARAM_VP: return launch_tma<R, B2_PARAM_VP>(p, s0, sm, s1, xlo, xcount);
+        case B2_PARAM_M: return launch_tma<R, B2_PARAM_M>(p, s0, sm, s1, xlo, xcount);
+    }
+    return B2_ERR_INVALID;
+}
+
+int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
+    if (xcount <= 0) return B2_OK;
+    if (p.use_tma) {
+        switch (p.radius[2]) {
+            case 2: return launch_tma_pk<2>(p, slot0, slotm, slot1, xlo, xcount);
+            case 4: return launch_tma_pk<4>(p, slot0, slotm, slot1, xlo, xcount);
+            case 6: return launch_tma_pk<6>(p, slot0, slotm, slot1, xlo, xcount);
+            case 8: return launch_tma_pk<8>(p, slot0, slotm, slot1, xlo, xcount);
+        }
+        return B2_ERR_INVALID;
+    }
+    IsoGK k;
+    k.u0 = p.u + (size_t)slot0 * p.slot_elems;
+    k.um = p.u + (size_t)slotm * p.slot_elems;
+    k.u1 = p.u + (size_t)slot1 * p.slot_elems;
+    k.damp = p.damp;
+    k.param = p.param;
+    k.sx = p.sx;
+    k.sy = p.sy;
+    k.n0 = xcount;
+    k.n1 = p.n[1];
+    k.n2 = p.n[2];
+    k.o0 = p.o[0] + xlo;
+    k.o1 = p.o[1];
+    k.o2 = p.o[2];
+    k.r0 = p.radius[0];
+    k.r1 = p.radius[1];
+    k.r2 = p.radius[2];
+    k.param_kind = p.param_kind;
+    k.inv_dt = 1.0f / p.dt;
+    k.inv_dt2 = 1.0f / (p.dt * p.dt);
+    k.m_dt2 = (1.0f / (p.vp * p.vp)) * k.inv_dt2;
+    memcpy(k.w, p.w, sizeof(k.w));
+    dim3 block(64, 4, 1);
+    dim3 grid((k.n2 + 63) / 64, (k.n1 + 3) / 4, (unsigned)std::min(xcount, 65535));
+    timing_begin();
+    k_iso_generic<<<grid, block, 0, stream()>>>(k);
+    timing_end();
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
+}  // namespace b2

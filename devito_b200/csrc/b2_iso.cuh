@@ -1,0 +1,37 @@
+// Internal interface of the isotropic-acoustic stencil kernels (b2_iso.cu).
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+struct IsoPlan {
+    // geometry (internal dims are always 3: for 2-D grids dim 0 is a dummy of extent 1)
+    int radius[3] = {0, 0, 0};
+    int so = 0;
+    int a[3] = {1, 1, 1};        // allocated extents
+    int n[3] = {1, 1, 1};        // iteration extents
+    int o[3] = {0, 0, 0};        // array index of the first iterated point
+    long long sx = 0, sy = 0;    // element strides of dim0 / dim1 (dim2 stride = 1)
+    size_t slot_elems = 0;
+    int tsize = 3;
+    float *u = nullptr;
+    const float *damp = nullptr;
+    const float *param = nullptr;
+    int param_kind = B2_PARAM_SCALAR;
+    float vp = 1.f, dt = 1.f;
+    float w[3][B2_MAX_RADIUS + 1] = {};
+    // TMA path
+    bool use_tma = false;
+    CUtensorMap tm_uh, tm_uc, tm_damp, tm_par;
+    int lx = 0;
+};
+
+// Prepare the plan (decides generic vs TMA kernel, encodes tensor maps). `kernel`: 0 auto,
+// 1 force generic, 2 force TMA (error if the layout does not qualify).
+int iso_plan_init(IsoPlan &p, int kernel);
+
+// One time step over x in [xlo, xlo + xcount) (relative to the iteration origin):
+// u[slot1] = update(u[slot0], u[slotm]).
+int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount);
+
+}  // namespace b2

@@ -1,0 +1,167 @@
+// Runtime plumbing of libb200stencil: stream, error string, staging of `struct dataobj`
+// arrays (host <-> device, mirroring the reference's `acc enter data copyin / exit data
+// copyout` placed by DeviceAwareDataManager, devito/passes/iet/definitions.py:636-671),
+// launch counter, kernel timing, small device-memory utilities.
+#include "b2_common.cuh"
+#include <cstdarg>
+#include <vector>
+
+namespace b2 {
+
+thread_local std::string g_last_error;
+cudaStream_t g_stream = nullptr;
+cudaStream_t g_user_stream = nullptr;
+unsigned long long g_launches = 0;
+
+static bool g_timing_on = false;
+static std::vector<cudaEvent_t> g_timing_events;   // pairs (begin, end)
+static size_t g_timing_used = 0;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+cudaStream_t stream() {
+    if (g_user_stream) return g_user_stream;
+    if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
+    return g_stream;
+}
+
+void timing_begin() {
+    if (!g_timing_on) return;
+    if (g_timing_used + 2 > g_timing_events.size()) {
+        if (g_timing_events.size() >= 16384) return;   // bounded pool
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        g_timing_events.push_back(a);
+        g_timing_events.push_back(b);
+    }
+    cudaEventRecord(g_timing_events[g_timing_used], stream());
+}
+
+void timing_end() {
+    if (!g_timing_on) return;
+    if (g_timing_used + 2 > g_timing_events.size()) return;
+    cudaEventRecord(g_timing_events[g_timing_used + 1], stream());
+    g_timing_used += 2;
+}
+
+int stage_in(const b2_dataobj *obj, int ndim, DevArray &out, bool copy_in) {
+    if (!obj) { set_error("stage_in: NULL dataobj"); return B2_ERR_INVALID; }
+    out.ndim = ndim;
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) { out.size[i] = obj->size[i]; n *= (size_t)obj->size[i]; }
+    out.nbytes = obj->nbytes ? (size_t)obj->nbytes : n * 4;
+    out.h = obj->data;
+    if (obj->dmap) {
+        out.d = obj->dmap;
+        out.owned = false;
+        return B2_OK;
+    }
+    if (!obj->data) { set_error("stage_in: dataobj has neither data nor dmap"); return B2_ERR_INVALID; }
+    B2_CUDA(cudaMalloc(&out.d, out.nbytes), B2_ERR_MEMORY);
+    out.owned = true;
+    if (copy_in)
+        B2_CUDA(cudaMemcpyAsync(out.d, out.h, out.nbytes, cudaMemcpyHostToDevice, stream()),
+                B2_ERR_MEMORY);
+    return B2_OK;
+}
+
+int stage_out(DevArray &a, bool copy_back) {
+    if (!a.owned) return B2_OK;
+    int rc = B2_OK;
+    if (copy_back) {
+        cudaError_t e = cudaMemcpyAsync(a.h, a.d, a.nbytes, cudaMemcpyDeviceToHost, stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream());
+        if (e != cudaSuccess) { set_error("stage_out: %s", cudaGetErrorString(e)); rc = B2_ERR_MEMORY; }
+    }
+    cudaFree(a.d);
+    a.d = nullptr;
+    a.owned = false;
+    return rc;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+int b2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *b2_last_error(void) { return g_last_error.c_str(); }
+
+const char *b2_version(void) { return "b200stencil 0.1 (sm_100a)"; }
+
+unsigned long long b2_launch_count(void) { return g_launches; }
+
+void b2_kernel_timing_enable(int on) { g_timing_on = on != 0; }
+
+void b2_kernel_timing_reset(void) { g_timing_used = 0; }
+
+double b2_kernel_timing_ms(int *nlaunches) {
+    double total = 0.0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < g_timing_used; i += 2) {
+        float ms = 0.f;
+        cudaEventSynchronize(g_timing_events[i + 1]);
+        if (cudaEventElapsedTime(&ms, g_timing_events[i], g_timing_events[i + 1]) == cudaSuccess) {
+            total += ms;
+            ++n;
+        }
+    }
+    if (nlaunches) *nlaunches = n;
+    return n ? total / n : 0.0;
+}
+
+void *b2_malloc_device(unsigned long nbytes, int deviceid) {
+    void *p = nullptr;
+    if (cudaSetDevice(deviceid) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&p, nbytes) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void b2_free_device(void *p, int deviceid) {
+    cudaSetDevice(deviceid);
+    cudaFree(p);
+}
+
+int b2_memcpy_h2d(void *dst, const void *src, unsigned long nbytes, int deviceid) {
+    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    B2_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, stream()), B2_ERR_MEMORY);
+    B2_CUDA(cudaStreamSynchronize(stream()), B2_ERR_MEMORY);
+    return B2_OK;
+}
+
+int b2_memcpy_d2h(void *dst, const void *src, unsigned long nbytes, int deviceid) {
+    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    B2_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, stream()), B2_ERR_MEMORY);
+    B2_CUDA(cudaStreamSynchronize(stream()), B2_ERR_MEMORY);
+    return B2_OK;
+}
+
+int b2_memset_device(void *dst, int value, unsigned long nbytes, int deviceid) {
+    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    B2_CUDA(cudaMemsetAsync(dst, value, nbytes, stream()), B2_ERR_MEMORY);
+    return B2_OK;
+}
+
+int b2_synchronize(int deviceid) {
+    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    B2_CUDA(cudaStreamSynchronize(stream()), B2_ERR_DEVICE);
+    return B2_OK;
+}
+
+void b2_set_stream(void *s) { g_user_stream = (cudaStream_t)s; }
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// Sparse source injection / receiver interpolation kernels (internal interface).
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+struct SparseDev {
+    bool present = false;
+    DevArray data, gp, w[3];
+    int npoint_total = 0;   // second extent of data
+    int nt = 0;
+    int p_m = 0, p_M = -1;
+    int r = 1;
+    int ndim = 3;
+};
+
+// Field geometry the sparse kernels need (internal 3-dim convention, see IsoPlan)
+struct FieldGeom {
+    long long sx = 0, sy = 0;
+    size_t slot_elems = 0;
+    int so = 0;
+    int ndim = 3;
+    int lo[3] = {0, 0, 0};      // x_m, y_m, z_m
+    int hi[3] = {0, 0, 0};      // x_M, y_M, z_M
+};
+
+int sparse_stage_in(const b2_sparse *s, int ndim, SparseDev &out, bool copy_data_in);
+int sparse_stage_out(SparseDev &s, bool copy_data_back);
+
+// u[cell] += w*w*w * src[time][p] * scale(cell) for up to two fields (TTI injects into u and v)
+// scale(cell) = dt^2 * vp^2 | dt^2 * vp[cell]^2 | dt^2 / m[cell]
+int launch_inject(const SparseDev &s, const FieldGeom &g, float *f0, float *f1, int time,
+                  int param_kind, const float *param, float scalar_scale, float dt2);
+
+// rec[time][p] = sum w*w*w * (f0[cell] (+ f1[cell]))
+int launch_interp(const SparseDev &s, const FieldGeom &g, const float *f0, const float *f1, int time);
+
+}  // namespace b2

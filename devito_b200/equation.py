@@ -1,0 +1,64 @@
+"""Equations and the linear solve used to derive explicit time updates.
+
+`Eq`/`Inc` mirror devito/types/equation.py; `solve` mirrors devito/operations/solve.py:19-78:
+the expression must be linear in the target, and the result is `-rest / coefficient`."""
+from .symbolics import Expr, as_expr, linear_terms, Number, NonLinear
+
+__all__ = ['Eq', 'Inc', 'solve']
+
+
+class Eq:
+    is_Increment = False
+
+    def __init__(self, lhs, rhs=0, subdomain=None, coefficients=None, implicit_dims=None, **kwargs):
+        self.lhs = as_expr(lhs)
+        self.rhs = as_expr(rhs)
+        self.subdomain = subdomain
+        self.implicit_dims = implicit_dims
+
+    @property
+    def args(self):
+        return (self.lhs, self.rhs)
+
+    def func(self, lhs, rhs, subdomain=None, **kwargs):
+        return type(self)(lhs, rhs, subdomain=subdomain if subdomain is not None else self.subdomain,
+                          implicit_dims=self.implicit_dims)
+
+    @property
+    def evaluate(self):
+        return self.func(self.lhs, self.rhs.evaluate)
+
+    def subs(self, mapping):
+        return self.func(self.lhs.subs(mapping), self.rhs.subs(mapping))
+
+    xreplace = subs
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self.lhs!r}, {self.rhs!r})"
+
+    # list-like concatenation convenience (`[eq] + src_term`)
+    def __add__(self, other):
+        return [self] + list(other)
+
+    def __radd__(self, other):
+        return list(other) + [self]
+
+
+class Inc(Eq):
+    is_Increment = True
+
+
+def solve(eq, target, **kwargs):
+    """Algebraically solve `eq == 0` (or an `Eq`) for `target`; `eq` must be linear in it."""
+    if isinstance(eq, Eq):
+        eq = eq.lhs - eq.rhs
+    expr = as_expr(eq).evaluate
+    target = as_expr(target)
+    try:
+        terms, rest = linear_terms(expr, lambda a: a == target)
+    except NonLinear as e:
+        raise ValueError(f"solve: expression is not linear in {target!r}: {e}") from None
+    if not terms:
+        raise ValueError(f"solve: {target!r} does not appear in the expression")
+    coef = list(terms.values())[0]
+    return (-1 * rest) / coef

@@ -1,0 +1,987 @@
+"""`Operator`: same construction/apply contract as the reference, different engine.
+
+Reference contract kept (devito/operator/operator.py): `Operator(exprs, subs=, name=, opt=,
+platform=, language=, compiler=)` (:168), `op.apply(**overrides)` / `op(**overrides)` (:906,
+:956), `op.arguments(**kw)` (:796), `op.cfunction` (:857), the returned
+`PerformanceSummary` (operator/profiling.py:432), non-zero return code -> `ExecutionError`
+(:734-772), unknown kwargs -> `InvalidArgument` (:588-592).
+
+What is replaced: the reference lowers the expressions through its compiler
+(`_lower`, :283-315) and JIT-compiles C.  Here `Operator.__init__` runs a *semantic pattern
+recogniser*: the time-update equations are decomposed into their linear stencil
+(`symbolics.linear_terms`), and that stencil is compared — numerically, at random parameter
+values — with the stencil the hand-written CUDA kernels implement (isotropic acoustic:
+examples/seismic/acoustic/operators.py:71-150; TTI centred: examples/seismic/tti/
+operators.py:186-247, 431-480).  On a match the operator becomes a thin marshalling layer
+over the C ABI in include/b200stencil.h (one FFI crossing per `apply`, like the reference's
+`cfunction(*arg_values)`, :1032).  Everything else (set-up operators) goes to the NumPy
+interpreter.  The recognised path NEVER falls back to the CPU.
+"""
+import ctypes
+import itertools
+import time as _time
+from collections import OrderedDict
+
+import numpy as np
+
+from .symbolics import (Expr, Number, Symbol, Add, Mul, Pow, Call, Access, as_expr, linear_terms,
+                        NonLinear, fd_weights, fd_offsets, _py_funcs)
+from .types import Function, TimeFunction, Constant, Dimension
+from .sparse import Injection, Interpolation, SparseTimeFunction
+from .equation import Eq, Inc
+from .interpreter import Interpreter
+from .parameters import configuration
+from .exceptions import InvalidArgument, ExecutionError, BackendUnavailable, InvalidOperator
+from .logger import perf, warning
+from .tools import flatten
+from . import _lib as L_
+from . import distributed
+
+__all__ = ['Operator', 'PerformanceSummary']
+
+B2_PARAM_SCALAR, B2_PARAM_VP, B2_PARAM_M = 0, 1, 2
+
+
+# ---------------------------------------------------------------------------------------------
+# performance summary (devito/operator/profiling.py:432-527)
+# ---------------------------------------------------------------------------------------------
+class PerfEntry:
+    def __init__(self, time, gflopss=None, gpointss=None, oi=None, ops=None, itershapes=None):
+        self.time = time
+        self.gflopss = gflopss
+        self.gpointss = gpointss
+        self.oi = oi
+        self.ops = ops
+        self.itershapes = itershapes
+
+    def __repr__(self):
+        return f"PerfEntry(time={self.time}, gpointss={self.gpointss})"
+
+
+class PerformanceSummary(OrderedDict):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.globals = {}
+
+    @property
+    def timings(self):
+        return OrderedDict((k, v.time) for k, v in self.items())
+
+    @property
+    def gflopss(self):
+        return OrderedDict((k, v.gflopss) for k, v in self.items())
+
+    @property
+    def gpointss(self):
+        return OrderedDict((k, v.gpointss) for k, v in self.items())
+
+    @property
+    def oi(self):
+        return OrderedDict((k, v.oi) for k, v in self.items())
+
+    @property
+    def time(self):
+        return sum(v.time for v in self.values())
+
+
+# ---------------------------------------------------------------------------------------------
+# scalar evaluation of coefficient expressions (for the recogniser)
+# ---------------------------------------------------------------------------------------------
+def eval_scalar(expr, leaf):
+    if isinstance(expr, Number):
+        return float(expr.value)
+    if expr.is_Access or expr.is_Symbol:
+        return leaf(expr)
+    if isinstance(expr, Add):
+        return sum(eval_scalar(a, leaf) for a in expr.args)
+    if isinstance(expr, Mul):
+        out = 1.0
+        for a in expr.args:
+            out *= eval_scalar(a, leaf)
+        return out
+    if isinstance(expr, Pow):
+        return eval_scalar(expr.base, leaf) ** eval_scalar(expr.exponent, leaf)
+    if isinstance(expr, Call):
+        return float(_py_funcs[expr.name](eval_scalar(expr.arg, leaf)))
+    if expr.is_Derivative:
+        return eval_scalar(expr.evaluate, leaf)
+    raise TypeError(type(expr).__name__)
+
+
+def _space_offsets(acc, space_dims):
+    """Integer (time_shift, (dx, dy, dz)) of an access, or None if not a plain shifted access."""
+    f = acc.function
+    tshift = 0
+    offs = []
+    for idx, d in zip(acc.index_objs, f.dimensions):
+        if idx.absolute is not None or idx.shift.denominator != 1:
+            return None
+        if d.is_Time:
+            tshift = int(idx.shift)
+        else:
+            if idx.base is not d and idx.base != d:
+                return None
+            offs.append(int(idx.shift))
+    return tshift, tuple(offs)
+
+
+def second_derivative_weights(space_order, h):
+    """w[k]/h^2, k = 0..so/2 (symmetric). Reference: `u.laplace` -> per-dim
+    finite_diff_weights(2, range(-so/2, so/2+1), 0), each evalf(9) (finite_difference.py:185-187)."""
+    R = space_order // 2
+    w = fd_weights(2, list(range(-R, R + 1)), 0)
+    return [w[R + k] / (float(h) ** 2) for k in range(R + 1)]
+
+
+def half_node_first_derivative_weights(space_order, h):
+    """Weights of `f.dx(fd_order=so/2, x0=x+h/2)` for offsets (-R/2+1 .. R/2), R = so/2
+    (devito/finite_differences/tools.py:289-297; tti/operators.py:88-102)."""
+    R = space_order // 2
+    offs = fd_offsets(R, 0.5) if False else list(range(-R // 2 + 1, R // 2 + 1))
+    from fractions import Fraction
+    w = fd_weights(1, offs, Fraction(1, 2))
+    return [c / float(h) for c in w]
+
+
+class _Unrecognised(Exception):
+    pass
+
+
+# ---------------------------------------------------------------------------------------------
+# the operator
+# ---------------------------------------------------------------------------------------------
+class Operator:
+    _known_opts = ('opt', 'platform', 'language', 'compiler', 'mpi', 'allocator', 'profiling',
+                   'autotune', 'deviceid')
+
+    def __init__(self, expressions, subs=None, name='Kernel', **kwargs):
+        self.name = name
+        self._options = {k: kwargs.get(k) for k in self._known_opts if k in kwargs}
+        items = flatten([expressions] if not isinstance(expressions, (list, tuple)) else list(expressions))
+        self._items = []
+        for it in items:
+            if isinstance(it, Eq):
+                self._items.append(('eq', it))
+            elif isinstance(it, Injection):
+                self._items.append(('inject', it))
+            elif isinstance(it, Interpolation):
+                self._items.append(('interp', it))
+            else:
+                raise InvalidOperator(f"unsupported expression type {type(it).__name__}")
+        self._subs = {as_expr(k): v for k, v in (subs or {}).items()}
+        self._plan = None
+        self._why_not = None
+        try:
+            self._plan = self._recognise()
+        except _Unrecognised as e:
+            self._why_not = str(e)
+        self._interp = None if self._plan is not None else Interpreter(self._items, None, self._subs, name=name)
+        self._profiler_last = None
+
+    # ------------------------------------------------------------------------------------------
+    # recognition
+    # ------------------------------------------------------------------------------------------
+    @property
+    def backend(self):
+        return 'cuda-sm100a' if self._plan is not None else 'numpy-interpreter'
+
+    def _recognise(self):
+        eqs = [o for k, o in self._items if k == 'eq']
+        injs = [o for k, o in self._items if k == 'inject']
+        itps = [o for k, o in self._items if k == 'interp']
+        if not eqs or any(e.is_Increment for e in eqs):
+            raise _Unrecognised("no plain time-update equations")
+        updates = []
+        for e in eqs:
+            lhs = e.lhs
+            if not (lhs.is_Access and getattr(lhs.function, 'is_TimeFunction', False)):
+                raise _Unrecognised("lhs is not a TimeFunction")
+            f = lhs.function
+            so = _space_offsets(lhs, None)
+            if so is None or so[0] != 1 or any(so[1]):
+                raise _Unrecognised("lhs is not `f.forward`")
+            if f.time_order != 2:
+                raise _Unrecognised("time_order != 2")
+            if e.subdomain is not None and any(d.is_Sub for d in e.subdomain.dimensions):
+                raise _Unrecognised("restricted subdomain")
+            updates.append((f, e))
+        if len(injs) > 1 or len(itps) > 1:
+            raise _Unrecognised("more than one injection/interpolation")
+        if len(updates) == 1:
+            return self._recognise_iso(updates[0], injs, itps)
+        if len(updates) == 2:
+            return self._recognise_tti(updates, injs, itps)
+        raise _Unrecognised("unsupported number of update equations")
+
+    def _coeffs(self, rhs, fields):
+        rhs = rhs.evaluate
+        if self._subs:
+            rhs = rhs.subs(self._subs)
+        fset = {id(f) for f in fields}
+        try:
+            terms, rest = linear_terms(rhs, lambda a: id(a.function) in fset)
+        except NonLinear as e:
+            raise _Unrecognised(f"update is not linear in the wavefield: {e}") from None
+        if not (rest.is_Number and float(rest.value) == 0.0):
+            raise _Unrecognised("update has a source term that is not a sparse injection")
+        return terms
+
+    @staticmethod
+    def _leaves(exprs):
+        """Non-wavefield leaves of the coefficient expressions."""
+        funcs, consts, syms = {}, {}, {}
+        for ex in exprs:
+            for n in ex.preorder():
+                if n.is_Access:
+                    funcs[id(n.function)] = n
+                elif n.is_Constant:
+                    consts[id(n)] = n
+                elif n.is_Symbol and not n.is_Dimension:
+                    syms[n.name] = n
+        return list(funcs.values()), list(consts.values()), list(syms.values())
+
+    def _probe_env(self, rng, funcs, consts, syms, grid, fixed=None):
+        vals = {}
+        for a in funcs:
+            vals[('f', id(a.function))] = rng.uniform(0.5, 2.0)
+        for c in consts:
+            vals[('c', id(c))] = rng.uniform(0.1, 0.9)
+        for s in syms:
+            vals[('s', s.name)] = rng.uniform(0.5, 2.0)
+        for sp, v in grid.spacing_map.items():
+            vals[('s', sp.name)] = float(v)
+        vals.update(fixed or {})
+
+        def leaf(n):
+            if n.is_Access:
+                return vals[('f', id(n.function))]
+            if n.is_Constant:
+                return vals[('c', id(n))]
+            return vals[('s', n.name)]
+        return vals, leaf
+
+    def _spacing_values(self, grid):
+        out = []
+        for d, h in zip(grid.dimensions, grid.spacing):
+            v = self._subs.get(d.spacing)
+            out.append(float(v if v is not None else h))
+        return out
+
+    def _recognise_iso(self, update, injs, itps):
+        u, eq = update
+        grid = u.grid
+        nd = grid.dim
+        if nd not in (2, 3):
+            raise _Unrecognised("only 2-D/3-D grids")
+        so = u.space_order
+        if so % 2 or so < 2 or so // 2 > 8:
+            raise _Unrecognised(f"space_order {so} unsupported")
+        R = so // 2
+        terms = self._coeffs(eq.rhs, [u])
+        # the stencil support must be exactly the (2R*nd + 1)-point star at t plus the centre at t-1
+        keyed = {}
+        for acc, coef in terms.items():
+            k = _space_offsets(acc, None)
+            if k is None:
+                raise _Unrecognised("non-affine wavefield access")
+            keyed[k] = coef
+        zero = (0,) * nd
+        star = {(0, zero)}
+        for d in range(nd):
+            for k in range(1, R + 1):
+                for s in (-k, k):
+                    o = [0] * nd
+                    o[d] = s
+                    star.add((0, tuple(o)))
+        if set(keyed) != star | {(-1, zero)}:
+            raise _Unrecognised("stencil support is not the isotropic star")
+        funcs, consts, syms = self._leaves(keyed.values())
+        for a in funcs:
+            k = _space_offsets(a, None)
+            if getattr(a.function, 'is_TimeFunction', False) or k is None or any(k[1]):
+                raise _Unrecognised("parameter field accessed off-centre")
+        dtsym = grid.stepping_dim.spacing
+        hs = self._spacing_values(grid)
+        w = [second_derivative_weights(so, h) for h in hs]
+        rng = np.random.default_rng(1234)
+        roles = None
+        for probe in range(3):
+            vals, leaf = self._probe_env(rng, funcs, consts, syms, grid)
+            dt = vals.get(('s', dtsym.name))
+            if dt is None:
+                raise _Unrecognised("no time spacing in the update")
+            c = {k: eval_scalar(v, leaf) for k, v in keyed.items()}
+            o1 = [0] * nd
+            o1[-1] = 1
+            cz = c[(0, tuple(o1))]
+            if cz == 0:
+                raise _Unrecognised("degenerate stencil")
+            den = w[-1][1] / cz
+            m_eff = -c[(-1, zero)] * dt * dt * den
+            d_eff = (den - m_eff / (dt * dt)) * dt
+            if roles is None:
+                roles = self._iso_roles(m_eff, d_eff, den, vals, funcs, consts)
+            # verify the full stencil against the kernel's formula
+            m_role, d_role = roles
+            m_chk = self._role_value(m_role, vals)
+            d_chk = self._role_value(d_role, vals) if d_role is not None else 0.0
+            den_chk = m_chk / (dt * dt) + d_chk / dt
+            pred = {(-1, zero): -m_chk / (dt * dt) / den_chk,
+                    (0, zero): (2 * m_chk / (dt * dt) + d_chk / dt + sum(wd[0] for wd in w)) / den_chk}
+            for d in range(nd):
+                for k in range(1, R + 1):
+                    for s in (-k, k):
+                        o = [0] * nd
+                        o[d] = s
+                        pred[(0, tuple(o))] = w[d][k] / den_chk
+            for k, v in pred.items():
+                if abs(c[k] - v) > 1e-9 * max(1.0, abs(v)):
+                    raise _Unrecognised(f"coefficient mismatch at {k}: {c[k]} vs {v}")
+        m_role, d_role = roles
+        plan = {'kind': 'iso', 'u': u, 'grid': grid, 'so': so, 'R': R, 'w': w,
+                'm_role': m_role, 'damp': d_role[1] if d_role is not None else None,
+                'dt': dtsym, 'src': None, 'rec': None, 'rec_toff': 0}
+        self._attach_sparse(plan, injs, itps, [u], funcs, consts, syms, m_role)
+        return plan
+
+    @staticmethod
+    def _role_value(role, vals):
+        kind, obj = role
+        if kind == 'vp_f':
+            v = vals[('f', id(obj))]
+            return 1.0 / (v * v)
+        if kind == 'vp_c':
+            v = vals[('c', id(obj))]
+            return 1.0 / (v * v)
+        if kind == 'm_f':
+            return vals[('f', id(obj))]
+        if kind == 'm_c':
+            return vals[('c', id(obj))]
+        if kind == 'damp_f':
+            return vals[('f', id(obj))]
+        if kind == 'one':
+            return 1.0
+        raise KeyError(kind)
+
+    def _iso_roles(self, m_eff, d_eff, den, vals, funcs, consts):
+        def close(a, b):
+            return abs(a - b) <= 1e-9 * max(1.0, abs(b))
+        m_role = None
+        for a in funcs:
+            v = vals[('f', id(a.function))]
+            if close(m_eff, 1.0 / (v * v)):
+                m_role = ('vp_f', a.function)
+            elif close(m_eff, v):
+                m_role = ('m_f', a.function)
+        for cst in consts:
+            v = vals[('c', id(cst))]
+            if close(m_eff, 1.0 / (v * v)):
+                m_role = ('vp_c', cst)
+            elif close(m_eff, v):
+                m_role = ('m_c', cst)
+        if m_role is None and close(m_eff, 1.0):
+            m_role = ('one', None)
+        if m_role is None:
+            raise _Unrecognised("cannot identify the squared-slowness parameter")
+        d_role = None
+        if abs(d_eff) > 1e-9 * abs(den):
+            for a in funcs:
+                if close(d_eff, vals[('f', id(a.function))]):
+                    d_role = ('damp_f', a.function)
+            if d_role is None:
+                raise _Unrecognised("cannot identify the damping field")
+        return m_role, d_role
+
+    def _attach_sparse(self, plan, injs, itps, fields, funcs, consts, syms, m_role):
+        grid = plan['grid']
+        dtsym = plan['dt']
+        rng = np.random.default_rng(4321)
+        if injs:
+            inj = injs[0]
+            sf = inj.sfunction
+            if not isinstance(sf, SparseTimeFunction) or sf.interpolation not in ('linear', 'sinc'):
+                raise _Unrecognised("unsupported sparse function for injection")
+            tgt = {id(f) for f in fields}
+            if {id(a.function) for a in inj.fields} != tgt:
+                raise _Unrecognised("injection targets differ from the updated fields")
+            for a, ex in zip(inj.fields, inj.exprs):
+                k = _space_offsets(a, None)
+                if k is None or k[0] != 1 or any(k[1]):
+                    raise _Unrecognised("injection must target `f.forward`")
+                ex = ex.evaluate.subs(self._subs) if self._subs else ex.evaluate
+                f2, c2, s2 = self._leaves([ex])
+                for probe in range(2):
+                    vals, leaf = self._probe_env(rng, f2, c2, s2, grid)
+                    srcv = None
+                    for acc in f2:
+                        if acc.function is sf:
+                            srcv = vals[('f', id(sf))]
+                    if srcv is None:
+                        raise _Unrecognised("injected expression does not contain the source")
+                    dt = vals.get(('s', dtsym.name))
+                    got = eval_scalar(ex, leaf)
+                    if dt is None:
+                        # `src * dt**2 / m` with a literal dt (tests/test_gpu_openacc.py:205-251)
+                        plan['inject_literal'] = True
+                        m_val = self._role_value(m_role, vals)
+                        lit = got * m_val / srcv
+                        plan['inject_dt2'] = lit
+                        continue
+                    want = srcv * dt * dt / self._role_value(m_role, vals)
+                    if abs(got - want) > 1e-9 * max(1.0, abs(want)):
+                        raise _Unrecognised("injected expression is not src*dt^2/m")
+            plan['src'] = sf
+        if itps:
+            itp = itps[0]
+            sf = itp.sfunction
+            if not isinstance(sf, SparseTimeFunction) or sf.interpolation not in ('linear', 'sinc'):
+                raise _Unrecognised("unsupported sparse function for interpolation")
+            if itp.increment:
+                raise _Unrecognised("incremental interpolation")
+            ex = itp.expr.evaluate
+            accs = [n for n in ex.preorder() if n.is_Access]
+            if {id(a.function) for a in accs} != {id(f) for f in fields} or len(accs) != len(fields):
+                raise _Unrecognised("interpolated expression is not the (sum of the) wavefield(s)")
+            toffs = set()
+            for a in accs:
+                k = _space_offsets(a, None)
+                if k is None or any(k[1]) or k[0] not in (0, 1):
+                    raise _Unrecognised("interpolated access must be f or f.forward")
+                toffs.add(k[0])
+            if len(toffs) != 1:
+                raise _Unrecognised("mixed time offsets in the interpolated expression")
+            # must be a plain sum with unit coefficients
+            vals = {id(a.function): float(i + 2) for i, a in enumerate(accs)}
+            got = eval_scalar(ex, lambda n: vals[id(n.function)])
+            if abs(got - sum(vals.values())) > 1e-12:
+                raise _Unrecognised("interpolated expression is not a plain sum")
+            plan['rec'] = sf
+            plan['rec_toff'] = toffs.pop()
+
+    # -- TTI -------------------------------------------------------------------------------------
+    def _recognise_tti(self, updates, injs, itps):
+        (u, equ), (v, eqv) = updates
+        grid = u.grid
+        if grid.dim != 3 or v.grid is not grid:
+            raise _Unrecognised("TTI fast path is 3-D only")
+        so = u.space_order
+        if so != v.space_order or so % 4 or so // 2 > 8:
+            raise _Unrecognised(f"TTI needs space_order multiple of 4 (got {so})")
+        R = so // 2
+        tu = self._coeffs(equ.rhs, [u, v])
+        tv = self._coeffs(eqv.rhs, [u, v])
+
+        def keyed(terms):
+            out = {}
+            for acc, coef in terms.items():
+                k = _space_offsets(acc, None)
+                if k is None:
+                    raise _Unrecognised("non-affine wavefield access")
+                out[('u' if acc.function is u else 'v',) + k] = coef
+            return out
+        ku, kv = keyed(tu), keyed(tv)
+        funcs, consts, syms = self._leaves(list(ku.values()) + list(kv.values()))
+        byname = {c.name: c for c in consts}
+        need = ('vp', 'epsilon', 'delta', 'theta')
+        if any(n not in byname for n in need):
+            raise _Unrecognised("TTI fast path needs scalar vp/epsilon/delta/theta[/phi] Constants")
+        damp = None
+        for a in funcs:
+            k = _space_offsets(a, None)
+            if getattr(a.function, 'is_TimeFunction', False) or k is None or any(k[1]):
+                raise _Unrecognised("parameter field accessed off-centre")
+            if damp is not None:
+                raise _Unrecognised("array-valued Thomsen parameters are not on the fast path yet")
+            damp = a.function
+        dtsym = grid.stepping_dim.spacing
+        hs = self._spacing_values(grid)
+        w2 = [second_derivative_weights(so, h) for h in hs]
+        w1 = [half_node_first_derivative_weights(so, h) for h in hs]
+        rng = np.random.default_rng(99)
+        for probe in range(2):
+            vals, leaf = self._probe_env(rng, funcs, consts, syms, grid)
+            dt = vals[('s', dtsym.name)]
+            par = {n: vals[('c', id(byname[n]))] for n in byname}
+            dval = vals[('f', id(damp))] if damp is not None else 0.0
+            pu, pv = predict_tti(w2, w1, R, par['vp'], par['epsilon'], par['delta'], par['theta'],
+                                 par.get('phi', 0.0), dval, dt)
+            for got, pred, nm in ((ku, pu, 'u'), (kv, pv, 'v')):
+                keys = set(got) | set(pred)
+                for k in keys:
+                    g = eval_scalar(got[k], leaf) if k in got else 0.0
+                    p = pred.get(k, 0.0)
+                    if abs(g - p) > 1e-8 * max(1.0, abs(p)):
+                        raise _Unrecognised(f"TTI coefficient mismatch in {nm} at {k}: {g} vs {p}")
+        plan = {'kind': 'tti', 'u': u, 'v': v, 'grid': grid, 'so': so, 'R': R, 'w2': w2, 'w1': w1,
+                'consts': byname, 'damp': damp, 'dt': dtsym, 'src': None, 'rec': None, 'rec_toff': 0,
+                'm_role': ('vp_c', byname['vp'])}
+        self._attach_sparse(plan, injs, itps, [u, v], funcs, consts, syms, plan['m_role'])
+        return plan
+
+    # ------------------------------------------------------------------------------------------
+    # introspection
+    # ------------------------------------------------------------------------------------------
+    def __str__(self):
+        if self._plan is None:
+            return (f"/* Operator `{self.name}`: NumPy interpreter ({len(self._items)} expressions)"
+                    f"{' -- not recognised: ' + self._why_not if self._why_not else ''} */")
+        p = self._plan
+        entry = 'b2_iso_forward' if p['kind'] == 'iso' else 'b2_tti_forward'
+        return (f"/* Operator `{self.name}` -> libb200stencil.so::{entry} (sm_100a)\n"
+                f"   space_order={p['so']} radius={p['R']} src={p['src'] and p['src'].name} "
+                f"rec={p['rec'] and p['rec'].name} rec_toff={p['rec_toff']} */")
+
+    ccode = property(__str__)
+
+    @property
+    def cfunction(self):
+        """The C-ABI entry point this operator calls (devito/operator/operator.py:857-869)."""
+        if self._plan is None:
+            raise InvalidOperator("interpreted operators have no C entry point")
+        L = L_.load_library()
+        return L.b2_iso_forward if self._plan['kind'] == 'iso' else L.b2_tti_forward
+
+    @property
+    def parameters(self):
+        p = self._plan
+        if p is None:
+            return tuple(self._interp.functions.values())
+        out = [p['u']] + ([p['v']] if p['kind'] == 'tti' else [])
+        if p.get('damp') is not None:
+            out.append(p['damp'])
+        if p['kind'] == 'iso':
+            out.append(p['m_role'][1])
+        else:
+            out.extend(p['consts'].values())
+        out += [s for s in (p['src'], p['rec']) if s is not None]
+        return tuple(o for o in out if o is not None)
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    def __call__(self, **kwargs):
+        return self.apply(**kwargs)
+
+    def apply(self, **kwargs):
+        if self._plan is None:
+            return self._apply_interp(**kwargs)
+        if self._plan['kind'] == 'iso':
+            return self._apply_iso(**kwargs)
+        return self._apply_tti(**kwargs)
+
+    def arguments(self, **kwargs):
+        if self._plan is None:
+            return self._interp_args(dict(kwargs))
+        return self._prepare(dict(kwargs))[0]
+
+    _prepare_arguments = arguments
+
+    # -- generic -----------------------------------------------------------------------------------
+    _ignored_kwargs = ('autotune', 'nthreads', 'nthreads_nonaffine', 'deviceid', 'devicerm',
+                       'resident', 'kernel', 'errctl')
+
+    def _interp_args(self, kwargs):
+        it = self._interp
+        fns = it.functions
+        scalars = {}
+        bounds = {}
+        grid = next((f.grid for f in fns.values() if f.grid is not None), None)
+        if grid is not None:
+            for sp, v in grid.spacing_map.items():
+                scalars[sp.name] = float(kwargs.pop(sp.name, v))
+            for d, n in zip(grid.dimensions, grid.shape):
+                lo = kwargs.pop(d.min_name, 0)
+                hi = kwargs.pop(d.max_name, n - 1)
+                bounds[d.name] = (lo, hi)
+                scalars[d.min_name] = lo
+                scalars[d.max_name] = hi
+                scalars[f'{d.name}_size'] = n
+        if 'dt' in kwargs:
+            scalars['dt'] = float(kwargs.pop('dt'))
+        # Constants by name
+        for kind, _, obj, lhs, rhs in it.items:
+            exprs = [rhs] if kind == 'eq' else (list(obj.exprs) if kind == 'inject' else [obj.expr])
+            for ex in exprs:
+                for n in ex.preorder():
+                    if n.is_Constant and n.name in kwargs:
+                        scalars[n.name] = float(kwargs.pop(n.name))
+        # time range
+        tlo, thi = it.time_shifts()
+        sized = [f for f in fns.values() if (getattr(f, 'is_SparseTimeFunction', False))
+                 or (getattr(f, 'is_TimeFunction', False) and not f.is_buffered)]
+        time_m = kwargs.pop('time_m', None)
+        time_M = kwargs.pop('time_M', kwargs.pop('time', None))
+        if it.has_time:
+            if time_m is None:
+                time_m = -min(tlo, 0)
+            if time_M is None:
+                if not sized:
+                    raise InvalidArgument("No value found for parameter time_M")
+                nt = min(f.nt if getattr(f, 'is_SparseTimeFunction', False) else f.time_size for f in sized)
+                time_M = nt - 1 - max(thi, 0)
+        else:
+            time_m, time_M = 0, 0
+        for k in list(kwargs):
+            if k in self._ignored_kwargs or k in fns:
+                kwargs.pop(k)
+        if kwargs and not configuration['ignore-unknowns']:
+            raise InvalidArgument(f"Unrecognized argument(s) {sorted(kwargs)} in kwargs")
+        return {'time_m': time_m, 'time_M': time_M, 'scalars': scalars, 'bounds': bounds}
+
+    def _apply_interp(self, **kwargs):
+        args = self._interp_args(dict(kwargs))
+        t0 = _time.perf_counter()
+        self._interp.run(args['time_m'], args['time_M'], args['scalars'], args['bounds'])
+        el = _time.perf_counter() - t0
+        summary = PerformanceSummary()
+        summary['section0'] = PerfEntry(el)
+        summary.globals['fdlike'] = PerfEntry(el)
+        return summary
+
+    # -- CUDA path ---------------------------------------------------------------------------------
+    def _resolve(self, kwargs, obj):
+        """User override by name (object of the same kind), else the default object."""
+        if obj is None:
+            return None
+        v = kwargs.pop(obj.name, None)
+        return obj if v is None else v
+
+    def _prepare(self, kwargs):
+        p = self._plan
+        grid = p['grid']
+        nd = grid.dim
+        args = OrderedDict()
+        hold = []          # keep ctypes/ndarray objects alive during the call
+        u = self._resolve(kwargs, p['u'])
+        fields = [u]
+        if p['kind'] == 'tti':
+            v = self._resolve(kwargs, p['v'])
+            fields.append(v)
+        for f in fields:
+            if not isinstance(f, TimeFunction) or f.space_order != p['so'] or f.grid.shape != grid.shape:
+                raise InvalidArgument(f"incompatible override for a wavefield")
+        args['fields'] = fields
+        damp = self._resolve(kwargs, p['damp']) if p.get('damp') is not None else None
+        if damp is not None and not isinstance(damp, Function):
+            raise InvalidArgument("`damp` override must be a Function")
+        args['damp'] = damp
+        # parameters
+        if p['kind'] == 'iso':
+            kind, obj = p['m_role']
+            args['param_kind'] = B2_PARAM_SCALAR
+            args['param'] = None
+            args['vp'] = 1.0
+            if kind == 'one':
+                pass
+            else:
+                val = kwargs.pop(obj.name, obj)
+                if isinstance(val, Function):
+                    args['param'] = val
+                    args['param_kind'] = B2_PARAM_VP if kind.startswith('vp') else B2_PARAM_M
+                else:
+                    sval = float(val.data if isinstance(val, Constant) else val)
+                    args['vp'] = sval if kind.startswith('vp') else 1.0 / np.sqrt(sval)
+        else:
+            for n, c in p['consts'].items():
+                val = kwargs.pop(n, c)
+                if isinstance(val, Function):
+                    raise InvalidArgument(f"array-valued `{n}` needs an Operator built with a Function")
+                args[n] = float(val.data if isinstance(val, Constant) else val)
+            args.setdefault('phi', 0.0)
+        # spacing / dt
+        dt = kwargs.pop('dt', None)
+        if dt is None:
+            raise InvalidArgument("No value found for parameter dt")
+        args['dt'] = float(np.float32(dt))
+        for sp in grid.spacing_symbols:
+            if sp.name in kwargs:
+                hv = kwargs.pop(sp.name)
+                cur = self._spacing_values(grid)[grid.spacing_symbols.index(sp)]
+                if abs(float(hv) - cur) > 1e-6 * abs(cur):
+                    raise InvalidArgument(f"runtime override of {sp.name} is not supported by the "
+                                          "pre-built kernels; rebuild the Operator")
+        # bounds
+        lo, hi = [], []
+        for d, n in zip(grid.dimensions, grid.shape):
+            a = kwargs.pop(d.min_name, 0)
+            b = kwargs.pop(d.max_name, n - 1)
+            if a < 0 or b > n - 1:
+                raise InvalidArgument(f"OOB detected due to {d.min_name}={a}, {d.max_name}={b}")
+            lo.append(int(a))
+            hi.append(int(b))
+        args['lo'], args['hi'] = lo, hi
+        # sparse
+        src = self._resolve(kwargs, p['src'])
+        rec = self._resolve(kwargs, p['rec'])
+        args['src'], args['rec'] = src, rec
+        # time range (devito/types/dimension.py:279-331)
+        sized = [s for s in (src, rec) if s is not None]
+        sized += [f for f in fields if not f.is_buffered]
+        time_m = kwargs.pop('time_m', None)
+        time_M = kwargs.pop('time_M', kwargs.pop('time', None))
+        if time_m is None:
+            time_m = 1           # u[t-1] is read: lower offset -1
+        if time_M is None:
+            if not sized:
+                raise InvalidArgument("No value found for parameter time_M")
+            nt = min(s.nt if getattr(s, 'is_SparseTimeFunction', False) else s.time_size for s in sized)
+            time_M = nt - 2      # u[t+1] is written: upper offset +1
+        for s in sized:
+            n = s.nt if getattr(s, 'is_SparseTimeFunction', False) else s.time_size - 1
+            if time_M >= n or time_m < 0:
+                raise InvalidArgument(f"OOB detected due to time_M={time_M}")
+        args['time_m'], args['time_M'] = int(time_m), int(time_M)
+        args['resident'] = bool(kwargs.pop('resident', True)) and not bool(kwargs.pop('devicerm', 0))
+        args['kernel'] = int(kwargs.pop('kernel', 0))
+        args['errctl'] = int(kwargs.pop('errctl', 1 if configuration.get('errctl') == 'max' else 0))
+        args['deviceid'] = kwargs.pop('deviceid', None)
+        for k in ('autotune', 'nthreads', 'nthreads_nonaffine'):
+            kwargs.pop(k, None)
+        if kwargs and not configuration['ignore-unknowns']:
+            raise InvalidArgument(f"Unrecognized argument(s) {sorted(kwargs)} in kwargs")
+        return args, hold
+
+    def _device(self, args):
+        import torch
+        dev = args.get('deviceid')
+        if dev is None or dev < 0:
+            dev = configuration['deviceid']
+        if dev is None or dev < 0:
+            dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        return int(dev)
+
+    @staticmethod
+    def _as_layout(fn, so, like):
+        """Host array of a parameter Function in the allocated layout of the wavefield
+        (halo `so`); parameters defined with a different space_order are re-padded."""
+        if fn.space_order == so:
+            return None
+        src = fn.data_ro_with_halo
+        h = fn.space_order
+        dom = src[tuple(slice(h, src.shape[i] - h) for i in range(src.ndim))]
+        if h >= so:
+            d = h - so
+            return np.ascontiguousarray(src[tuple(slice(d, src.shape[i] - d) for i in range(src.ndim))])
+        out = np.pad(dom, so, mode='edge')
+        inner = tuple(slice(so - h, out.shape[i] - (so - h)) for i in range(out.ndim))
+        out[inner] = src
+        return np.ascontiguousarray(out)
+
+    def _field_obj(self, fn, dev, resident, hold, so=None, written=False):
+        """b2_dataobj for a dense function: resident (dmap set) or host-staged."""
+        import torch
+        if so is not None and fn.space_order != so:
+            host = self._as_layout(fn, so, None)
+            hold.append(host)
+            halo = tuple((0, 0) if d.is_Time else (so, so) for d in fn.dimensions)
+            if resident:
+                t = torch.from_numpy(host).to(f'cuda:{dev}')
+                hold.append(t)
+                ob = L_.make_dataobj(host=host, dev_ptr=t.data_ptr(), halo=halo)
+            else:
+                ob = L_.make_dataobj(host=host, halo=halo)
+            hold.append(ob)
+            return ob
+        st = fn.storage
+        if resident:
+            t = st.to_device(torch.device('cuda', dev))
+            ob = L_.make_dataobj(dev_ptr=t.data_ptr(), shape=st.shape, halo=fn.halo)
+            if written:
+                st.mark_device_written()
+        else:
+            host = st.host if written else st.host_ro
+            ob = L_.make_dataobj(host=host, halo=fn.halo)
+        hold.append(ob)
+        return ob
+
+    def _sparse_obj(self, sf, grid, hold, written=False):
+        if sf is None:
+            return None
+        gp, ws = sf.tabulate()
+        # positions relative to this rank's sub-domain (x-slab decomposition)
+        off = grid.distributor.offsets
+        if any(off):
+            gp = gp - np.asarray(off, dtype=np.int32)[None, :]
+            gp = np.ascontiguousarray(gp.astype(np.int32))
+        host = sf.storage.host if written else sf.storage.host_ro
+        data = L_.make_dataobj(host=host)
+        gpo = L_.make_dataobj(host=gp)
+        wos = [L_.make_dataobj(host=w) for w in ws]
+        s = L_.Sparse()
+        s.data = data.ptr
+        s.gp = gpo.ptr
+        for i, wo in enumerate(wos):
+            s.w[i] = wo.ptr
+        s.p_m, s.p_M = 0, sf.npoint - 1
+        s.r = sf.r
+        hold.extend([gp, ws, data, gpo, wos, s])
+        return s
+
+    def _finish(self, rc, L, timers, args, nfields_pts, t_wall):
+        if rc != 0:
+            msg = L.b2_last_error().decode()
+            if rc == 100:
+                raise ExecutionError(f"Operator `{self.name}`: NaN/Inf detected ({msg})")
+            raise ExecutionError(f"Operator `{self.name}` failed with code {rc}: {msg}")
+        nsteps = args['time_M'] - args['time_m'] + 1
+        pts = float(np.prod([h - l + 1 for l, h in zip(args['lo'], args['hi'])])) * nsteps
+        summary = PerformanceSummary()
+        tot = timers.section0 + timers.section1 + timers.section2
+        for nm in ('section0', 'section1', 'section2'):
+            t = getattr(timers, nm)
+            summary[nm] = PerfEntry(t, gpointss=(pts / t / 1e9 if t > 0 and nm == 'section0' else None))
+        summary.globals['fdlike'] = PerfEntry(t_wall, gpointss=pts / t_wall / 1e9 if t_wall > 0 else None)
+        summary.globals['fdlike-nosetup'] = PerfEntry(tot, gpointss=pts / tot / 1e9 if tot > 0 else None)
+        perf(f"Operator `{self.name}` ran in {t_wall:.4f} s [{pts / max(tot, 1e-12) / 1e9:.2f} GPts/s on device]")
+        self._profiler_last = summary
+        return summary
+
+    def _w_arrays(self, wlists, hold):
+        arr = (ctypes.POINTER(ctypes.c_float) * 3)()
+        for i, w in enumerate(wlists):
+            a = np.ascontiguousarray(np.asarray(w, dtype=np.float32))
+            hold.append(a)
+            arr[i] = a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        return arr
+
+    def _apply_iso(self, **kwargs):
+        L = L_.lib()
+        args, hold = self._prepare(dict(kwargs))
+        p = self._plan
+        grid = p['grid']
+        nd = grid.dim
+        dev = self._device(args)
+        res = args['resident']
+        a = L_.IsoArgs()
+        a.ndim = nd
+        a.space_order = p['so']
+        a.radius = p['R']
+        a.w = self._w_arrays(p['w'], hold)
+        u = args['fields'][0]
+        a.u = self._field_obj(u, dev, res, hold, written=True).ptr
+        a.damp = self._field_obj(args['damp'], dev, res, hold, so=p['so']).ptr if args['damp'] is not None else None
+        a.param_kind = args['param_kind']
+        a.param = self._field_obj(args['param'], dev, res, hold, so=p['so']).ptr if args['param'] is not None else None
+        a.vp = args['vp']
+        a.dt = args['dt']
+        lo, hi = args['lo'], args['hi']
+        a.x_m, a.x_M, a.y_m, a.y_M = lo[0], hi[0], lo[1], hi[1]
+        if nd == 3:
+            a.z_m, a.z_M = lo[2], hi[2]
+        a.time_m, a.time_M = args['time_m'], args['time_M']
+        s = self._sparse_obj(args['src'], grid, hold)
+        r = self._sparse_obj(args['rec'], grid, hold, written=True)
+        a.src = ctypes.pointer(s) if s is not None else None
+        a.rec = ctypes.pointer(r) if r is not None else None
+        a.rec_toff = p['rec_toff']
+        a.errctl = args['errctl']
+        a.deviceid = dev
+        a.kernel = args['kernel']
+        a.halo = distributed.halo_context(dev) if grid.distributor.is_parallel else None
+        timers = L_.Profiler()
+        a.timers = ctypes.pointer(timers)
+        if p.get('inject_literal'):
+            # injection used a literal dt**2 (not the `dt` symbol): it must agree with runtime dt
+            if abs(p['inject_dt2'] - a.dt * a.dt) > 1e-5 * p['inject_dt2']:
+                raise InvalidArgument("literal dt in the injected expression differs from runtime dt")
+        t0 = _time.perf_counter()
+        rc = L.b2_iso_forward(ctypes.byref(a))
+        t_wall = _time.perf_counter() - t0
+        return self._finish(rc, L, timers, args, 1, t_wall)
+
+    def _apply_tti(self, **kwargs):
+        L = L_.lib()
+        args, hold = self._prepare(dict(kwargs))
+        p = self._plan
+        grid = p['grid']
+        dev = self._device(args)
+        res = args['resident']
+        a = L_.TtiArgs()
+        a.space_order = p['so']
+        a.radius = p['R']
+        a.w2 = self._w_arrays(p['w2'], hold)
+        a.w1 = self._w_arrays(p['w1'], hold)
+        u, v = args['fields']
+        a.u = self._field_obj(u, dev, res, hold, written=True).ptr
+        a.v = self._field_obj(v, dev, res, hold, written=True).ptr
+        a.damp = self._field_obj(args['damp'], dev, res, hold, so=p['so']).ptr if args['damp'] is not None else None
+        a.vp, a.epsilon, a.delta = args['vp'], args['epsilon'], args['delta']
+        a.theta, a.phi = args['theta'], args['phi']
+        a.dt = args['dt']
+        lo, hi = args['lo'], args['hi']
+        a.x_m, a.x_M, a.y_m, a.y_M, a.z_m, a.z_M = lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]
+        a.time_m, a.time_M = args['time_m'], args['time_M']
+        s = self._sparse_obj(args['src'], grid, hold)
+        r = self._sparse_obj(args['rec'], grid, hold, written=True)
+        a.src = ctypes.pointer(s) if s is not None else None
+        a.rec = ctypes.pointer(r) if r is not None else None
+        a.rec_toff = p['rec_toff']
+        a.errctl = args['errctl']
+        a.deviceid = dev
+        a.kernel = args['kernel']
+        a.halo = distributed.halo_context(dev) if grid.distributor.is_parallel else None
+        timers = L_.Profiler()
+        a.timers = ctypes.pointer(timers)
+        t0 = _time.perf_counter()
+        rc = L.b2_tti_forward(ctypes.byref(a))
+        t_wall = _time.perf_counter() - t0
+        return self._finish(rc, L, timers, args, 2, t_wall)
+
+
+# ---------------------------------------------------------------------------------------------
+# the stencil the TTI kernels implement, as linear coefficients (float64) — used only by the
+# recogniser to confirm that a user's equations are this scheme.
+# ---------------------------------------------------------------------------------------------
+def predict_tti(w2, w1, R, vp, eps, delta, theta, phi, damp, dt):
+    h = R // 2
+    st, ct, sp, cp = np.sin(theta), np.cos(theta), np.sin(phi), np.cos(phi)
+    c = [st * cp, st * sp, ct]
+    e2 = 1 + 2 * eps
+    sd = np.sqrt(1 + 2 * delta)
+
+    def unit(d, o):
+        v = [0, 0, 0]
+        v[d] = o
+        return tuple(v)
+
+    def add(dst, key, val):
+        dst[key] = dst.get(key, 0.0) + val
+
+    # Gz as offset -> coefficient
+    gz = {}
+    for d in range(3):
+        for j in range(R):
+            add(gz, unit(d, j - h + 1), c[d] * w1[d][j])
+    # Gzz = sum_d D-_d (c_d * Gz)
+    gzz = {}
+    for d in range(3):
+        for j in range(R):
+            o = unit(d, j - h)
+            for k, val in gz.items():
+                add(gzz, tuple(a + b for a, b in zip(o, k)), c[d] * w1[d][j] * val)
+    lap = {}
+    add(lap, (0, 0, 0), sum(w[0] for w in w2))
+    for d in range(3):
+        for k in range(1, R + 1):
+            add(lap, unit(d, k), w2[d][k])
+            add(lap, unit(d, -k), w2[d][k])
+    m_dt2 = 1.0 / (vp * vp) / (dt * dt)
+    den = m_dt2 + damp / dt
+    pu, pv = {}, {}
+    for k, val in lap.items():
+        add(pu, ('u', 0) + (k,), e2 * val / den)
+        add(pv, ('u', 0) + (k,), sd * val / den)
+    for k, val in gzz.items():
+        add(pu, ('u', 0) + (k,), -e2 * val / den)
+        add(pu, ('v', 0) + (k,), sd * val / den)
+        add(pv, ('u', 0) + (k,), -sd * val / den)
+        add(pv, ('v', 0) + (k,), val / den)
+    z = (0, 0, 0)
+    add(pu, ('u', 0, z), (2 * m_dt2 + damp / dt) / den)
+    add(pu, ('u', -1, z), -m_dt2 / den)
+    add(pv, ('v', 0, z), (2 * m_dt2 + damp / dt) / den)
+    add(pv, ('v', -1, z), -m_dt2 / den)
+    # drop exact zeros produced by cancellation
+    pu = {k: v for k, v in pu.items() if abs(v) > 1e-14}
+    pv = {k: v for k, v in pv.items() if abs(v) > 1e-14}
+    return pu, pv

@@ -1,0 +1,60 @@
+"""Isotropic acoustic forward modelling (mirror of examples/seismic/acoustic/operators.py:50-150
+and wavesolver.py:11-120, forward operator only — adjoint/gradient are SURVEY §8f)."""
+from .. import Eq, Operator, TimeFunction, solve
+from ..tools import memoized_meth
+
+__all__ = ['iso_stencil', 'ForwardOperator', 'AcousticWaveSolver']
+
+
+def iso_stencil(field, model, kernel='OT2', **kwargs):
+    """u.dt2 * m - laplace(u) + damp * u.dt = 0 solved for u.forward (operators.py:71-107)."""
+    if kernel != 'OT2':
+        raise NotImplementedError("only the OT2 kernel is on this backend's path")
+    unext = field.forward
+    eq_time = solve(model.m * field.dt2 - field.laplace - kwargs.get('q', 0) + model.damp * field.dt,
+                    unext)
+    return [Eq(unext, eq_time, subdomain=model.grid.subdomains['physdomain'])]
+
+
+def ForwardOperator(model, geometry, space_order=4, save=False, kernel='OT2', **kwargs):
+    """operators.py:113-150"""
+    m = model.m
+    u = TimeFunction(name='u', grid=model.grid, save=geometry.nt if save else None, time_order=2,
+                     space_order=space_order)
+    src, rec = geometry.src, geometry.rec
+    s = model.grid.stepping_dim.spacing
+    eqn = iso_stencil(u, model, kernel)
+    src_term = src.inject(field=u.forward, expr=src * s ** 2 / m)
+    rec_term = rec.interpolate(expr=u)
+    return Operator(eqn + src_term + rec_term, subs=model.spacing_map, name='Forward', **kwargs)
+
+
+class AcousticWaveSolver:
+    """wavesolver.py:11-120 (`forward` only)."""
+
+    def __init__(self, model, geometry, kernel='OT2', space_order=4, **kwargs):
+        self.model = model
+        self.model._initialize_bcs(bcs="damp")
+        self.geometry = geometry
+        self.space_order = space_order
+        self.kernel = kernel
+        self._kwargs = kwargs
+
+    @property
+    def dt(self):
+        return self.model.critical_dt
+
+    @memoized_meth
+    def op_fwd(self, save=None):
+        return ForwardOperator(self.model, save=save, geometry=self.geometry, kernel=self.kernel,
+                               space_order=self.space_order, **self._kwargs)
+
+    def forward(self, src=None, rec=None, u=None, model=None, save=None, **kwargs):
+        src = src or self.geometry.src
+        rec = rec or self.geometry.rec
+        u = u or TimeFunction(name='u', grid=self.model.grid, save=self.geometry.nt if save else None,
+                              time_order=2, space_order=self.space_order)
+        model = model or self.model
+        kwargs.update(model.physical_params(**kwargs))
+        summary = self.op_fwd(save).apply(src=src, rec=rec, u=u, dt=kwargs.pop('dt', self.dt), **kwargs)
+        return rec, u, summary

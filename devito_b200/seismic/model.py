@@ -1,0 +1,273 @@
+"""Physical model for seismic wave propagation (host-side mirror of the reference's
+`examples/seismic/model.py`, written against this package's DSL).
+
+Numerical definitions that matter for parity with the reference:
+  * absorbing-layer profile `damp` — examples/seismic/model.py:25-63 (`initialize_damp`);
+  * CFL time step — model.py:353-382 (`_cfl_coeff`, `critical_dt`: weights over +-space_order,
+    value rounded through "%.3e" to the model dtype);
+  * squared slowness m = 1/vp^2 — model.py:407-411;
+  * parameters given as arrays are edge-padded into the absorbing layers — `_gen_phys_param`
+    (model.py:180-191) via `initialize_function`.
+"""
+import numpy as np
+from sympy import finite_diff_weights
+
+from .. import (Grid, SubDomain, Function, Constant, Eq, Inc, Operator, SubDimension, Abs, sin,
+                warning, mmax, mmin, initialize_function, gaussian_smooth)
+
+__all__ = ['SeismicModel', 'Model', 'demo_model', 'initialize_damp']
+
+
+def initialize_damp(damp, padsizes, spacing, abc_type="damp", fs=False):
+    """Fill `damp` with the absorbing-layer profile. Written with the DSL (SubDimensions + Inc)
+    exactly like the reference does, so that it exercises the generic operator path."""
+    eqs = [Eq(damp, 1.0 if abc_type == "mask" else 0.0)]
+    for (nbl, nbr), d in zip(padsizes, damp.dimensions):
+        if not fs or d is not damp.dimensions[-1]:
+            coeff = 1.5 * np.log(1.0 / 0.001) / nbl
+            left = SubDimension.left(name=f'abc_{d.name}_l', parent=d, thickness=nbl)
+            pos = Abs((nbl - (left - d.symbolic_min) + 1) / float(nbl))
+            val = coeff * (pos - sin(2 * np.pi * pos) / (2 * np.pi))
+            val = -val if abc_type == "mask" else val
+            eqs.append(Inc(damp.subs({d: left}), val / d.spacing))
+        coeff = 1.5 * np.log(1.0 / 0.001) / nbr
+        right = SubDimension.right(name=f'abc_{d.name}_r', parent=d, thickness=nbr)
+        pos = Abs((nbr - (d.symbolic_max - right) + 1) / float(nbr))
+        val = coeff * (pos - sin(2 * np.pi * pos) / (2 * np.pi))
+        val = -val if abc_type == "mask" else val
+        eqs.append(Inc(damp.subs({d: right}), val / d.spacing))
+    Operator(eqs, name='initdamp')()
+
+
+class PhysicalDomain(SubDomain):
+    name = 'physdomain'
+
+    def __init__(self, so, fs=False):
+        super().__init__()
+        self.so, self.fs = so, fs
+
+    def define(self, dimensions):
+        out = {d: d for d in dimensions}
+        if self.fs:
+            out[dimensions[-1]] = ('middle', self.so, 0)
+        return out
+
+
+class SeismicModel:
+    """Velocity model + absorbing layers on a `Grid` that includes `nbl` points per side."""
+    _known_parameters = ['vp', 'damp', 'vs', 'b', 'epsilon', 'delta', 'theta', 'phi', 'qp', 'qs',
+                         'lam', 'mu']
+
+    def __init__(self, origin, spacing, shape, space_order, vp, nbl=20, fs=False,
+                 dtype=np.float32, subdomains=(), bcs="mask", grid=None, topology=None, **kwargs):
+        self.shape = tuple(shape)
+        self.space_order = space_order
+        self.nbl = int(nbl)
+        self.origin = tuple(dtype(o) for o in origin)
+        self.fs = fs
+        if fs:
+            raise NotImplementedError("free-surface models are outside this backend's scope (SURVEY §8f)")
+        origin_pml = [dtype(o - s * nbl) for o, s in zip(origin, spacing)]
+        shape_pml = np.array(shape) + 2 * self.nbl
+        subdomains = tuple(subdomains) + (PhysicalDomain(space_order, fs=fs),)
+        if grid is None:
+            extent = tuple(np.array(spacing) * (shape_pml - 1))
+            self.grid = Grid(extent=extent, shape=tuple(int(s) for s in shape_pml), origin=origin_pml,
+                             dtype=dtype, subdomains=subdomains, topology=topology)
+        else:
+            self.grid = grid
+        self._physical_parameters = set()
+        self.damp = None
+        self._initialize_bcs(bcs=bcs)
+        self._initialize_physics(vp, space_order, **kwargs)
+        self._dt = kwargs.get('dt')
+        self._dt_scale = 1
+
+    # -- boundary conditions ----------------------------------------------------------------------
+    def _initialize_bcs(self, bcs="damp"):
+        if self.nbl == 0:
+            self.damp = 1 if bcs == "mask" else 0
+            return
+        init = self.damp is None
+        if init:
+            self.damp = Function(name="damp", grid=self.grid, space_order=self.space_order)
+        if callable(bcs):
+            bcs(self.damp, self.nbl)
+        else:
+            re_init = ((bcs == "mask" and mmin(self.damp) == 0) or
+                       (bcs == "damp" and mmax(self.damp) == 1))
+            if init or re_init:
+                if re_init and not init:
+                    other = "damp" if bcs == "mask" else "mask"
+                    warning(f"Re-initializing damp profile from {other} to {bcs}")
+                self._fill_damp(bcs)
+        self._physical_parameters.update(['damp'])
+
+    def _fill_damp(self, bcs):
+        dist = self.grid.distributor
+        if dist.is_parallel:
+            # the profile depends on global indices: evaluate on the global shape, keep our slab
+            g = Grid(shape=self.grid.shape_global, extent=self.grid.extent, origin=self.grid.origin,
+                     dtype=self.grid.dtype, topology=None, _serial=True) if False else None
+            prof = damp_profile(self.grid.shape_global, self.padsizes, self.grid.spacing, bcs)
+            lo, hi = dist.x_range
+            self.damp.data[:] = prof[lo:hi]
+        else:
+            initialize_damp(self.damp, self.padsizes, self.spacing, abc_type=bcs, fs=self.fs)
+
+    @property
+    def padsizes(self):
+        return [(self.nbl, self.nbl) for _ in range(self.dim)]
+
+    # -- physics ----------------------------------------------------------------------------------
+    def _gen_phys_param(self, field, name, space_order, default_value=0, **kwargs):
+        if field is None:
+            return default_value
+        if isinstance(field, np.ndarray):
+            function = Function(name=name, grid=self.grid, space_order=space_order)
+            initialize_function(function, field, self.padsizes)
+        else:
+            function = Constant(name=name, value=field, dtype=self.grid.dtype)
+        self._physical_parameters.update([name])
+        return function
+
+    def _initialize_physics(self, vp, space_order, **kwargs):
+        if 'vs' in kwargs:
+            raise NotImplementedError("elastic models are outside this backend's scope (SURVEY §8f)")
+        self.vp = self._gen_phys_param(vp, 'vp', space_order)
+        for name in self._known_parameters:
+            if kwargs.get(name) is not None:
+                setattr(self, name, self._gen_phys_param(kwargs.get(name), name, space_order))
+
+    def physical_params(self, **kwargs):
+        known = [getattr(self, i) for i in self.physical_parameters]
+        return {i.name: kwargs.get(i.name, i) or i for i in known}
+
+    @property
+    def physical_parameters(self):
+        return tuple(self._physical_parameters)
+
+    @property
+    def dim(self): return self.grid.dim
+    @property
+    def spacing(self): return self.grid.spacing
+    @property
+    def space_dimensions(self): return self.grid.dimensions
+    @property
+    def spacing_map(self): return self.grid.spacing_map
+    @property
+    def dtype(self): return self.grid.dtype
+    @property
+    def domain_size(self):
+        return tuple((d - 1) * s for d, s in zip(self.shape, self.spacing))
+
+    @property
+    def m(self):
+        """Squared slowness 1/vp^2 (model.py:407-411)."""
+        return 1 / (self.vp * self.vp)
+
+    # -- time step ----------------------------------------------------------------------------------
+    @property
+    def _max_vp(self):
+        return mmax(self.vp)
+
+    @property
+    def _thomsen_scale(self):
+        if 'epsilon' in self._physical_parameters:
+            return np.sqrt(1 + 2 * mmax(self.epsilon))
+        return 1
+
+    @property
+    def dt_scale(self): return self._dt_scale
+
+    @dt_scale.setter
+    def dt_scale(self, val): self._dt_scale = val
+
+    @property
+    def _cfl_coeff(self):
+        coeffs = finite_diff_weights(2, range(-self.space_order, self.space_order + 1), 0)[-1][-1]
+        return np.sqrt(4.0 / float(self.grid.dim * sum(np.abs(np.array(coeffs, dtype=np.float64)))))
+
+    @property
+    def critical_dt(self):
+        dt = self._cfl_coeff * np.min(self.spacing) / (self._thomsen_scale * self._max_vp)
+        dt = self.dtype("%.3e" % (self.dt_scale * dt))
+        return self._dt if self._dt else dt
+
+    def update(self, name, value):
+        try:
+            param = getattr(self, name)
+        except AttributeError:
+            setattr(self, name, self._gen_phys_param(value, name, self.space_order))
+            return
+        if isinstance(value, np.ndarray):
+            if value.shape == param.shape:
+                param.data[:] = value[:]
+            elif value.shape == self.shape:
+                initialize_function(param, value, self.nbl)
+            else:
+                raise ValueError(f"Incorrect input size {value.shape}")
+        else:
+            param.data = value
+
+    def smooth(self, physical_parameters, sigma=5.0):
+        params = self.physical_params()
+        for i in physical_parameters:
+            gaussian_smooth(params[i], sigma=sigma)
+
+
+Model = SeismicModel
+
+
+def damp_profile(shape, padsizes, spacing, abc_type="damp"):
+    """NumPy evaluation of the same profile as `initialize_damp` (used for slab-decomposed grids,
+    where the profile must follow global indices)."""
+    out = np.full(shape, 1.0 if abc_type == "mask" else 0.0, dtype=np.float64)
+    for ax, ((nbl, nbr), h) in enumerate(zip(padsizes, spacing)):
+        n = shape[ax]
+        prof = np.zeros(n)
+        i = np.arange(nbl)
+        pos = np.abs((nbl - i + 1) / float(nbl))
+        prof[:nbl] += 1.5 * np.log(1000.0) / nbl * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / float(h)
+        j = np.arange(n - nbr, n)
+        pos = np.abs((nbr - (n - 1 - j) + 1) / float(nbr))
+        prof[n - nbr:] += 1.5 * np.log(1000.0) / nbr * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / float(h)
+        sh = [1] * len(shape)
+        sh[ax] = n
+        out = out + (-prof if abc_type == "mask" else prof).reshape(sh)
+    return out.astype(np.float32)
+
+
+def demo_model(preset, **kwargs):
+    """Preset models with the reference's names and defaults
+    (examples/seismic/preset_models.py:20-238): `constant-isotropic`, `constant-tti`,
+    `layers-isotropic`, `layers-tti`."""
+    space_order = kwargs.pop('space_order', 2)
+    shape = kwargs.pop('shape', (101, 101))
+    spacing = kwargs.pop('spacing', tuple(10. for _ in shape))
+    origin = kwargs.pop('origin', tuple(0. for _ in shape))
+    nbl = kwargs.pop('nbl', 10)
+    dtype = kwargs.pop('dtype', np.float32)
+    vp = kwargs.pop('vp', 1.5)
+    nlayers = kwargs.pop('nlayers', 3)
+    kwargs.pop('fs', None)
+    p = preset.lower()
+    if p == 'constant-isotropic':
+        return SeismicModel(space_order=space_order, vp=vp, origin=origin, shape=shape, dtype=dtype,
+                            spacing=spacing, nbl=nbl, **kwargs)
+    if p in ('constant-tti', 'constant-tti-noazimuth'):
+        phi = .35 if (len(shape) > 2 and p != 'constant-tti-noazimuth') else None
+        return SeismicModel(space_order=space_order, vp=vp, origin=origin, shape=shape, dtype=dtype,
+                            spacing=spacing, nbl=nbl, epsilon=.3, delta=.2, theta=.7, phi=phi,
+                            bcs="damp", **kwargs)
+    if p == 'layers-isotropic':
+        vp_top = kwargs.pop('vp_top', 1.5)
+        vp_bottom = kwargs.pop('vp_bottom', 3.5)
+        v = np.empty(shape, dtype=dtype)
+        v[:] = vp_top
+        vp_i = np.linspace(vp_top, vp_bottom, nlayers)
+        for i in range(1, nlayers):
+            v[..., i * int(shape[-1] / nlayers):] = vp_i[i]
+        return SeismicModel(space_order=space_order, vp=v, origin=origin, shape=shape, dtype=dtype,
+                            spacing=spacing, nbl=nbl, bcs="damp", **kwargs)
+    raise ValueError(f"unknown or unsupported preset {preset!r}")

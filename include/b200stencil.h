@@ -1,0 +1,179 @@
+/*
+ * b200stencil.h — C ABI of the B200-native wave-propagation backend (libb200stencil.so).
+ *
+ * This is the drop-in boundary for the ONE hot path named in BASELINE.json: the time loop
+ * that the reference's `Operator` emits for acoustic / TTI wave propagation.  In the
+ * reference that loop is a JIT-generated C function
+ *
+ *     int Forward(struct dataobj *damp_vec, ..., struct dataobj *u_vec, const float vp,
+ *                 const int x_M, const int x_m, ..., const int time_M, const int time_m,
+ *                 ..., struct profiler *timers)
+ *
+ * looked up with `getattr(lib, name)` and called once per `Operator.apply`
+ * (devito/operator/operator.py:857-869 `cfunction`, :1032 the FFI crossing; printed
+ * samples of the generated code: examples/seismic/tutorials/08_snapshotting.ipynb:461-505).
+ * The entry points below take exactly the same kinds of things — `struct dataobj`
+ * descriptors, scalar spacings/dt, inclusive iteration bounds, a `struct profiler` — but
+ * are pre-built for sm_100a instead of generated.  Only plain pointers, ints and floats
+ * cross the boundary (no torch types).
+ *
+ * Conventions shared with the reference
+ *   - arrays are C row-major `(time, x, y, z)`, z fastest, halo = space_order points per
+ *     side on every space dimension (devito/types/dense.py:1256-1259), `time` has
+ *     `size[0]` slots addressed `time % size[0]` (ModuloDimension t0/t1/t2,
+ *     devito/ir/clusters/algorithms.py:321-427);
+ *   - bounds `x_m..x_M`, `time_m..time_M`, `p_*_m..p_*_M` are INCLUSIVE
+ *     (devito/types/dimension.py:279-331);
+ *   - return value: 0 ok; 100 NaN/Inf in the wavefield; 200..203 device/launch failures
+ *     (devito/passes/iet/errors.py:192-198).  We add 210 = invalid argument.
+ */
+#ifndef B200STENCIL_H
+#define B200STENCIL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Identical to the reference's `struct dataobj` (devito/types/dense.py:737-746; printed in
+ * examples/performance/01_gpu.ipynb:262-273).  `data` is the HOST array; `dmap` is the
+ * device-resident mirror.  The reference fills `dmap` in C-land per call
+ * (devito/passes/iet/languages/openacc.py:245-247); here:
+ *    dmap == NULL : the callee allocates device memory, copies `data` H2D on entry, copies
+ *                   written arrays D2H on exit and frees (== reference `devicerm=1`);
+ *    dmap != NULL : the array is device-resident at `dmap` (same layout); no copies.    */
+struct b2_dataobj {
+    void *data;
+    int *size;              /* allocated shape, ndim entries                               */
+    unsigned long nbytes;
+    unsigned long *npsize;  /* unused by this library (may be NULL)                        */
+    unsigned long *dsize;   /* unused by this library (may be NULL)                        */
+    int *hsize;             /* halo sizes  [d0_L, d0_R, d1_L, ...] (may be NULL)           */
+    int *hofs;              /* halo offsets (may be NULL)                                  */
+    int *oofs;              /* owned offsets (may be NULL)                                 */
+    void *dmap;
+};
+
+/* Same role as the reference's `struct profiler` (devito/types/misc.py:41-68; printed
+ * 01_gpu.ipynb cell 23): accumulated seconds per section.  section0 = stencil update,
+ * section1 = source injection, section2 = receiver interpolation, haloupdate0 = exchange. */
+struct b2_profiler {
+    double section0;
+    double section1;
+    double section2;
+    double haloupdate0;
+};
+
+/* One SparseTimeFunction with the host-tabulated tables the reference passes
+ * (`*_gp`, `*_wx/wy/wz`; devito/operations/interpolators.py:390-421, 674-718). */
+struct b2_sparse {
+    struct b2_dataobj *data;      /* (nt, npoint) f32                                      */
+    struct b2_dataobj *gp;        /* (npoint, ndim) i32 : base cell index                  */
+    struct b2_dataobj *w[3];      /* (npoint, 2r) f32 per dim; unused dims NULL             */
+    int p_m, p_M;                 /* inclusive point range                                  */
+    int r;                        /* interpolation radius (linear: 1, sinc: 4)              */
+};
+
+/* What the sparse terms of the Operator look like (acoustic/operators.py:143-146,
+ * tti/operators.py:475-477). */
+enum { B2_PARAM_SCALAR = 0, B2_PARAM_VP = 1, B2_PARAM_M = 2 };
+
+/* Halo-exchange context for slab decomposition along x (replaces `MPI_Comm comm, struct
+ * neighborhood *nb` of the generated code, devito/mpi/distributed.py:822-902). Opaque. */
+typedef struct b2_halo_ctx b2_halo_ctx;
+
+/* ---- isotropic acoustic forward (replaces generated `Forward`,
+ *      examples/seismic/acoustic/operators.py:71-150) -------------------------------------
+ * u[t+1] = ( m (2u[t] - u[t-1])/dt^2 + damp u[t]/dt + sum_d sum_k w_d[k] u[t][.. +k ..] )
+ *          / ( m/dt^2 + damp/dt ),   m = 1/vp^2
+ * then  u[t+1][cell] += w.w.w * src[t][p] * dt^2 / m(cell)     (section1)
+ * then  rec[t][p] = sum w.w.w * u[t + rec_toff][cell]           (section2)
+ */
+struct b2_iso_args {
+    int ndim;                         /* 2 or 3                                             */
+    int space_order;                  /* halo width of u/damp/param arrays                  */
+    int radius;                       /* stencil radius (space_order/2)                     */
+    const float *w[3];                /* per-dim FD weights incl. 1/h^2: w[d][0..radius]    *
+                                       * (symmetric; w[d][0] is the centre weight)          */
+    struct b2_dataobj *u;             /* (tsize, x+2so, y+2so, z+2so)                       */
+    struct b2_dataobj *damp;          /* NULL -> no damping term                            */
+    int param_kind;                   /* B2_PARAM_*                                         */
+    struct b2_dataobj *param;         /* vp or m array when param_kind != SCALAR            */
+    float vp;                         /* scalar velocity when param_kind == SCALAR          */
+    float dt;
+    int x_m, x_M, y_m, y_M, z_m, z_M; /* for ndim==2 the z entries are ignored              */
+    int time_m, time_M;
+    struct b2_sparse *src;            /* NULL -> no injection                               */
+    struct b2_sparse *rec;            /* NULL -> no interpolation                           */
+    int rec_toff;                     /* 0: rec reads u[t] (pre-update), 1: u[t+1]          */
+    int errctl;                       /* !=0: NaN check every 100 steps -> return 100       */
+    int deviceid;
+    int kernel;                       /* 0 auto, 1 force generic kernel, 2 force TMA kernel */
+    b2_halo_ctx *halo;                /* NULL -> single device                              */
+    struct b2_profiler *timers;       /* may be NULL                                        */
+};
+int b2_iso_forward(const struct b2_iso_args *a);
+
+/* ---- TTI centred forward (replaces generated `ForwardTTI`,
+ *      examples/seismic/tti/operators.py:186-247, 431-480), scalar Thomsen parameters ----- */
+struct b2_tti_args {
+    int space_order;                  /* 3-D only                                           */
+    int radius;                       /* space_order/2                                      */
+    const float *w2[3];               /* 2nd-derivative weights incl 1/h^2, [0..radius]     */
+    const float *w1[3];               /* half-node 1st-derivative weights incl 1/h:         *
+                                       * `radius` entries for offsets (-r/2+1 .. r/2) about  *
+                                       * x+h/2 (devito/finite_differences/tools.py:280-308)  */
+    struct b2_dataobj *u, *v;
+    struct b2_dataobj *damp;
+    float vp, epsilon, delta, theta, phi;
+    float dt;
+    int x_m, x_M, y_m, y_M, z_m, z_M;
+    int time_m, time_M;
+    struct b2_sparse *src;            /* injected into both u and v                         */
+    struct b2_sparse *rec;            /* samples u+v                                        */
+    int rec_toff;
+    int errctl;
+    int deviceid;
+    int kernel;
+    b2_halo_ctx *halo;
+    struct b2_profiler *timers;
+};
+int b2_tti_forward(const struct b2_tti_args *a);
+
+/* ---- halo exchange under x-slab decomposition (replaces `haloupdate0`/`sendrecv0`,
+ *      devito/mpi/routines.py:285-552; printed examples/mpi/overview.ipynb:503-560) -------- */
+/* NCCL bootstrap: rank 0 calls b2_nccl_unique_id, the 128 bytes are broadcast by the host
+ * framework, every rank calls b2_halo_create. `nccl_lib` = path of libnccl.so.2 (or NULL). */
+int  b2_nccl_unique_id(const char *nccl_lib, char id_out[128]);
+b2_halo_ctx *b2_halo_create(const char *nccl_lib, const char id[128], int rank, int nranks,
+                            int deviceid);
+void b2_halo_destroy(b2_halo_ctx *ctx);
+/* Exchange `width` yz-planes of time slot `slot` of field `f` (device-resident) with the
+ * x-neighbours: owned planes -> neighbour halo. Blocking w.r.t. the library stream. */
+int  b2_halo_update(b2_halo_ctx *ctx, struct b2_dataobj *f, int slot, int width);
+
+/* ---- utilities ---------------------------------------------------------------------------- */
+int         b2_device_count(void);
+const char *b2_last_error(void);
+const char *b2_version(void);
+/* number of kernels launched by this library since load (for bench.py `gpu_launches`) */
+unsigned long long b2_launch_count(void);
+/* average device time (ms) of the stencil kernel launches since the last reset, measured
+ * with CUDA events on the library stream; used for bench.py `roofline.achieved`. */
+void   b2_kernel_timing_reset(void);
+double b2_kernel_timing_ms(int *nlaunches);
+void   b2_kernel_timing_enable(int on);
+/* device memory helpers for hosts that do not use torch */
+void *b2_malloc_device(unsigned long nbytes, int deviceid);
+void  b2_free_device(void *p, int deviceid);
+int   b2_memcpy_h2d(void *dst, const void *src, unsigned long nbytes, int deviceid);
+int   b2_memcpy_d2h(void *dst, const void *src, unsigned long nbytes, int deviceid);
+int   b2_memset_device(void *dst, int value, unsigned long nbytes, int deviceid);
+int   b2_synchronize(int deviceid);
+/* make the library enqueue its work on an externally owned CUDA stream (cudaStream_t as
+ * void*); NULL -> the library's own non-blocking stream. */
+void  b2_set_stream(void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200STENCIL_H */

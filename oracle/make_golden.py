@@ -1,0 +1,128 @@
+"""Generate golden vectors by running the REFERENCE itself (devito @ /root/reference) with its
+own CPU OpenMP backend and gcc, in the build container.
+
+  PYTHONPATH=oracle/refshim:/root/reference DEVITO_LANGUAGE=openmp DEVITO_ARCH=gcc \
+  DEVITO_SAFE_MATH=1 DEVITO_LOGGING=ERROR python oracle/make_golden.py
+
+`oracle/refshim` holds stand-ins for three pure-Python dependencies of the reference that are
+not installable offline (cgen, codepy, anytree); the numerical path (SymPy lowering -> C ->
+gcc) is the reference's own.  The fixtures land in tests/golden/*.npz; the reference is not
+needed to run the tests.
+"""
+import os
+import sys
+
+import numpy as np
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB",
+          {k: (v.shape if hasattr(v, 'shape') and v.ndim else v) for k, v in arrays.items() if np.size(v) < 8})
+
+
+def kat2d():
+    """tests/test_gpu_openacc.py:205-251 (norm(rec) = 490.56 +- 1e-2)."""
+    from devito import Grid, TimeFunction, Function, Eq, Operator, solve, norm
+    from examples.seismic import TimeAxis, RickerSource, Receiver
+    shape, extent = (101, 101), (1000, 1000)
+    v = np.empty(shape, dtype=np.float32)
+    v[:, :51] = 1.5
+    v[:, 51:] = 2.5
+    grid = Grid(shape=shape, extent=extent, origin=(0., 0.))
+    dt = 1.6
+    time_range = TimeAxis(start=0., stop=1000., step=dt)
+    src = RickerSource(name='src', grid=grid, f0=0.010, npoint=1, time_range=time_range)
+    src.coordinates.data[0, :] = np.array(extent) * .5
+    src.coordinates.data[0, -1] = 20.
+    rec = Receiver(name='rec', grid=grid, npoint=101, time_range=time_range)
+    rec.coordinates.data[:, 0] = np.linspace(0, extent[0], num=101)
+    rec.coordinates.data[:, 1] = 20.
+    u = TimeFunction(name="u", grid=grid, time_order=2, space_order=2)
+    m = Function(name='m', grid=grid)
+    m.data[:] = 1. / (v * v)
+    stencil = Eq(u.forward, solve(m * u.dt2 - u.laplace, u.forward))
+    src_term = src.inject(field=u.forward, expr=src * dt ** 2 / m)
+    rec_term = rec.interpolate(expr=u.forward)
+    op = Operator([stencil] + src_term + rec_term)
+    op(time=time_range.num - 1, dt=dt)
+    save('kat2d_so2', norm_rec=np.float32(norm(rec)), rec=np.array(rec.data[::5, ::4]),
+         u_last=np.array(u.data[(time_range.num) % 3, ::2, ::2]), nt=time_range.num,
+         src=np.array(src.data[:, 0]))
+
+
+def acoustic(name, so, n, nbl, tn, preset='constant-isotropic', interpolation='linear', **kw):
+    from devito import norm
+    from examples.seismic import demo_model, setup_geometry
+    from examples.seismic.acoustic import AcousticWaveSolver
+    model = demo_model(preset, spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl, space_order=so,
+                       dtype=np.float32, **kw)
+    geometry = setup_geometry(model, tn, interpolation=interpolation)
+    solver = AcousticWaveSolver(model, geometry, space_order=so)
+    rec, u, _ = solver.forward()
+    extra = {}
+    if not model.vp.is_Constant:
+        extra['vp'] = np.array(model.vp.data)
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(model.critical_dt), nt=geometry.nt,
+         damp=np.array(model.damp.data), src=np.array(geometry.src.data),
+         src_coords=np.array(geometry.src.coordinates.data),
+         rec_coords=np.array(geometry.rec.coordinates.data), rec=np.array(rec.data),
+         u=np.array(u.data), norm_rec=np.float32(norm(rec)), norm_u=np.float32(norm(u)), **extra)
+
+
+def tti(name, so, n, nbl, tn):
+    from devito import norm
+    from examples.seismic import demo_model, setup_geometry
+    from examples.seismic.tti import AnisotropicWaveSolver
+    model = demo_model('constant-tti', spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl,
+                       space_order=so, dtype=np.float32)
+    geometry = setup_geometry(model, tn)
+    solver = AnisotropicWaveSolver(model, geometry, space_order=so)
+    rec, u, v, _ = solver.forward()
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(model.critical_dt), nt=geometry.nt,
+         damp=np.array(model.damp.data), src=np.array(geometry.src.data),
+         src_coords=np.array(geometry.src.coordinates.data),
+         rec_coords=np.array(geometry.rec.coordinates.data), rec=np.array(rec.data),
+         u=np.array(u.data), v=np.array(v.data), norm_rec=np.float32(norm(rec)),
+         norm_u=np.float32(norm(u)), norm_v=np.float32(norm(v)),
+         epsilon=np.float32(model.epsilon.data), delta=np.float32(model.delta.data),
+         theta=np.float32(model.theta.data), phi=np.float32(model.phi.data))
+
+
+def coefficients():
+    """FD weights and CFL numbers straight from the reference's machinery."""
+    from devito import Grid, TimeFunction
+    from examples.seismic import demo_model
+    out = {}
+    for so in (4, 8, 12, 16):
+        model = demo_model('constant-isotropic', spacing=(10., 10., 10.), shape=(8, 8, 8), nbl=2,
+                           space_order=so, dtype=np.float32)
+        out[f'dt_iso_so{so}'] = np.float32(model.critical_dt)
+        mt = demo_model('constant-tti', spacing=(10., 10., 10.), shape=(8, 8, 8), nbl=2,
+                        space_order=so, dtype=np.float32)
+        out[f'dt_tti_so{so}'] = np.float32(mt.critical_dt)
+    save('coefficients', **out)
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'tti8', 'tti4', 'coef']
+    if 'kat2d' in which:
+        kat2d()
+    if 'iso8' in which:
+        acoustic('iso3d_so8', so=8, n=20, nbl=8, tn=150.0)
+    if 'iso12' in which:
+        acoustic('iso3d_so12', so=12, n=20, nbl=8, tn=150.0)
+    if 'iso4layers' in which:
+        acoustic('iso3d_so4_layers', so=4, n=20, nbl=8, tn=150.0, preset='layers-isotropic', nlayers=3)
+    if 'iso8sinc' in which:
+        acoustic('iso3d_so8_sinc', so=8, n=20, nbl=8, tn=100.0, interpolation='sinc')
+    if 'tti8' in which:
+        tti('tti3d_so8', so=8, n=20, nbl=8, tn=150.0)
+    if 'tti4' in which:
+        tti('tti3d_so4', so=4, n=20, nbl=8, tn=120.0)
+    if 'coef' in which:
+        coefficients()

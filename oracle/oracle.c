@@ -1,0 +1,273 @@
+/*
+ * oracle.c — CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may call this.  The product path (devito_b200 + libb200stencil.so) never does.
+ *
+ * Parity is PINNED: this restatement is checked (tests/test_oracle_golden.py) against
+ *   (a) golden vectors produced by running the reference itself (devito @ 436199c, CPU
+ *       OpenMP backend, gcc) in the build container — see oracle/make_golden.py, fixtures
+ *       in tests/golden/*.npz;
+ *   (b) the reference's own known-answer test norm(rec) = 490.56 +- 1e-2
+ *       (tests/test_gpu_openacc.py:205-251).
+ *
+ * What it restates (all citations relative to the reference tree):
+ *   iso update      examples/seismic/acoustic/operators.py:71-107 (iso_stencil), :50-68
+ *                   (laplacian); generated form `Forward` section0
+ *   TTI update      examples/seismic/tti/operators.py:65-104 (Gzz_centered), :146-183
+ *                   (Gh_centered), :186-247 (kernel_centered), :12-39 (second_order_stencil)
+ *   injection       devito/operations/interpolators.py:553-624 (_inject), guards :284-311
+ *   interpolation   devito/operations/interpolators.py:510-551 (_interpolate)
+ *   time loop       slot rotation t0 = time%T, t1 = (time+1)%T, t2 = (time-1)%T
+ *                   (devito/ir/clusters/algorithms.py:321-427; printed in
+ *                   examples/seismic/tutorials/08_snapshotting.ipynb:473)
+ * The arithmetic is written in the operation order of the C code the reference generates
+ * (float32 throughout), so that with DEVITO_SAFE_MATH=1 the two agree to rounding.
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define IDX3(x, y, z) ((size_t)(x) * sx + (size_t)(y) * sy + (size_t)(z))
+
+typedef struct {
+    float *data;       /* (nt, npoint) */
+    const int *gp;     /* (npoint, ndim) */
+    const float *w[3]; /* (npoint, 2r) */
+    int nt, npoint, p_m, p_M, r;
+} osparse;
+
+/* sparse ops on one field slot; ndim 2 or 3; lo/hi inclusive iteration bounds */
+static void inject(const osparse *s, int ndim, float *f0, float *f1, size_t sx, size_t sy, int so,
+                   const int *lo, const int *hi, int time, int param_kind, const float *param,
+                   float vp, float dt) {
+    if (!s || time < 0 || time >= s->nt) return;
+    const int n = 2 * s->r, r = s->r;
+    for (int p = s->p_m; p <= s->p_M; ++p) {
+        const float sv = s->data[(size_t)time * s->npoint + p];
+        if (ndim == 3) {
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b)
+                    for (int c = 0; c < n; ++c) {
+                        const int cx = s->gp[p * 3 + 0] + a - r + 1;
+                        const int cy = s->gp[p * 3 + 1] + b - r + 1;
+                        const int cz = s->gp[p * 3 + 2] + c - r + 1;
+                        if (cx < lo[0] - r || cx > hi[0] + r || cy < lo[1] - r || cy > hi[1] + r ||
+                            cz < lo[2] - r || cz > hi[2] + r)
+                            continue;
+                        const size_t i = IDX3(cx + so, cy + so, cz + so);
+                        float scale;
+                        if (param_kind == 0) scale = (vp * vp) * (dt * dt);
+                        else if (param_kind == 1) scale = (param[i] * param[i]) * (dt * dt);
+                        else scale = (dt * dt) / param[i];
+                        const float val = scale * s->w[0][p * n + a] * s->w[1][p * n + b] *
+                                          s->w[2][p * n + c] * sv;
+                        f0[i] += val;
+                        if (f1) f1[i] += val;
+                    }
+        } else {
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) {
+                    const int cx = s->gp[p * 2 + 0] + a - r + 1;
+                    const int cy = s->gp[p * 2 + 1] + b - r + 1;
+                    if (cx < lo[0] - r || cx > hi[0] + r || cy < lo[1] - r || cy > hi[1] + r) continue;
+                    const size_t i = (size_t)(cx + so) * sy + (size_t)(cy + so);
+                    float scale;
+                    if (param_kind == 0) scale = (vp * vp) * (dt * dt);
+                    else if (param_kind == 1) scale = (param[i] * param[i]) * (dt * dt);
+                    else scale = (dt * dt) / param[i];
+                    f0[i] += scale * s->w[0][p * n + a] * s->w[1][p * n + b] * sv;
+                }
+        }
+    }
+}
+
+static void interp(const osparse *s, int ndim, const float *f0, const float *f1, size_t sx, size_t sy,
+                   int so, const int *lo, const int *hi, int time) {
+    if (!s || time < 0 || time >= s->nt) return;
+    const int n = 2 * s->r, r = s->r;
+#pragma omp parallel for schedule(static)
+    for (int p = s->p_m; p <= s->p_M; ++p) {
+        float sum = 0.0f;
+        if (ndim == 3) {
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b)
+                    for (int c = 0; c < n; ++c) {
+                        const int cx = s->gp[p * 3 + 0] + a - r + 1;
+                        const int cy = s->gp[p * 3 + 1] + b - r + 1;
+                        const int cz = s->gp[p * 3 + 2] + c - r + 1;
+                        if (cx < lo[0] - r || cx > hi[0] + r || cy < lo[1] - r || cy > hi[1] + r ||
+                            cz < lo[2] - r || cz > hi[2] + r)
+                            continue;
+                        const size_t i = IDX3(cx + so, cy + so, cz + so);
+                        float v = f0[i];
+                        if (f1) v += f1[i];
+                        sum += s->w[0][p * n + a] * s->w[1][p * n + b] * s->w[2][p * n + c] * v;
+                    }
+        } else {
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) {
+                    const int cx = s->gp[p * 2 + 0] + a - r + 1;
+                    const int cy = s->gp[p * 2 + 1] + b - r + 1;
+                    if (cx < lo[0] - r || cx > hi[0] + r || cy < lo[1] - r || cy > hi[1] + r) continue;
+                    const size_t i = (size_t)(cx + so) * sy + (size_t)(cy + so);
+                    sum += s->w[0][p * n + a] * s->w[1][p * n + b] * f0[i];
+                }
+        }
+        s->data[(size_t)time * s->npoint + p] = sum;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * isotropic acoustic forward.  u: (tsize, [ax,] ay, az) with halo `so`;  w[d][0..radius].
+ * `alloc` = allocated extents per space dim; lo/hi = inclusive bounds per space dim.
+ * ---------------------------------------------------------------------------------------- */
+int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, int radius,
+                       const float *wx, const float *wy, const float *wz, const float *damp,
+                       int param_kind, const float *param, float vp, float dt, const int *lo,
+                       const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
+                       int rec_toff) {
+    const int R = radius;
+    size_t sx, sy, slot;
+    if (ndim == 3) {
+        sy = (size_t)alloc[2];
+        sx = (size_t)alloc[1] * alloc[2];
+        slot = (size_t)alloc[0] * sx;
+    } else {
+        sy = (size_t)alloc[1];
+        sx = 0;
+        slot = (size_t)alloc[0] * sy;
+    }
+    const float r2 = 1.0f / (dt * dt);
+    const float r3 = 1.0f / dt;
+    const float r1s = 1.0f / (vp * vp);
+    for (int time = time_m; time <= time_M; ++time) {
+        const int t0 = ((time % tsize) + tsize) % tsize;
+        const int t1 = (((time + 1) % tsize) + tsize) % tsize;
+        const int t2 = (((time - 1) % tsize) + tsize) % tsize;
+        const float *u0 = u + (size_t)t0 * slot;
+        const float *um = u + (size_t)t2 * slot;
+        float *u1 = u + (size_t)t1 * slot;
+        if (ndim == 3) {
+#pragma omp parallel for collapse(2) schedule(static)
+            for (int x = lo[0]; x <= hi[0]; ++x)
+                for (int y = lo[1]; y <= hi[1]; ++y)
+                    for (int z = lo[2]; z <= hi[2]; ++z) {
+                        const size_t i = IDX3(x + so, y + so, z + so);
+                        float lap = (wx[0] + wy[0] + wz[0]) * u0[i];
+                        for (int k = 1; k <= R; ++k)
+                            lap += wx[k] * (u0[i - k * sx] + u0[i + k * sx]) +
+                                   wy[k] * (u0[i - k * sy] + u0[i + k * sy]) +
+                                   wz[k] * (u0[i - k] + u0[i + k]);
+                        float r1 = r1s;
+                        if (param_kind == 1) r1 = 1.0f / (param[i] * param[i]);
+                        else if (param_kind == 2) r1 = param[i];
+                        const float d = damp ? damp[i] : 0.0f;
+                        u1[i] = (-r1 * (-2.0f * r2 * u0[i] + r2 * um[i]) + r3 * d * u0[i] + lap) /
+                                (r1 * r2 + r3 * d);
+                    }
+        } else {
+#pragma omp parallel for schedule(static)
+            for (int x = lo[0]; x <= hi[0]; ++x)
+                for (int y = lo[1]; y <= hi[1]; ++y) {
+                    const size_t i = (size_t)(x + so) * sy + (size_t)(y + so);
+                    float lap = (wx[0] + wy[0]) * u0[i];
+                    for (int k = 1; k <= R; ++k)
+                        lap += wx[k] * (u0[i - k * sy] + u0[i + k * sy]) + wy[k] * (u0[i - k] + u0[i + k]);
+                    float r1 = r1s;
+                    if (param_kind == 1) r1 = 1.0f / (param[i] * param[i]);
+                    else if (param_kind == 2) r1 = param[i];
+                    const float d = damp ? damp[i] : 0.0f;
+                    u1[i] = (-r1 * (-2.0f * r2 * u0[i] + r2 * um[i]) + r3 * d * u0[i] + lap) /
+                            (r1 * r2 + r3 * d);
+                }
+        }
+        inject(src, ndim, u1, NULL, sx, sy, so, lo, hi, time, param_kind, param, vp, dt);
+        interp(rec, ndim, rec_toff ? u1 : u0, NULL, sx, sy, so, lo, hi, time);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * TTI centred forward, scalar parameters, 3-D.  w2[d][0..R] second-derivative weights,
+ * w1[d][0..R-1] half-node first-derivative weights (offsets -R/2+1..R/2 about x+h/2).
+ * Follows the generated `ForwardTTI`: first the rotated first derivatives Gz(u), Gz(v) on
+ * the box extended by [-R/2, R/2-1] (reference: CIRE temporaries r12..r17), then the update.
+ * ---------------------------------------------------------------------------------------- */
+int oracle_tti_forward(float *u, float *v, int tsize, const int *alloc, int so, int radius,
+                       const float *w2x, const float *w2y, const float *w2z, const float *w1x,
+                       const float *w1y, const float *w1z, const float *damp, float vp,
+                       float epsilon, float delta, float theta, float phi, float dt, const int *lo,
+                       const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
+                       int rec_toff) {
+    const int R = radius, h = radius / 2;
+    const size_t sy = (size_t)alloc[2], sx = (size_t)alloc[1] * alloc[2];
+    const size_t slot = (size_t)alloc[0] * sx;
+    float *gzu = (float *)calloc(slot, sizeof(float));
+    float *gzv = (float *)calloc(slot, sizeof(float));
+    if (!gzu || !gzv) return 202;
+    const float r18 = sqrtf(2 * delta + 1);
+    const float ct = cosf(theta), st = sinf(theta), sp = sinf(phi), cp = cosf(phi);
+    const float cz = ct, cy = sp * st, cx = st * cp;
+    const float e2 = 2 * epsilon + 1;
+    const float r9 = 1.0f / (vp * vp), r10 = 1.0f / (dt * dt), r11 = 1.0f / dt;
+    for (int time = time_m; time <= time_M; ++time) {
+        const int t0 = ((time % tsize) + tsize) % tsize;
+        const int t1 = (((time + 1) % tsize) + tsize) % tsize;
+        const int t2 = (((time - 1) % tsize) + tsize) % tsize;
+        const float *u0 = u + (size_t)t0 * slot, *v0 = v + (size_t)t0 * slot;
+        const float *um = u + (size_t)t2 * slot, *vm = v + (size_t)t2 * slot;
+        float *u1 = u + (size_t)t1 * slot, *v1 = v + (size_t)t1 * slot;
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int x = lo[0] - h; x <= hi[0] + h - 1; ++x)
+            for (int y = lo[1] - h; y <= hi[1] + h - 1; ++y)
+                for (int z = lo[2] - h; z <= hi[2] + h - 1; ++z) {
+                    const size_t i = IDX3(x + so, y + so, z + so);
+                    float dxu = 0, dyu = 0, dzu = 0, dxv = 0, dyv = 0, dzv = 0;
+                    for (int j = 0; j < R; ++j) {
+                        const ptrdiff_t o = j - h + 1;
+                        dxu += w1x[j] * u0[i + o * (ptrdiff_t)sx];
+                        dyu += w1y[j] * u0[i + o * (ptrdiff_t)sy];
+                        dzu += w1z[j] * u0[i + o];
+                        dxv += w1x[j] * v0[i + o * (ptrdiff_t)sx];
+                        dyv += w1y[j] * v0[i + o * (ptrdiff_t)sy];
+                        dzv += w1z[j] * v0[i + o];
+                    }
+                    gzu[i] = cz * dzu + cy * dyu + cx * dxu;
+                    gzv[i] = cz * dzv + cy * dyv + cx * dxv;
+                }
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int x = lo[0]; x <= hi[0]; ++x)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int z = lo[2]; z <= hi[2]; ++z) {
+                    const size_t i = IDX3(x + so, y + so, z + so);
+                    float lap = (w2x[0] + w2y[0] + w2z[0]) * u0[i];
+                    for (int k = 1; k <= R; ++k)
+                        lap += w2x[k] * (u0[i - k * sx] + u0[i + k * sx]) +
+                               w2y[k] * (u0[i - k * sy] + u0[i + k * sy]) +
+                               w2z[k] * (u0[i - k] + u0[i + k]);
+                    /* outer half-node derivatives of (r12,r13,r14) and (r15,r16,r17) */
+                    float H0 = 0, Hz = 0;
+                    for (int j = 0; j < R; ++j) {
+                        const ptrdiff_t o = j - h;
+                        const size_t iz = i + o, iy = i + o * (ptrdiff_t)sy, ix = i + o * (ptrdiff_t)sx;
+                        H0 += w1z[j] * (gzv[iz] * (r18 * cz) - gzu[iz] * e2 * cz) +
+                              w1x[j] * (gzv[ix] * (r18 * cx) - gzu[ix] * e2 * cx) +
+                              w1y[j] * (gzv[iy] * (r18 * cy) - gzu[iy] * e2 * cy);
+                        Hz += w1z[j] * (gzv[iz] * cz - gzu[iz] * (r18 * cz)) +
+                              w1y[j] * (gzv[iy] * cy - gzu[iy] * (r18 * cy)) +
+                              w1x[j] * (gzv[ix] * cx - gzu[ix] * (r18 * cx));
+                    }
+                    const float d = damp ? damp[i] : 0.0f;
+                    const float r26 = 1.0f / (r10 * r9 + r11 * d);
+                    u1[i] = r26 * (e2 * lap + r10 * r9 * (2.0f * u0[i] - um[i]) + r11 * d * u0[i] + H0);
+                    v1[i] = r26 * (r11 * d * v0[i] + r18 * lap - r9 * (-2.0f * r10 * v0[i] + r10 * vm[i]) + Hz);
+                }
+        inject(src, 3, u1, v1, sx, sy, so, lo, hi, time, 0, NULL, vp, dt);
+        interp(rec, 3, rec_toff ? u1 : u0, rec_toff ? v1 : v0, sx, sy, so, lo, hi, time);
+    }
+    free(gzu);
+    free(gzv);
+    return 0;
+}

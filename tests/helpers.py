@@ -1,0 +1,55 @@
+"""Shared problem set-up for the parity tests: rebuilds the inputs of a golden fixture with the
+ORACLE's host-side restatements (oracle/oracle.py), independent of the product package."""
+import os
+
+import numpy as np
+
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+def rel_linf(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def domain(arr, so):
+    sl = (slice(None),) + tuple(slice(so, s - so) for s in arr.shape[1:])
+    return arr[sl]
+
+
+def iso_problem(n, nbl, so, tn, f0=0.010, vp=1.5, h=10.0, interpolation='linear', r=None,
+                nrec_grid=True, vp_array=None):
+    """Inputs of `demo_model('constant-isotropic') + setup_geometry` restated with the oracle."""
+    N = n + 2 * nbl
+    spacing = (np.float32(h),) * 3
+    origin = tuple(np.float32(-nbl * h) for _ in range(3))
+    vp_max = float(vp if vp_array is None else vp_array.max())
+    dt = float(O.critical_dt(so, 3, h, vp_max))
+    nt, tvals = O.time_axis(0.0, tn, dt)
+    damp = O.damp_field((N, N, N), nbl, spacing, so)
+    dom = tuple((n - 1) * h for _ in range(3))
+    src_c = np.array([[dom[0] * .5, dom[1] * .5, h]])
+    rx = np.linspace(0, dom[0], n)
+    ry = np.linspace(0, dom[1], n)
+    rec_c = np.empty((n * n, 3))
+    rec_c[:, 0] = np.repeat(rx, n)
+    rec_c[:, 1] = np.tile(ry, n)
+    rec_c[:, 2] = 2 * h
+    rr = r or (1 if interpolation == 'linear' else 4)
+    sgp, sw = O.tabulate(src_c.astype(np.float32), origin, spacing, rr, interpolation)
+    rgp, rw = O.tabulate(rec_c.astype(np.float32), origin, spacing, rr, interpolation)
+    src = np.zeros((nt, 1), dtype=np.float32)
+    src[:, 0] = O.ricker(f0, tvals)
+    rec = np.zeros((nt, n * n), dtype=np.float32)
+    w = [O.fd2_weights(so, h)] * 3
+    u = np.zeros((3, N + 2 * so, N + 2 * so, N + 2 * so), dtype=np.float32)
+    return dict(N=N, so=so, dt=dt, nt=nt, damp=damp, w=w, u=u, vp=vp,
+                src=dict(data=src, gp=sgp, w=sw, r=rr), rec=dict(data=rec, gp=rgp, w=rw, r=rr),
+                src_coords=src_c, rec_coords=rec_c, origin=origin, spacing=spacing)
