@@ -384,11 +384,17 @@ class FieldStorage:
         self.host_valid = True
 
     def to_device(self, device):
-        """Device tensor holding current data (upload if the host copy is newer)."""
+        """Device tensor holding current data (upload if the host copy is newer). A function
+        whose host array was never touched is all zeros: it is created directly on the device."""
         import torch
+        tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
+               np.dtype(np.float64): torch.float64}[self.dtype]
         if self.dev is None or self.dev.device != device:
-            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
-                   np.dtype(np.float64): torch.float64}[self.dtype]
+            if self._host is None:
+                self.dev = torch.zeros(self.shape, dtype=tdt, device=device)
+                self.dev_valid = True
+                self.host_valid = False
+                return self.dev
             self.dev = torch.empty(self.shape, dtype=tdt, device=device)
             self.dev_valid = False
         if not self.dev_valid:

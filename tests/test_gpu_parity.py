@@ -1,0 +1,152 @@
+"""Parity of the CUDA path against the oracle and the reference's golden vectors.
+
+All tests call through the public API (`Operator.apply`, which crosses the C ABI in
+include/b200stencil.h exactly once per call). Tolerances: BASELINE.json north_star —
+L-inf relative error < 1e-5 isotropic, < 1e-4 TTI."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from helpers import load_golden, rel_linf, domain, iso_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _solver(kind, so, n, nbl, tn, interpolation='linear', **kw):
+    from devito_b200.seismic import (demo_model, setup_geometry, AcousticWaveSolver,
+                                     AnisotropicWaveSolver)
+    preset = 'constant-isotropic' if kind == 'iso' else 'constant-tti'
+    model = demo_model(preset, spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl, space_order=so, **kw)
+    geometry = setup_geometry(model, tn, interpolation=interpolation)
+    cls = AcousticWaveSolver if kind == 'iso' else AnisotropicWaveSolver
+    return model, geometry, cls(model, geometry, space_order=so)
+
+
+@pytest.mark.parametrize('name,so,interp', [('iso3d_so8', 8, 'linear'), ('iso3d_so12', 12, 'linear'),
+                                            ('iso3d_so8_sinc', 8, 'sinc')])
+@pytest.mark.parametrize('kernel', [1, 0])
+def test_iso_vs_reference_golden(name, so, interp, kernel):
+    g = load_golden(name)
+    model, geometry, solver = _solver('iso', so, int(g['n']), int(g['nbl']), float(g['tn']), interp)
+    assert solver.op_fwd().backend == 'cuda-sm100a'
+    rec, u, summary = solver.forward(kernel=kernel)
+    assert rel_linf(u.data, g['u']) < 1e-5
+    assert rel_linf(rec.data, g['rec']) < 1e-5
+    from devito_b200 import norm
+    assert abs(float(norm(rec)) - float(g['norm_rec'])) < 1e-4 * float(g['norm_rec'])
+
+
+def test_iso_array_vp_vs_reference_golden():
+    g = load_golden('iso3d_so4_layers')
+    from devito_b200.seismic import demo_model, setup_geometry, AcousticWaveSolver
+    model = demo_model('layers-isotropic', spacing=(10., 10., 10.), shape=(20, 20, 20), nbl=8,
+                       space_order=4, nlayers=3)
+    assert rel_linf(model.vp.data, g['vp']) < 1e-6
+    geometry = setup_geometry(model, float(g['tn']))
+    solver = AcousticWaveSolver(model, geometry, space_order=4)
+    rec, u, _ = solver.forward()
+    assert rel_linf(u.data, g['u']) < 1e-5
+    assert rel_linf(rec.data, g['rec']) < 1e-5
+
+
+@pytest.mark.parametrize('name,so', [('tti3d_so8', 8), ('tti3d_so4', 4)])
+def test_tti_vs_reference_golden(name, so):
+    g = load_golden(name)
+    model, geometry, solver = _solver('tti', so, int(g['n']), int(g['nbl']), float(g['tn']))
+    assert solver.op_fwd().backend == 'cuda-sm100a'
+    rec, u, v, _ = solver.forward()
+    assert rel_linf(u.data, g['u']) < 1e-4
+    assert rel_linf(v.data, g['v']) < 1e-4
+    assert rel_linf(rec.data, g['rec']) < 1e-4
+
+
+def test_kat2d_reference_known_answer():
+    """tests/test_gpu_openacc.py:205-251 of the reference: norm(rec) = 490.56 +- 1e-2."""
+    from devito_b200 import Grid, TimeFunction, Function, Eq, Operator, solve, norm
+    from devito_b200.seismic import TimeAxis, RickerSource, Receiver
+    shape, extent = (101, 101), (1000, 1000)
+    v = np.empty(shape, dtype=np.float32)
+    v[:, :51] = 1.5
+    v[:, 51:] = 2.5
+    grid = Grid(shape=shape, extent=extent, origin=(0., 0.))
+    dt = 1.6
+    time_range = TimeAxis(start=0., stop=1000., step=dt)
+    src = RickerSource(name='src', grid=grid, f0=0.010, npoint=1, time_range=time_range)
+    src.coordinates.data[0, :] = np.array(extent) * .5
+    src.coordinates.data[0, -1] = 20.
+    rec = Receiver(name='rec', grid=grid, npoint=101, time_range=time_range)
+    rec.coordinates.data[:, 0] = np.linspace(0, extent[0], num=101)
+    rec.coordinates.data[:, 1] = 20.
+    u = TimeFunction(name="u", grid=grid, time_order=2, space_order=2)
+    m = Function(name='m', grid=grid)
+    m.data[:] = 1. / (v * v)
+    stencil = Eq(u.forward, solve(m * u.dt2 - u.laplace, u.forward))
+    src_term = src.inject(field=u.forward, expr=src * dt ** 2 / m)
+    rec_term = rec.interpolate(expr=u.forward)
+    op = Operator([stencil] + src_term + rec_term)
+    assert op.backend == 'cuda-sm100a'
+    op(time=time_range.num - 1, dt=dt)
+    assert np.isclose(norm(rec), 490.56, atol=1e-2, rtol=0)
+    g = load_golden('kat2d_so2')
+    assert rel_linf(rec.data[::5, ::4], g['rec']) < 1e-4
+
+
+@pytest.mark.parametrize('so,n,nbl', [(8, 56, 12), (12, 40, 10), (4, 32, 8), (16, 40, 8)])
+def test_iso_tma_vs_oracle_larger(so, n, nbl):
+    """TMA kernel vs the oracle at sizes that exercise several tiles, partial tiles in y and z,
+    and several x-chunks."""
+    p = iso_problem(n, nbl, so, 120.0)
+    O.iso_forward(p['u'], so, p['w'], p['dt'], 1, p['nt'] - 2, damp=p['damp'], vp=1.5,
+                  src=p['src'], rec=p['rec'])
+    model, geometry, solver = _solver('iso', so, n, nbl, 120.0)
+    rec, u, _ = solver.forward(kernel=2)
+    assert rel_linf(u.data_with_halo, p['u']) < 1e-5
+    assert rel_linf(rec.data, p['rec']['data']) < 1e-5
+
+
+def test_host_staged_call_equals_resident_call():
+    """The C-ABI call with host buffers (dmap == NULL: H2D/D2H inside the call, like the
+    reference's per-apply copies) gives the same answer as the device-resident call."""
+    model, geometry, solver = _solver('iso', 8, 32, 8, 100.0)
+    rec1, u1, _ = solver.forward()
+    rec2, u2, _ = solver.forward(resident=False)
+    assert np.array_equal(np.asarray(u1.data), np.asarray(u2.data))
+    assert np.array_equal(np.asarray(rec1.data), np.asarray(rec2.data))
+
+
+def test_restart_on_time_subranges():
+    """Second caller of the C ABI in the reference (checkpointing/checkpoint.py:30-46): the loop
+    must be restartable on arbitrary [time_m, time_M] sub-ranges."""
+    model, geometry, solver = _solver('iso', 8, 32, 8, 120.0)
+    rec1, u1, _ = solver.forward()
+    from devito_b200 import TimeFunction
+    u2 = TimeFunction(name='u', grid=model.grid, time_order=2, space_order=8)
+    rec2 = geometry.rec
+    nt = geometry.nt
+    mid = nt // 2
+    solver.forward(u=u2, rec=rec2, time_m=1, time_M=mid)
+    solver.forward(u=u2, rec=rec2, time_m=mid + 1, time_M=nt - 2)
+    assert np.array_equal(np.asarray(u1.data), np.asarray(u2.data))
+    assert np.array_equal(np.asarray(rec1.data), np.asarray(rec2.data))
+
+
+def test_linearity_large():
+    """Size-independent property at a larger grid: the propagator is linear in the source."""
+    model, geometry, solver = _solver('iso', 8, 104, 12, 60.0)
+    src = geometry.src
+    rec1, u1, _ = solver.forward(src=src)
+    src2 = geometry.src
+    src2.data[:] = 2.5 * src.data
+    rec2, u2, _ = solver.forward(src=src2)
+    assert rel_linf(2.5 * np.asarray(u1.data), u2.data) < 1e-5
+    assert np.all(np.isfinite(u2.data))
+
+
+def test_error_code_on_nan():
+    """Return code 100 -> ExecutionError (devito/passes/iet/errors.py:192-198; operator.py:734-772)."""
+    from devito_b200 import ExecutionError
+    model, geometry, solver = _solver('iso', 8, 24, 6, 50.0)
+    src = geometry.src
+    src.data[3, 0] = np.nan
+    with pytest.raises(ExecutionError):
+        solver.forward(src=src, errctl=1)
