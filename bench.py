@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--nt', type=int, default=int(os.environ.get('B2_BENCH_NT', 128)),
                     help='time steps per Operator.apply')
     ap.add_argument('--space-order', type=int, default=8)
+    ap.add_argument('--workload', default='iso', choices=['iso', 'tti'],
+                    help="iso: the headline metric; tti: BASELINE config 4 (not the driver's line)")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
@@ -181,7 +183,8 @@ def main():
     import torch.distributed as dist
     import devito_b200 as dv
     from devito_b200 import _lib
-    from devito_b200.seismic import SeismicModel, AcquisitionGeometry, AcousticWaveSolver, TimeAxis
+    from devito_b200.seismic import (SeismicModel, AcquisitionGeometry, AcousticWaveSolver,
+                                     AnisotropicWaveSolver, TimeAxis)
 
     world = dv.init_distributed()
     rank, nranks = world.rank, world.size
@@ -195,8 +198,11 @@ def main():
     n = G - 2 * nbl
     # global grid: (nranks*G) x G x G, slab-decomposed along x (weak scaling)
     shape = (nranks * G - 2 * nbl, n, n)
+    tti = a.workload == 'tti'
+    extra = dict(epsilon=.3, delta=.2, theta=.7, phi=.35) if tti else {}
     model = SeismicModel(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=shape, space_order=so,
-                         vp=1.5, nbl=nbl, bcs="damp", topology=('*', 1, 1) if nranks > 1 else None)
+                         vp=1.5, nbl=nbl, bcs="damp", topology=('*', 1, 1) if nranks > 1 else None,
+                         **extra)
     dt = model.critical_dt
     tn = float(dt) * (NT + 1)
     src_c = np.array([[model.domain_size[0] * .5, model.domain_size[1] * .5, 10.0]])
@@ -204,9 +210,12 @@ def main():
     ry = np.linspace(0, model.domain_size[1], 16)
     rec_c = np.array([[x, y, 20.0] for x in rx for y in ry])           # 512 receivers
     geometry = AcquisitionGeometry(model, rec_c, src_c, t0=0.0, tn=tn, src_type='Ricker', f0=0.010)
-    solver = AcousticWaveSolver(model, geometry, space_order=so)
+    solver = (AnisotropicWaveSolver if tti else AcousticWaveSolver)(model, geometry, space_order=so)
     nt_steps = geometry.nt - 2                                          # time = 1 .. nt-2
     u = dv.TimeFunction(name='u', grid=model.grid, time_order=2, space_order=so)
+    v = dv.TimeFunction(name='v', grid=model.grid, time_order=2, space_order=so) if tti else None
+    fkw = dict(v=v) if tti else {}
+    b_alg = 28.0 if tti else B_ALG
     src, rec = geometry.src, geometry.rec
     pts_step = float(nranks) * G * G * G * nt_steps                     # points per apply (whole job)
 
@@ -234,7 +243,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    resident = lambda: solver.forward(src=src, rec=rec, u=u)
+    resident = lambda: solver.forward(src=src, rec=rec, u=u, **fkw)
     for _ in range(a.warmup):
         resident()
     launches0 = L.b2_launch_count()
@@ -256,14 +265,14 @@ def main():
         pts_launch = None
     roof = None
     if nl.value and k_ms > 0 and nranks == 1:
-        ach = B_ALG * pts_launch / (k_ms * 1e-3) / 1e9
+        ach = b_alg * pts_launch / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                "kernel": "k_iso_tma", "launch_ms": k_ms, "launches_timed": int(nl.value)}
+                "kernel": "k_tti_*" if tti else "k_iso_tma", "launch_ms": k_ms, "launches_timed": int(nl.value)}
 
     e2e = None
     if not a.no_e2e:
-        hostcall = lambda: solver.forward(src=src, rec=rec, u=u, resident=False)
+        hostcall = lambda: solver.forward(src=src, rec=rec, u=u, resident=False, **fkw)
         _ = u.data_with_halo          # materialise (pinned) host copies outside the timed region
         _ = model.damp.data_with_halo
         for _ in range(min(a.warmup, 1) or 1):
@@ -285,11 +294,11 @@ def main():
             cpu = {"value": None, "unit": "GPts/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}
 
     if rank == 0:
-        line = {"metric": "GPts/s (3D isotropic acoustic forward, so=%d, %d^3 per GPU)" % (so, G),
+        line = {"metric": "GPts/s (3D %s forward, so=%d, %d^3 per GPU)" % ("TTI" if tti else "isotropic acoustic", so, G),
                 "value": value, "unit": "GPts/s", "n_gpus": nranks, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": t_res / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"3D isotropic acoustic so={so}, grid {nranks * G}x{G}x{G} "
+                "config": {"workload": f"3D {'TTI centred' if tti else 'isotropic acoustic'} so={so}, grid {nranks * G}x{G}x{G} "
                                        f"(nbl=40 included), {nt_steps} time steps per apply, 1 Ricker source, "
                                        f"512 receivers, constant vp=1.5",
                            "decomposition": f"x-slabs over {nranks} GPU(s)" if nranks > 1 else "single GPU",

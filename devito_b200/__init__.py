@@ -9,7 +9,7 @@ from .logger import info, warning, error, perf, debug, set_log_level  # noqa: F4
 from .exceptions import (InvalidArgument, InvalidOperator, ExecutionError,  # noqa: F401
                          BackendUnavailable, DevitoError)
 from .symbolics import (sin, cos, sqrt, Abs, sign, exp, floor, INT, Derivative,  # noqa: F401
-                        retrieve_functions, retrieve_derivatives)
+                        retrieve_functions, retrieve_derivatives, div, grad)
 from .types import (Grid, SubDomain, Dimension, SpaceDimension, TimeDimension,  # noqa: F401
                     SteppingDimension, SubDimension, DefaultDimension, ConditionalDimension,
                     Function, TimeFunction, Constant, Buffer, NODE, CELL)
@@ -21,6 +21,28 @@ from .builtins import (norm, sumall, inner, mmin, mmax, assign, smooth, gaussian
 from .distributed import init_distributed  # noqa: F401
 
 __version__ = '0.1.0'
+
+
+class _OutOfScope:
+    """Names the reference's examples import at module level but that belong to SURVEY §8f
+    ("next") or out-of-scope rows: importing works, using raises."""
+    _what = ''
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError(f"{type(self).__name__} is outside this backend's scope: {self._what}")
+
+
+class CheckpointOperator(_OutOfScope):
+    _what = "pyrevolve checkpointing (devito/checkpointing/checkpoint.py); the C-ABI loop is " \
+            "restartable on [time_m, time_M] sub-ranges, which is what it needs"
+
+
+class DevitoCheckpoint(_OutOfScope):
+    _what = CheckpointOperator._what
+
+
+class Revolver(_OutOfScope):
+    _what = CheckpointOperator._what
 
 
 def install_as_devito():

@@ -11,6 +11,8 @@
 #include "b2_sparse.cuh"
 #include "b2_halo.cuh"
 #include <vector>
+#include <cstdlib>
+#include <string>
 
 using namespace b2;
 
@@ -164,7 +166,9 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     StepEvents &se = g_step_events;
     se.used = 0;
     const int nsteps = a->time_M - a->time_m + 1;
-    const bool per_step_events = timing && nsteps <= 4096;
+    // per-section timing costs 4 event records per step: only on request (B2_PROFILING=advanced)
+    static const bool adv = getenv("B2_PROFILING") && std::string(getenv("B2_PROFILING")) == "advanced";
+    const bool per_step_events = timing && adv && nsteps <= 4096;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (timing && !per_step_events) ev_begin = se.next();
 

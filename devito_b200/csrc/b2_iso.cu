@@ -73,6 +73,13 @@ __global__ void __launch_bounds__(256) k_iso_generic(IsoGK k) {
 // ------------------------------------------------------------------------------------------
 // TMA 2.5-D kernel
 // ------------------------------------------------------------------------------------------
+// The update is evaluated in the algebraically identical division-free form
+//     u+ = u + A (m/dt^2 (u - u-) + lap)            scalar m      (A = 1/(m/dt^2 + damp/dt))
+//     u+ = u + B (u - u-) + A lap                   array vp|m    (B = m/dt^2 * A)
+// with A (and B) tabulated once per call by k_iso_coef: the IEEE division, which cost ~1/5 of
+// the issued instructions of the first version of this kernel (profiles/r1a_*), leaves the
+// inner loop, and A replaces damp (B replaces vp|m) in the streamed arrays, so the HBM traffic
+// per point is unchanged (16 B, or 20 B with an array parameter).
 template <int R>
 struct IsoTK {
     float *__restrict__ u1;      // base of the output time slot
@@ -82,32 +89,41 @@ struct IsoTK {
     int xlo, xcount, lx;
     int ntz, nty;
     int slot0, slotm;
-    float m_dt2, inv_dt, inv_dt2;
+    float m_dt2;
     float wx[R + 1], wy[R + 1], wz[R + 1];
 };
 
 constexpr int ceil4(int v) { return (v + 3) / 4 * 4; }
 constexpr int align32f(int v) { return (v + 31) / 32 * 32; }   // 128-byte multiples in floats
 
-template <int R, int TY, int TZ4, int PF, int PK>
+// Ring layout: the u[t] planes live in a ring of exactly Q = 2R+1 stages, so that inside the
+// loop body (unrolled Q times) every shared-memory address is a compile-time offset; plane j
+// sits in stage j % Q, and the R planes beyond the one being read for output are the prefetch
+// depth. The (u[t-1], A[, B]) tiles of output step s use a second, shorter ring of NS >= R+1
+// stages indexed at run time (two loads per iteration only). One full/empty mbarrier pair per
+// u-stage covers both: the tiles of step s = j-2R travel with plane j.
+template <int R, int TY, int TZ4, int PK>
 struct IsoTmaCfg {
     static constexpr int RZ = ceil4(R);
     static constexpr int TZ = 4 * TZ4;
     static constexpr int BY = TY + 2 * R;
     static constexpr int BZ = TZ + 2 * RZ;
-    static constexpr int NU = R + 1 + PF;
-    static constexpr int NS = PF + 1;
     static constexpr int Q = 2 * R + 1;
+    static constexpr int NU = Q;
+    static constexpr int NS = R + 1;
     static constexpr int PLANE = align32f(BY * BZ);
     static constexpr int TILE = TY * TZ;
     static constexpr int NCW = TY * TZ4 / 32;          // consumer warps
-    static constexpr int NTILES = 2 + (PK != B2_PARAM_SCALAR ? 1 : 0);   // prev, damp, [param]
+    static constexpr int NTILES = 2 + (PK != B2_PARAM_SCALAR ? 1 : 0);   // prev, A, [B]
     static constexpr size_t SMEM =
         (size_t)(NU * PLANE + NS * TILE * NTILES) * 4 + 2 * NU * 8 + 128;
 };
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) {
     return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4sub(float4 a, float4 b) {
+    return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
 }
 __device__ __forceinline__ void f4fma(float4 &acc, float w, float4 v) {
     acc.x = fmaf(w, v.x, acc.x);
@@ -116,21 +132,21 @@ __device__ __forceinline__ void f4fma(float4 &acc, float w, float4 v) {
     acc.w = fmaf(w, v.w, acc.w);
 }
 
-template <int R, int TY, int TZ4, int PF, int PK>
+template <int R, int TY, int TZ4, int PK>
 __global__ void __launch_bounds__(TY *TZ4 + 32, 1)
 k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUtensorMap tm_uc,
-          const __grid_constant__ CUtensorMap tm_damp, const __grid_constant__ CUtensorMap tm_par,
+          const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
           const IsoTK<R> k) {
-    using C = IsoTmaCfg<R, TY, TZ4, PF, PK>;
+    using C = IsoTmaCfg<R, TY, TZ4, PK>;
     constexpr int RZ = C::RZ, TZ = C::TZ, BZ = C::BZ, NU = C::NU, NS = C::NS, Q = C::Q;
     constexpr int PLANE = C::PLANE, TILE = C::TILE, NCW = C::NCW;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_u = reinterpret_cast<float *>(smem_raw);
     float *s_prev = s_u + NU * PLANE;
-    float *s_damp = s_prev + NS * TILE;
-    float *s_par = s_damp + NS * TILE;
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_par + (PK != B2_PARAM_SCALAR ? NS * TILE : 0));
+    float *s_a = s_prev + NS * TILE;
+    float *s_b = s_a + NS * TILE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_b + (PK != B2_PARAM_SCALAR ? NS * TILE : 0));
     uint64_t *empty = full + NU;
 
     int b = blockIdx.x;
@@ -138,7 +154,7 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
     b /= k.ntz;
     const int iy = b % k.nty;
     const int ix = b / k.nty;
-    const int z0 = iz * TZ, y0 = iy * C::BY - iy * 2 * R;   // = iy * TY
+    const int z0 = iz * TZ, y0 = iy * TY;
     const int xs = k.xlo + ix * k.lx;
     const int xe = min(xs + k.lx, k.xlo + k.xcount);
     const int NP = (xe - xs) + 2 * R;
@@ -160,8 +176,8 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
         if (lane == 0) {
             b2ptx::tma_prefetch_desc(&tm_uh);
             b2ptx::tma_prefetch_desc(&tm_uc);
-            b2ptx::tma_prefetch_desc(&tm_damp);
-            if (PK != B2_PARAM_SCALAR) b2ptx::tma_prefetch_desc(&tm_par);
+            b2ptx::tma_prefetch_desc(&tm_a);
+            if (PK != B2_PARAM_SCALAR) b2ptx::tma_prefetch_desc(&tm_b);
             int slot = 0, round = 0, ss = 0;
             for (int j = 0; j < NP; ++j) {
                 if (round > 0) b2ptx::mbar_wait(&empty[slot], (round - 1) & 1);
@@ -174,10 +190,10 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
                 if (s >= 0) {
                     b2ptx::tma_load_4d(s_prev + ss * TILE, &tm_uc, &full[slot], k.oz + z0,
                                        k.oy + y0, k.ox + xs + s, k.slotm);
-                    b2ptx::tma_load_3d(s_damp + ss * TILE, &tm_damp, &full[slot], k.oz + z0,
-                                       k.oy + y0, k.ox + xs + s);
+                    b2ptx::tma_load_3d(s_a + ss * TILE, &tm_a, &full[slot], k.oz + z0, k.oy + y0,
+                                       k.ox + xs + s);
                     if (PK != B2_PARAM_SCALAR)
-                        b2ptx::tma_load_3d(s_par + ss * TILE, &tm_par, &full[slot], k.oz + z0,
+                        b2ptx::tma_load_3d(s_b + ss * TILE, &tm_b, &full[slot], k.oz + z0,
                                            k.oy + y0, k.ox + xs + s);
                     if (++ss == NS) ss = 0;
                 }
@@ -193,30 +209,33 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
     const bool yok = gy < k.ny;
     const int zcnt = yok ? min(max(k.nz - gz, 0), 4) : 0;
     const float *my_col = s_u + (ty + R) * BZ + RZ + 4 * tz4;
-    const int tile_off = ty * TZ + 4 * tz4;
-    float *outp = k.u1 + (long long)(k.ox + xs) * k.sx + (long long)(k.oy + gy) * k.sy + (k.oz + gz);
+    const float *my_prev = s_prev + ty * TZ + 4 * tz4;
+    float *outp = k.u1 + (long long)(k.ox + xs - 2 * R) * k.sx + (long long)(k.oy + gy) * k.sy + (k.oz + gz);
+    const long long osx = k.sx;
 
     float4 q[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const float wc = k.wx[0] + k.wy[0] + k.wz[0];
-    int slot_h = 0, par_h = 0;      // ring slot / parity of the newest plane j
-    int slot_c = 0;                 // ring slot of plane j-R (valid once j >= R)
-    int ss = 0;                     // prev/damp ring slot of output step j-2R
+    uint32_t par = 0;               // parity of the u-ring round
+    int ssoff = 0;                  // float offset of the tile-ring slot of output step j-2R
 
     for (int jb = 0; jb < NP; jb += Q) {
 #pragma unroll
         for (int p = 0; p < Q; ++p) {
             const int j = jb + p;
             if (j >= NP) break;
-            b2ptx::mbar_wait(&full[slot_h], par_h);
-            q[p] = b2ptx::lds128(my_col + slot_h * PLANE);
+            b2ptx::mbar_wait(&full[p], par);
+            q[p] = b2ptx::lds128(my_col + p * PLANE);
 
             if (j >= 2 * R) {
-                const float *cp = my_col + slot_c * PLANE;
-                const float4 c = q[(p - R + Q) % Q];
-                // z direction: gather the row segment [-RZ, 4+RZ) around my 4 points
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int pc = (p - R + Q) % Q;                // stage of the centre plane j-R
+                const float *cp = my_col + pc * PLANE;
+                const float4 c = q[pc];
+                // z direction: row segment [-RZ, 4+RZ) around my 4 points
                 float zr[4 + 2 * RZ];
 #pragma unroll
                 for (int m = 0; m < RZ / 4; ++m) {
@@ -243,29 +262,25 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
                 }
 #pragma unroll
                 for (int i = 1; i <= R; ++i)
-                    f4fma(acc, k.wx[i], f4add(q[(p - R - i + 2 * Q) % Q], q[(p - R + i + Q) % Q]));
+                    f4fma(acc, k.wx[i], f4add(q[(pc - i + Q) % Q], q[(pc + i) % Q]));
 
-                const float4 pv = b2ptx::lds128(s_prev + ss * TILE + tile_off);
-                const float4 dm = b2ptx::lds128(s_damp + ss * TILE + tile_off);
-                float4 md = make_float4(k.m_dt2, k.m_dt2, k.m_dt2, k.m_dt2);
-                if (PK == B2_PARAM_VP) {
-                    const float4 v = b2ptx::lds128(s_par + ss * TILE + tile_off);
-                    md = make_float4(k.inv_dt2 / (v.x * v.x), k.inv_dt2 / (v.y * v.y),
-                                     k.inv_dt2 / (v.z * v.z), k.inv_dt2 / (v.w * v.w));
-                } else if (PK == B2_PARAM_M) {
-                    const float4 v = b2ptx::lds128(s_par + ss * TILE + tile_off);
-                    md = make_float4(v.x * k.inv_dt2, v.y * k.inv_dt2, v.z * k.inv_dt2, v.w * k.inv_dt2);
-                }
+                const float4 pv = b2ptx::lds128(my_prev + ssoff);
+                const float4 ca = b2ptx::lds128(my_prev + (NS * TILE) + ssoff);
+                const float4 dcp = f4sub(c, pv);
                 float4 o;
-                {
-                    const float d0 = dm.x * k.inv_dt, d1 = dm.y * k.inv_dt, d2 = dm.z * k.inv_dt,
-                                d3 = dm.w * k.inv_dt;
-                    o.x = (fmaf(md.x, 2.f * c.x - pv.x, fmaf(d0, c.x, acc.x))) / (md.x + d0);
-                    o.y = (fmaf(md.y, 2.f * c.y - pv.y, fmaf(d1, c.y, acc.y))) / (md.y + d1);
-                    o.z = (fmaf(md.z, 2.f * c.z - pv.z, fmaf(d2, c.z, acc.z))) / (md.z + d2);
-                    o.w = (fmaf(md.w, 2.f * c.w - pv.w, fmaf(d3, c.w, acc.w))) / (md.w + d3);
+                if (PK == B2_PARAM_SCALAR) {
+                    o.x = fmaf(ca.x, fmaf(k.m_dt2, dcp.x, acc.x), c.x);
+                    o.y = fmaf(ca.y, fmaf(k.m_dt2, dcp.y, acc.y), c.y);
+                    o.z = fmaf(ca.z, fmaf(k.m_dt2, dcp.z, acc.z), c.z);
+                    o.w = fmaf(ca.w, fmaf(k.m_dt2, dcp.w, acc.w), c.w);
+                } else {
+                    const float4 cb = b2ptx::lds128(my_prev + (2 * NS * TILE) + ssoff);
+                    o.x = fmaf(ca.x, acc.x, fmaf(cb.x, dcp.x, c.x));
+                    o.y = fmaf(ca.y, acc.y, fmaf(cb.y, dcp.y, c.y));
+                    o.z = fmaf(ca.z, acc.z, fmaf(cb.z, dcp.z, c.z));
+                    o.w = fmaf(ca.w, acc.w, fmaf(cb.w, dcp.w, c.w));
                 }
-                float *dst = outp + (long long)(j - 2 * R) * k.sx;
+                float *dst = outp + (long long)j * osx;
                 if (zcnt == 4) {
                     *reinterpret_cast<float4 *>(dst) = o;
                 } else if (zcnt > 0) {
@@ -273,15 +288,37 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
                     if (zcnt > 1) dst[1] = o.y;
                     if (zcnt > 2) dst[2] = o.z;
                 }
-                if (++ss == NS) ss = 0;
+                ssoff += TILE;
+                if (ssoff == NS * TILE) ssoff = 0;
             }
             if (j >= R) {
                 __syncwarp();
-                if (lane == 0) b2ptx::mbar_arrive(&empty[slot_c]);
-                if (++slot_c == NU) slot_c = 0;
+                if (lane == 0) b2ptx::mbar_arrive(&empty[(p - R + Q) % Q]);
             }
-            if (++slot_h == NU) { slot_h = 0; par_h ^= 1; }
         }
+        par ^= 1;
+    }
+}
+
+// A = 1/(m/dt^2 + damp/dt), B = m/dt^2 * A on the full allocated array (halo included; halo
+// values are never used by the stencil)
+__global__ void __launch_bounds__(256)
+k_iso_coef(const float *__restrict__ damp, const float *__restrict__ param, int param_kind,
+           float m_dt2_scalar, float inv_dt, float inv_dt2, float *__restrict__ A,
+           float *__restrict__ B, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float md = m_dt2_scalar;
+        if (param_kind == B2_PARAM_VP) {
+            const float v = param[i];
+            md = inv_dt2 / (v * v);
+        } else if (param_kind == B2_PARAM_M) {
+            md = param[i] * inv_dt2;
+        }
+        const float a = 1.0f / (md + damp[i] * inv_dt);
+        A[i] = a;
+        if (B) B[i] = md * a;
     }
 }
 
@@ -330,16 +367,48 @@ static int make_tmap(CUtensorMap *tm, const void *base, int rank, const int *dim
     return B2_OK;
 }
 
-// tile configuration per radius (TY, TZ4, PF); tuned on B200 (see profiles/)
+// tile configuration per radius (TY, TZ4): sized so that the Q-stage plane ring plus the
+// (R+1)-stage tile ring fit the 227 KB of shared memory of one SM
 template <int R> struct TileOf;
-template <> struct TileOf<2> { static constexpr int TY = 32, TZ4 = 16, PF = 3; };
-template <> struct TileOf<4> { static constexpr int TY = 32, TZ4 = 16, PF = 3; };
-template <> struct TileOf<6> { static constexpr int TY = 32, TZ4 = 16, PF = 3; };
-template <> struct TileOf<8> { static constexpr int TY = 32, TZ4 = 16, PF = 2; };
+template <> struct TileOf<2> { static constexpr int TY = 32, TZ4 = 16; };
+template <> struct TileOf<4> { static constexpr int TY = 32, TZ4 = 16; };
+template <> struct TileOf<6> { static constexpr int TY = 16, TZ4 = 16; };
+template <> struct TileOf<8> { static constexpr int TY = 8, TZ4 = 16; };
 
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v ? atoi(v) : dflt;
+}
+
+// scratch for the coefficient arrays, cached across calls (re-allocated when the size changes)
+static float *g_coef[2] = {nullptr, nullptr};
+static size_t g_coef_elems[2] = {0, 0};
+
+static int coef_buffer(int which, size_t elems, float **out) {
+    if (g_coef_elems[which] != elems) {
+        if (g_coef[which]) cudaFree(g_coef[which]);
+        g_coef[which] = nullptr;
+        g_coef_elems[which] = 0;
+        B2_CUDA(cudaMalloc(&g_coef[which], elems * sizeof(float)), B2_ERR_MEMORY);
+        g_coef_elems[which] = elems;
+    }
+    *out = g_coef[which];
+    return B2_OK;
+}
+
+static int iso_coef_tabulate(IsoPlan &p) {
+    int rc;
+    if ((rc = coef_buffer(0, p.slot_elems, &p.coefA))) return rc;
+    p.coefB = nullptr;
+    if (p.param_kind != B2_PARAM_SCALAR)
+        if ((rc = coef_buffer(1, p.slot_elems, &p.coefB))) return rc;
+    const float inv_dt = 1.0f / p.dt, inv_dt2 = 1.0f / (p.dt * p.dt);
+    const float md = (1.0f / (p.vp * p.vp)) * inv_dt2;
+    k_iso_coef<<<148 * 8, 256, 0, stream()>>>(p.damp, p.param, p.param_kind, md, inv_dt, inv_dt2,
+                                               p.coefA, p.coefB, p.slot_elems);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
 }
 
 template <int R>
@@ -351,9 +420,9 @@ static int plan_tma(IsoPlan &p) {
     int rc;
     if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T::TZ4 + 2 * RZ, T::TY + 2 * R))) return rc;
     if ((rc = make_tmap(&p.tm_uc, p.u, 4, dims4, 4 * T::TZ4, T::TY))) return rc;
-    if ((rc = make_tmap(&p.tm_damp, p.damp, 3, dims3, 4 * T::TZ4, T::TY))) return rc;
+    if ((rc = make_tmap(&p.tm_damp, p.coefA, 3, dims3, 4 * T::TZ4, T::TY))) return rc;
     if (p.param_kind != B2_PARAM_SCALAR) {
-        if ((rc = make_tmap(&p.tm_par, p.param, 3, dims3, 4 * T::TZ4, T::TY))) return rc;
+        if ((rc = make_tmap(&p.tm_par, p.coefB, 3, dims3, 4 * T::TZ4, T::TY))) return rc;
     } else {
         p.tm_par = p.tm_damp;
     }
@@ -378,6 +447,8 @@ int iso_plan_init(IsoPlan &p, int kernel) {
     }
     p.use_tma = ok;
     if (!ok) return B2_OK;
+    int rc = iso_coef_tabulate(p);
+    if (rc) return rc;
     switch (R) {
         case 2: return plan_tma<2>(p);
         case 4: return plan_tma<4>(p);
@@ -390,8 +461,8 @@ int iso_plan_init(IsoPlan &p, int kernel) {
 template <int R, int PK>
 static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
     using T = TileOf<R>;
-    using C = IsoTmaCfg<R, T::TY, T::TZ4, T::PF, PK>;
-    auto kern = k_iso_tma<R, T::TY, T::TZ4, T::PF, PK>;
+    using C = IsoTmaCfg<R, T::TY, T::TZ4, PK>;
+    auto kern = k_iso_tma<R, T::TY, T::TZ4, PK>;
     static bool attr_set = false;
     if (!attr_set) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),
@@ -424,10 +495,7 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     const int ntx = (xcount + lx - 1) / lx;
     k.slot0 = slot0;
     k.slotm = slotm;
-    const float inv_dt = 1.0f / p.dt;
-    k.inv_dt = inv_dt;
-    k.inv_dt2 = 1.0f / (p.dt * p.dt);
-    k.m_dt2 = (1.0f / (p.vp * p.vp)) * k.inv_dt2;
+    k.m_dt2 = (1.0f / (p.vp * p.vp)) * (1.0f / (p.dt * p.dt));
     for (int i = 0; i <= R; ++i) {
         k.wx[i] = p.w[0][i];
         k.wy[i] = p.w[1][i];

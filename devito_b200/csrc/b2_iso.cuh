@@ -22,7 +22,8 @@ struct IsoPlan {
     float w[3][B2_MAX_RADIUS + 1] = {};
     // TMA path
     bool use_tma = false;
-    CUtensorMap tm_uh, tm_uc, tm_damp, tm_par;
+    CUtensorMap tm_uh, tm_uc, tm_damp, tm_par;   // tm_damp/tm_par map coefA/coefB
+    float *coefA = nullptr, *coefB = nullptr;    // tabulated update coefficients (library scratch)
     int lx = 0;
 };
 

@@ -52,6 +52,33 @@ void timing_end() {
     g_timing_used += 2;
 }
 
+// Small staging buffers (sparse tables, source/receiver traces) are recycled through a size-keyed
+// pool instead of cudaMalloc/cudaFree per call: cudaFree synchronises the whole device and both
+// cost ~0.1-1 ms, which showed up as a fixed per-apply overhead in the first benchmark.
+static std::vector<std::pair<size_t, void *>> g_pool_free;
+static const size_t kPoolMax = 64u << 20;
+
+static cudaError_t pool_alloc(void **p, size_t nbytes) {
+    if (nbytes <= kPoolMax) {
+        for (size_t i = 0; i < g_pool_free.size(); ++i) {
+            if (g_pool_free[i].first == nbytes) {
+                *p = g_pool_free[i].second;
+                g_pool_free.erase(g_pool_free.begin() + i);
+                return cudaSuccess;
+            }
+        }
+    }
+    return cudaMalloc(p, nbytes);
+}
+
+static void pool_release(void *p, size_t nbytes) {
+    if (nbytes <= kPoolMax && g_pool_free.size() < 256) {
+        g_pool_free.emplace_back(nbytes, p);
+        return;
+    }
+    cudaFree(p);
+}
+
 int stage_in(const b2_dataobj *obj, int ndim, DevArray &out, bool copy_in) {
     if (!obj) { set_error("stage_in: NULL dataobj"); return B2_ERR_INVALID; }
     out.ndim = ndim;
@@ -65,7 +92,7 @@ int stage_in(const b2_dataobj *obj, int ndim, DevArray &out, bool copy_in) {
         return B2_OK;
     }
     if (!obj->data) { set_error("stage_in: dataobj has neither data nor dmap"); return B2_ERR_INVALID; }
-    B2_CUDA(cudaMalloc(&out.d, out.nbytes), B2_ERR_MEMORY);
+    B2_CUDA(pool_alloc(&out.d, out.nbytes), B2_ERR_MEMORY);
     out.owned = true;
     if (copy_in)
         B2_CUDA(cudaMemcpyAsync(out.d, out.h, out.nbytes, cudaMemcpyHostToDevice, stream()),
@@ -81,7 +108,8 @@ int stage_out(DevArray &a, bool copy_back) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream());
         if (e != cudaSuccess) { set_error("stage_out: %s", cudaGetErrorString(e)); rc = B2_ERR_MEMORY; }
     }
-    cudaFree(a.d);
+    if (!copy_back) cudaStreamSynchronize(stream());   // pending async H2D/kernels still use it
+    pool_release(a.d, a.nbytes);
     a.d = nullptr;
     a.owned = false;
     return rc;

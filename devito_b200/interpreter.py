@@ -229,22 +229,22 @@ class Interpreter:
         r = sf.r
         nd = gp.shape[1]
         n = 2 * r
-        grids = np.meshgrid(*[np.arange(n)] * nd, indexing='ij')
         w = np.ones((sf.npoint,) + (n,) * nd)
         idxs = []
         valid = np.ones((sf.npoint,) + (n,) * nd, dtype=bool)
         space_dims = [d for d in field_fn.dimensions if d.is_Space]
         for j in range(nd):
-            k = grids[j][None, ...]
+            sh = (sf.npoint,) + tuple(n if i == j else 1 for i in range(nd))
+            k = np.arange(n).reshape((1,) + sh[1:])
             cell = gp[:, j].reshape((-1,) + (1,) * nd) + k - r + 1
             d = space_dims[j]
             size = field_fn.shape[field_fn.dimensions.index(d)]
             lo, hi = bounds.get(d.name, (0, size - 1))
-            valid &= (cell >= lo - r) & (cell <= hi + r)
+            valid = valid & (cell >= lo - r) & (cell <= hi + r)
             hl = field_fn.halo[field_fn.dimensions.index(d)][0]
-            valid &= (cell + hl >= 0) & (cell + hl < size + 2 * hl)
-            idxs.append(cell)
-            w = w * ws[j][:, k.reshape(-1)].reshape((sf.npoint,) + tuple(n if i == j else 1 for i in range(nd)))
+            valid = valid & (cell + hl >= 0) & (cell + hl < size + 2 * hl)
+            idxs.append(np.broadcast_to(cell, valid.shape))
+            w = w * ws[j].astype(np.float64).reshape(sh)
         return idxs, valid, w
 
     def _eval_at_cells(self, expr, sf, idxs, time, scalars):

@@ -794,16 +794,46 @@ class Operator:
         hold.append(ob)
         return ob
 
-    def _sparse_obj(self, sf, grid, hold, written=False):
+    def _sparse_obj(self, sf, grid, hold, written=False, post=None):
+        """b2_sparse for a SparseTimeFunction. Under x-slab decomposition every rank holds all
+        points (positions are made relative to the local slab; the kernels' bound guards drop
+        what lies outside). A *written* function (receivers) is evaluated only for the points
+        whose base cell this rank owns and merged with an all-reduce afterwards — the reference
+        scatters points to their owner ranks instead (devito/types/sparse.py:608-730)."""
         if sf is None:
             return None
         gp, ws = sf.tabulate()
-        # positions relative to this rank's sub-domain (x-slab decomposition)
-        off = grid.distributor.offsets
-        if any(off):
-            gp = gp - np.asarray(off, dtype=np.int32)[None, :]
-            gp = np.ascontiguousarray(gp.astype(np.int32))
+        dist = grid.distributor
         host = sf.storage.host if written else sf.storage.host_ro
+        if dist.is_parallel:
+            off = dist.offsets
+            gp = np.ascontiguousarray((gp - np.asarray(off, dtype=np.int32)[None, :]).astype(np.int32))
+            if written:
+                nloc = grid.shape[0]
+                mask = (gp[:, 0] >= 0) & (gp[:, 0] < nloc)
+                idx = np.nonzero(mask)[0]
+                gp = np.ascontiguousarray(gp[idx])
+                ws = [np.ascontiguousarray(w[idx]) for w in ws]
+                local = np.zeros((host.shape[0], len(idx)), dtype=host.dtype)
+                full = host
+
+                def merge():
+                    full[...] = 0
+                    full[:, idx] = local
+                    import torch
+                    import torch.distributed as tdist
+                    t = torch.from_numpy(full)
+                    if tdist.get_backend() == 'nccl':
+                        tg = t.cuda()
+                        tdist.all_reduce(tg)
+                        t.copy_(tg.cpu())
+                    else:
+                        tdist.all_reduce(t)
+                if post is not None:
+                    post.append(merge)
+                host = local
+                if len(idx) == 0:
+                    return None
         data = L_.make_dataobj(host=host)
         gpo = L_.make_dataobj(host=gp)
         wos = [L_.make_dataobj(host=w) for w in ws]
@@ -812,9 +842,9 @@ class Operator:
         s.gp = gpo.ptr
         for i, wo in enumerate(wos):
             s.w[i] = wo.ptr
-        s.p_m, s.p_M = 0, sf.npoint - 1
+        s.p_m, s.p_M = 0, host.shape[1] - 1
         s.r = sf.r
-        hold.extend([gp, ws, data, gpo, wos, s])
+        hold.extend([gp, ws, data, gpo, wos, s, host])
         return s
 
     def _finish(self, rc, L, timers, args, nfields_pts, t_wall):
@@ -870,7 +900,8 @@ class Operator:
             a.z_m, a.z_M = lo[2], hi[2]
         a.time_m, a.time_M = args['time_m'], args['time_M']
         s = self._sparse_obj(args['src'], grid, hold)
-        r = self._sparse_obj(args['rec'], grid, hold, written=True)
+        post = []
+        r = self._sparse_obj(args['rec'], grid, hold, written=True, post=post)
         a.src = ctypes.pointer(s) if s is not None else None
         a.rec = ctypes.pointer(r) if r is not None else None
         a.rec_toff = p['rec_toff']
@@ -887,6 +918,8 @@ class Operator:
         t0 = _time.perf_counter()
         rc = L.b2_iso_forward(ctypes.byref(a))
         t_wall = _time.perf_counter() - t0
+        for fn in post:
+            fn()
         return self._finish(rc, L, timers, args, 1, t_wall)
 
     def _apply_tti(self, **kwargs):
@@ -912,7 +945,8 @@ class Operator:
         a.x_m, a.x_M, a.y_m, a.y_M, a.z_m, a.z_M = lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]
         a.time_m, a.time_M = args['time_m'], args['time_M']
         s = self._sparse_obj(args['src'], grid, hold)
-        r = self._sparse_obj(args['rec'], grid, hold, written=True)
+        post = []
+        r = self._sparse_obj(args['rec'], grid, hold, written=True, post=post)
         a.src = ctypes.pointer(s) if s is not None else None
         a.rec = ctypes.pointer(r) if r is not None else None
         a.rec_toff = p['rec_toff']
@@ -925,6 +959,8 @@ class Operator:
         t0 = _time.perf_counter()
         rc = L.b2_tti_forward(ctypes.byref(a))
         t_wall = _time.perf_counter() - t0
+        for fn in post:
+            fn()
         return self._finish(rc, L, timers, args, 2, t_wall)
 
 

@@ -107,8 +107,6 @@ class SeismicModel:
         dist = self.grid.distributor
         if dist.is_parallel:
             # the profile depends on global indices: evaluate on the global shape, keep our slab
-            g = Grid(shape=self.grid.shape_global, extent=self.grid.extent, origin=self.grid.origin,
-                     dtype=self.grid.dtype, topology=None, _serial=True) if False else None
             prof = damp_profile(self.grid.shape_global, self.padsizes, self.grid.spacing, bcs)
             lo, hi = dist.x_range
             self.damp.data[:] = prof[lo:hi]

@@ -21,7 +21,7 @@ from functools import lru_cache
 
 import numpy as np
 
-__all__ = ['Expr', 'Number', 'Symbol', 'Add', 'Mul', 'Pow', 'Call', 'Access', 'Index',
+__all__ = ['div', 'grad', 'Expr', 'Number', 'Symbol', 'Add', 'Mul', 'Pow', 'Call', 'Access', 'Index',
            'Derivative', 'as_expr', 'sin', 'cos', 'sqrt', 'Abs', 'sign', 'exp', 'floor', 'INT',
            'fd_weights', 'fd_offsets', 'retrieve_functions', 'retrieve_derivatives',
            'linear_terms', 'NonLinear']
@@ -732,3 +732,18 @@ def linear_terms(expr, is_unknown):
         raise NonLinear(repr(e))
 
     return rec(expr)
+
+
+def div(expr, shift=None, order=None, method='FD', **kwargs):
+    """Sum of first derivatives along the space dimensions (devito/finite_differences/operators.py)."""
+    expr = as_expr(expr)
+    out = Number(0)
+    for d in expr._space_dims:
+        out = out + Derivative(expr, (d, 1), fd_order=order)
+    return out
+
+
+def grad(expr, shift=None, order=None, method='FD', **kwargs):
+    """Tuple of first derivatives along the space dimensions."""
+    expr = as_expr(expr)
+    return tuple(Derivative(expr, (d, 1), fd_order=order) for d in expr._space_dims)

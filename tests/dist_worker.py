@@ -1,0 +1,81 @@
+"""Worker for the world_size-2 tests (launched by torch.distributed.run). Mode 'host' needs no
+GPU (gloo): decomposition, parameter slabs, reductions. Mode 'gpu' runs the decomposed
+propagator with NCCL halo exchange and compares with the single-GPU result."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import devito_b200 as dv  # noqa: E402
+from devito_b200.seismic import (SeismicModel, demo_model, setup_geometry, AcousticWaveSolver,  # noqa: E402
+                                 AnisotropicWaveSolver, damp_profile)
+
+
+def host_mode():
+    import torch.distributed as dist
+    w = dv.init_distributed(backend='gloo')
+    assert w.size == 2
+    nbl, so, n = 6, 8, (21, 12, 12)
+    vp = np.linspace(1.5, 3.0, int(np.prod(n)), dtype=np.float32).reshape(n)
+    model = SeismicModel(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=n, space_order=so, vp=vp,
+                         nbl=nbl, bcs="damp", topology=('*', 1, 1))
+    d = model.grid.distributor
+    N = n[0] + 2 * nbl
+    parts = np.array_split(np.arange(N), 2)                 # devito/mpi/distributed.py:379-382
+    assert d.x_range == (int(parts[w.rank][0]), int(parts[w.rank][-1]) + 1)
+    assert model.grid.shape == (len(parts[w.rank]), n[1] + 2 * nbl, n[2] + 2 * nbl)
+    assert model.grid.shape_global == (N, n[1] + 2 * nbl, n[2] + 2 * nbl)
+    # damping profile and padded parameter follow GLOBAL indices
+    full = damp_profile(model.grid.shape_global, [(nbl, nbl)] * 3, model.grid.spacing)
+    lo, hi = d.x_range
+    assert np.array_equal(np.asarray(model.damp.data), full[lo:hi])
+    vp_full = np.pad(np.pad(vp, nbl, mode='edge'), so, mode='edge')
+    assert np.array_equal(np.asarray(model.vp.data_with_halo), vp_full[lo:hi + 2 * so])
+    # reductions agree with the serial values on every rank
+    assert np.isclose(dv.mmax(model.vp), vp.max())
+    serial_norm = np.sqrt(np.sum(full.astype(np.float64) ** 2))
+    assert np.isclose(float(dv.norm(model.damp)), serial_norm, rtol=1e-6)
+    assert model.critical_dt > 0
+    # sparse points are expressed relative to the local slab
+    geometry = setup_geometry(model, 30.0)
+    op = AcousticWaveSolver(model, geometry, space_order=so).op_fwd()
+    assert op.backend == 'cuda-sm100a'
+    dist.barrier()
+    if w.rank == 0:
+        print('DIST-HOST-OK')
+
+
+def gpu_mode(kind):
+    import torch
+    import torch.distributed as dist
+    w = dv.init_distributed()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dv.configuration['deviceid'] = local
+    so, nbl, n, tn = 8, 10, (44, 28, 28), 150.0
+    preset = 'constant-isotropic' if kind == 'iso' else 'constant-tti'
+    cls = AcousticWaveSolver if kind == 'iso' else AnisotropicWaveSolver
+    model = demo_model(preset, spacing=(10., 10., 10.), shape=n, nbl=nbl, space_order=so, topology=('*', 1, 1))
+    geometry = setup_geometry(model, tn)
+    out = cls(model, geometry, space_order=so).forward()
+    rec, u = out[0], out[1]
+    lo, hi = model.grid.distributor.x_range
+    np.save(f'/tmp/b2_dist_{kind}_u_{w.rank}.npy', np.asarray(u.data))
+    if w.rank == 0:
+        np.save(f'/tmp/b2_dist_{kind}_rec.npy', np.asarray(rec.data))
+        np.save(f'/tmp/b2_dist_{kind}_ranges.npy', np.array([lo, hi]))
+    dist.barrier()
+    from devito_b200.distributed import finalize_distributed
+    finalize_distributed()
+    if w.rank == 0:
+        print('DIST-GPU-DONE')
+
+
+if __name__ == '__main__':
+    if sys.argv[1] == 'host':
+        host_mode()
+    else:
+        gpu_mode(sys.argv[2])
