@@ -15,7 +15,9 @@
 // Kernel 1 (two-pass, any even radius): pass A writes Gz(u), Gz(v) to scratch, pass B
 // applies the outer derivatives + Laplacian + time update.
 #include "b2_tti.cuh"
+#include "b2_ptx.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace b2 {
 
@@ -97,26 +99,495 @@ __global__ void __launch_bounds__(256) k_tti_update(TtiK k) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 2 (fused, radius 2 or 4): one pass over HBM — 28 B/point (u,v: t r, t-1 r, t+1 w; A r).
+// ------------------------------------------------------------------------------------------
+// A CTA owns a (TY x 64) yz-tile and marches along x. Per x-iteration (output plane x):
+//   producer warp : TMA-loads the haloed planes u[t](x+R) and v[t](x+R-1) into shared rings;
+//   stage A       : all consumer threads evaluate Gz(u), Gz(v) at plane x+1 on the tile extended
+//                   by [-R/2, R/2-1] in y and z (inputs from the shared u/v planes x..x+3) and
+//                   store them in a 4-plane shared ring — the reference materialises these
+//                   intermediates in HBM/scratch arrays (CIRE temporaries r12..r17);
+//   stage B       : each thread owns 4 consecutive z points: Laplacian (x-taps from a register
+//                   queue, y/z taps from the shared plane), the outer half-node derivatives of
+//                   Gz from the shared Gz ring, the coupled update, 16-byte stores.
+// The update uses the tabulated A = 1/(m/dt^2 + damp/dt): f+ = f + A (m/dt^2 (f - f-) + H).
+struct TtiFK {
+    float *__restrict__ u1;
+    float *__restrict__ v1;
+    const float *__restrict__ um;
+    const float *__restrict__ vm;
+    const float *__restrict__ A;
+    long long sx, sy;
+    int ny, nz;
+    int ox, oy, oz;
+    int xlo, xcount, lx;
+    int ntz, nty;
+    int slot0;
+    float m_dt2;
+    float cx, cy, cz;          // sin(th)cos(ph), sin(th)sin(ph), cos(th)
+    float e2, sd;              // 1+2eps, sqrt(1+2delta)
+    float w2x[5], w2y[5], w2z[5];
+    float w1x[4], w1y[4], w1z[4];
+};
+
+template <int R, int TY>
+struct TtiCfg {
+    static constexpr int H = R / 2;
+    static constexpr int TZ4 = 16, TZ = 64, RZ = 4;
+    static constexpr int PR = TY + 2 * R;            // rows of a u/v plane box
+    static constexpr int BZ = TZ + 2 * RZ;           // 72
+    static constexpr int GR = TY + R;                // rows of a Gz plane: [-H, TY+H-1] (+pad)
+    static constexpr int NUU = R + 1 + 2;            // u planes x..x+R, +2 prefetch
+    static constexpr int NUV = R + 2;                // v planes x..x+R-1, +2 prefetch
+    static constexpr int NG = R + 1;                 // Gz planes x-H..x+H-1, +1 so that stage A of the
+                                                     // next iteration never overwrites a plane still read
+    static constexpr int NB = 4;                     // barrier ring
+    static constexpr int PLANE = ((PR * BZ + 31) / 32) * 32;
+    static constexpr int GPLANE = ((GR * BZ + 31) / 32) * 32;
+    static constexpr int NCT = TY * TZ4;             // consumer threads
+    static constexpr int NCW = NCT / 32;
+    static constexpr int GGROUPS = (TY + R - 1) * (BZ / 4);   // float4 groups of the extended tile
+    static constexpr size_t SMEM = (size_t)((NUU + NUV) * PLANE + 2 * NG * GPLANE) * 4 + 2 * NB * 8 + 128;
+};
+
+template <int R, int TY>
+__global__ void __launch_bounds__(TY * 16 + 32, 1)
+k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
+            const TtiFK k) {
+    using C = TtiCfg<R, TY>;
+    constexpr int H = C::H, TZ = C::TZ, RZ = C::RZ, BZ = C::BZ, PR = C::PR, GR = C::GR;
+    constexpr int NUU = C::NUU, NUV = C::NUV, NG = C::NG, NB = C::NB;
+    constexpr int PLANE = C::PLANE, GPLANE = C::GPLANE, NCT = C::NCT, NCW = C::NCW;
+    constexpr int PRE = 2 * R;                      // priming iterations before the first output
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_u = reinterpret_cast<float *>(smem_raw);
+    float *s_v = s_u + NUU * PLANE;
+    float *s_gu = s_v + NUV * PLANE;
+    float *s_gv = s_gu + NG * GPLANE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_gv + NG * GPLANE);
+    uint64_t *empty = full + NB;
+
+    int b = blockIdx.x;
+    const int iz = b % k.ntz;
+    b /= k.ntz;
+    const int iy = b % k.nty;
+    const int ix = b / k.nty;
+    const int z0 = iz * TZ, y0 = iy * TY;
+    const int xs = k.xlo + ix * k.lx;
+    const int xe = min(xs + k.lx, k.xlo + k.xcount);
+    const int NIT = (xe - xs) + PRE;                // iterations: x = xs - PRE + it
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) {
+            b2ptx::mbar_init(&full[i], 1);
+            b2ptx::mbar_init(&empty[i], NCW);
+        }
+        b2ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        if (lane == 0) {
+            b2ptx::tma_prefetch_desc(&tm_u);
+            b2ptx::tma_prefetch_desc(&tm_v);
+            // batch `it` carries u plane (x+R) and v plane (x+R-1) of iteration x = xs-PRE+it.
+            // Its slots were last read in iteration it-3 (u plane x-3+R... see DESIGN.md §3.3).
+            for (int it = 0; it < NIT; ++it) {
+                const int x = xs - PRE + it;
+                if (it >= 3) {
+                    const int w = it - 3;
+                    b2ptx::mbar_wait(&empty[w % NB], (w / NB) & 1);
+                }
+                const int pu = x + R;                    // u plane index (relative to origin)
+                const int pv = x + R - 1;
+                const bool hv = pv >= xs - (R - 1);      // v planes below xs-R+1 are never used
+                b2ptx::mbar_arrive_expect_tx(&full[it % NB], (uint32_t)(PR * BZ * 4) * (hv ? 2u : 1u));
+                b2ptx::tma_load_4d(s_u + ((pu % NUU + NUU) % NUU) * PLANE, &tm_u, &full[it % NB],
+                                   k.oz + z0 - RZ, k.oy + y0 - R, k.ox + pu, k.slot0);
+                if (hv)
+                    b2ptx::tma_load_4d(s_v + ((pv % NUV + NUV) % NUV) * PLANE, &tm_v, &full[it % NB],
+                                       k.oz + z0 - RZ, k.oy + y0 - R, k.ox + pv, k.slot0);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int ty = tid / 16, tz4 = tid % 16;
+    const int gy = y0 + ty, gz = z0 + 4 * tz4;
+    const bool yok = gy < k.ny;
+    const int zcnt = yok ? min(max(k.nz - gz, 0), 4) : 0;
+    const int my_off = (ty + R) * BZ + RZ + 4 * tz4;          // own column in a u/v plane box
+    const int my_goff = (ty + H) * BZ + RZ + 4 * tz4;         // own column in a Gz plane
+    const long long gidx0 = (long long)(k.oy + gy) * k.sy + (k.oz + gz);
+
+    float4 uq[2 * R + 1];
+#pragma unroll
+    for (int i = 0; i <= 2 * R; ++i) uq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float wc = k.w2x[0] + k.w2y[0] + k.w2z[0];
+
+    // prefetched (one iteration ahead) u[t-1], v[t-1], A of the next output plane
+    float4 pf_u = make_float4(0, 0, 0, 0), pf_v = pf_u, pf_a = pf_u;
+
+    for (int it = 0; it < NIT; ++it) {
+        const int x = xs - PRE + it;
+        b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
+
+        // queue: uq[i] = u plane x - R + i   (newest = x + R)
+#pragma unroll
+        for (int i = 0; i < 2 * R; ++i) uq[i] = uq[i + 1];
+        uq[2 * R] = b2ptx::lds128(s_u + (((x + R) % NUU + NUU) % NUU) * PLANE + my_off);
+
+        // ---- stage A: Gz(u), Gz(v) at plane g = x + H - 1 ... see below: g = x + H - 1 + ... ----
+        // Gz at plane g needs f planes g-H+1 .. g+H; the newest complete one is g = x + R - H - ... :
+        // u planes up to x+R and v planes up to x+R-1 are present, so g = x + R - 1 - H = x + H - 1.
+        const int g = x + H - 1;
+        if (g >= xs - H) {
+            const float *up[R], *vp[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int pl = g - H + 1 + j;
+                up[j] = s_u + ((pl % NUU + NUU) % NUU) * PLANE;
+                vp[j] = s_v + ((pl % NUV + NUV) % NUV) * PLANE;
+            }
+            float *gu = s_gu + ((g % NG + NG) % NG) * GPLANE;
+            float *gv = s_gv + ((g % NG + NG) % NG) * GPLANE;
+            for (int grp = tid; grp < C::GGROUPS; grp += NCT) {
+                const int gr = grp / (BZ / 4);               // Gz row 0..TY+R-2  <-> y = y0 - H + gr
+                const int gc = grp % (BZ / 4);               // float4 column      <-> z = z0 - RZ + 4 gc
+                const int poff = (gr + R - H) * BZ + 4 * gc; // same point in a u/v plane box
+                float4 ru = make_float4(0, 0, 0, 0), rv = ru;
+                // x taps
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const float4 a = b2ptx::lds128(up[j] + poff);
+                    const float4 c = b2ptx::lds128(vp[j] + poff);
+                    const float w = k.cx * k.w1x[j];
+                    ru.x = fmaf(w, a.x, ru.x); ru.y = fmaf(w, a.y, ru.y); ru.z = fmaf(w, a.z, ru.z); ru.w = fmaf(w, a.w, ru.w);
+                    rv.x = fmaf(w, c.x, rv.x); rv.y = fmaf(w, c.y, rv.y); rv.z = fmaf(w, c.z, rv.z); rv.w = fmaf(w, c.w, rv.w);
+                }
+                // y taps (plane g = index H-1 in up/vp)
+                const float *uc = up[H - 1] + poff, *vc = vp[H - 1] + poff;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const float4 a = b2ptx::lds128(uc + (j - H + 1) * BZ);
+                    const float4 c = b2ptx::lds128(vc + (j - H + 1) * BZ);
+                    const float w = k.cy * k.w1y[j];
+                    ru.x = fmaf(w, a.x, ru.x); ru.y = fmaf(w, a.y, ru.y); ru.z = fmaf(w, a.z, ru.z); ru.w = fmaf(w, a.w, ru.w);
+                    rv.x = fmaf(w, c.x, rv.x); rv.y = fmaf(w, c.y, rv.y); rv.z = fmaf(w, c.z, rv.z); rv.w = fmaf(w, c.w, rv.w);
+                }
+                // z taps: row segment [-4, 8) around the 4 points (clamped at the box edges)
+                {
+                    float zu[12], zv[12];
+                    const bool hl = gc > 0, hr = gc < BZ / 4 - 1;
+                    const float4 lu = hl ? b2ptx::lds128(uc - 4) : make_float4(0, 0, 0, 0);
+                    const float4 cu = b2ptx::lds128(uc);
+                    const float4 rru = hr ? b2ptx::lds128(uc + 4) : make_float4(0, 0, 0, 0);
+                    const float4 lv = hl ? b2ptx::lds128(vc - 4) : make_float4(0, 0, 0, 0);
+                    const float4 cv = b2ptx::lds128(vc);
+                    const float4 rrv = hr ? b2ptx::lds128(vc + 4) : make_float4(0, 0, 0, 0);
+                    zu[0] = lu.x; zu[1] = lu.y; zu[2] = lu.z; zu[3] = lu.w; zu[4] = cu.x; zu[5] = cu.y; zu[6] = cu.z; zu[7] = cu.w;
+                    zu[8] = rru.x; zu[9] = rru.y; zu[10] = rru.z; zu[11] = rru.w;
+                    zv[0] = lv.x; zv[1] = lv.y; zv[2] = lv.z; zv[3] = lv.w; zv[4] = cv.x; zv[5] = cv.y; zv[6] = cv.z; zv[7] = cv.w;
+                    zv[8] = rrv.x; zv[9] = rrv.y; zv[10] = rrv.z; zv[11] = rrv.w;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        const float w = k.cz * k.w1z[j];
+                        const int o = 4 + j - H + 1;
+                        ru.x = fmaf(w, zu[o + 0], ru.x); ru.y = fmaf(w, zu[o + 1], ru.y);
+                        ru.z = fmaf(w, zu[o + 2], ru.z); ru.w = fmaf(w, zu[o + 3], ru.w);
+                        rv.x = fmaf(w, zv[o + 0], rv.x); rv.y = fmaf(w, zv[o + 1], rv.y);
+                        rv.z = fmaf(w, zv[o + 2], rv.z); rv.w = fmaf(w, zv[o + 3], rv.w);
+                    }
+                }
+                *reinterpret_cast<float4 *>(gu + gr * BZ + 4 * gc) = ru;
+                *reinterpret_cast<float4 *>(gv + gr * BZ + 4 * gc) = rv;
+            }
+        }
+        // Gz(plane g) written by all threads must be visible before its y/z neighbours are read
+        // (stage B of iteration x reads plane x = g - H + 1 ... written in an EARLIER iteration when
+        // H > 1; for H == 1 it is this iteration's plane). One CTA-wide barrier among consumers.
+        asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
+
+        // ---- stage B: output plane x ----
+        if (x >= xs) {
+            const float *cpl = s_u + ((x % NUU + NUU) % NUU) * PLANE + my_off;   // u plane x, own column
+            const float4 c = uq[R];
+            const float4 vcn = b2ptx::lds128(s_v + ((x % NUV + NUV) % NUV) * PLANE + my_off);
+            // Laplacian of u
+            float4 lap = make_float4(wc * c.x, wc * c.y, wc * c.z, wc * c.w);
+            {
+                const float4 l = b2ptx::lds128(cpl - 4), r = b2ptx::lds128(cpl + 4);
+                float zr[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int i = 1; i <= R; ++i) {
+                    lap.x = fmaf(k.w2z[i], zr[4 - i] + zr[4 + i], lap.x);
+                    lap.y = fmaf(k.w2z[i], zr[5 - i] + zr[5 + i], lap.y);
+                    lap.z = fmaf(k.w2z[i], zr[6 - i] + zr[6 + i], lap.z);
+                    lap.w = fmaf(k.w2z[i], zr[7 - i] + zr[7 + i], lap.w);
+                }
+            }
+#pragma unroll
+            for (int i = 1; i <= R; ++i) {
+                const float4 a = b2ptx::lds128(cpl - i * BZ), bb = b2ptx::lds128(cpl + i * BZ);
+                lap.x = fmaf(k.w2y[i], a.x + bb.x, lap.x); lap.y = fmaf(k.w2y[i], a.y + bb.y, lap.y);
+                lap.z = fmaf(k.w2y[i], a.z + bb.z, lap.z); lap.w = fmaf(k.w2y[i], a.w + bb.w, lap.w);
+            }
+#pragma unroll
+            for (int i = 1; i <= R; ++i) {
+                const float4 a = uq[R - i], bb = uq[R + i];
+                lap.x = fmaf(k.w2x[i], a.x + bb.x, lap.x); lap.y = fmaf(k.w2x[i], a.y + bb.y, lap.y);
+                lap.z = fmaf(k.w2x[i], a.z + bb.z, lap.z); lap.w = fmaf(k.w2x[i], a.w + bb.w, lap.w);
+            }
+            // Gzz(u), Gzz(v): outer half-node derivatives of Gz at offsets -H..H-1
+            float4 zu4 = make_float4(0, 0, 0, 0), zv4 = zu4;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {                       // x direction: planes x-H+j
+                const int pl = x - H + j;
+                const int so_ = ((pl % NG + NG) % NG) * GPLANE + my_goff;
+                const float4 a = b2ptx::lds128(s_gu + so_), bb = b2ptx::lds128(s_gv + so_);
+                const float w = k.cx * k.w1x[j];
+                zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
+                zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
+            }
+            const float *gpu_ = s_gu + ((x % NG + NG) % NG) * GPLANE + my_goff;
+            const float *gpv_ = s_gv + ((x % NG + NG) % NG) * GPLANE + my_goff;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {                       // y direction: rows y-H+j
+                const float4 a = b2ptx::lds128(gpu_ + (j - H) * BZ), bb = b2ptx::lds128(gpv_ + (j - H) * BZ);
+                const float w = k.cy * k.w1y[j];
+                zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
+                zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
+            }
+            {
+                const float4 lu = b2ptx::lds128(gpu_ - 4), cu = b2ptx::lds128(gpu_), ru_ = b2ptx::lds128(gpu_ + 4);
+                const float4 lv = b2ptx::lds128(gpv_ - 4), cv = b2ptx::lds128(gpv_), rv_ = b2ptx::lds128(gpv_ + 4);
+                float au[12] = {lu.x, lu.y, lu.z, lu.w, cu.x, cu.y, cu.z, cu.w, ru_.x, ru_.y, ru_.z, ru_.w};
+                float av[12] = {lv.x, lv.y, lv.z, lv.w, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y, rv_.z, rv_.w};
+#pragma unroll
+                for (int j = 0; j < R; ++j) {                   // z direction: offsets j-H
+                    const float w = k.cz * k.w1z[j];
+                    const int o = 4 + j - H;
+                    zu4.x = fmaf(w, au[o + 0], zu4.x); zu4.y = fmaf(w, au[o + 1], zu4.y);
+                    zu4.z = fmaf(w, au[o + 2], zu4.z); zu4.w = fmaf(w, au[o + 3], zu4.w);
+                    zv4.x = fmaf(w, av[o + 0], zv4.x); zv4.y = fmaf(w, av[o + 1], zv4.y);
+                    zv4.z = fmaf(w, av[o + 2], zv4.z); zv4.w = fmaf(w, av[o + 3], zv4.w);
+                }
+            }
+            const long long gi = (long long)(k.ox + x) * k.sx + gidx0;
+            float4 pu = pf_u, pv = pf_v, pa = pf_a;
+            if (x == xs && zcnt > 0) {      // first output plane of the chunk: nothing prefetched yet
+                if (zcnt == 4) {
+                    pu = *reinterpret_cast<const float4 *>(k.um + gi);
+                    pv = *reinterpret_cast<const float4 *>(k.vm + gi);
+                    pa = *reinterpret_cast<const float4 *>(k.A + gi);
+                } else {
+                    float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gi + i]; t[4 + i] = k.vm[gi + i]; t[8 + i] = k.A[gi + i]; }
+                    pu = make_float4(t[0], t[1], t[2], t[3]);
+                    pv = make_float4(t[4], t[5], t[6], t[7]);
+                    pa = make_float4(t[8], t[9], t[10], t[11]);
+                }
+            }
+            if (x + 1 < xe && zcnt > 0) {   // prefetch for the next plane
+                const long long gn = gi + k.sx;
+                if (zcnt == 4) {
+                    pf_u = *reinterpret_cast<const float4 *>(k.um + gn);
+                    pf_v = *reinterpret_cast<const float4 *>(k.vm + gn);
+                    pf_a = *reinterpret_cast<const float4 *>(k.A + gn);
+                } else {
+                    float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gn + i]; t[4 + i] = k.vm[gn + i]; t[8 + i] = k.A[gn + i]; }
+                    pf_u = make_float4(t[0], t[1], t[2], t[3]);
+                    pf_v = make_float4(t[4], t[5], t[6], t[7]);
+                    pf_a = make_float4(t[8], t[9], t[10], t[11]);
+                }
+            }
+            float4 ou, ov;
+#define B2_TTI_UPD(F)                                                              \
+            {                                                                      \
+                const float gh = lap.F - zu4.F;                                    \
+                const float H0 = fmaf(k.e2, gh, k.sd * zv4.F);                     \
+                const float Hz = fmaf(k.sd, gh, zv4.F);                            \
+                ou.F = fmaf(pa.F, fmaf(k.m_dt2, c.F - pu.F, H0), c.F);             \
+                ov.F = fmaf(pa.F, fmaf(k.m_dt2, vcn.F - pv.F, Hz), vcn.F);         \
+            }
+            B2_TTI_UPD(x) B2_TTI_UPD(y) B2_TTI_UPD(z) B2_TTI_UPD(w)
+#undef B2_TTI_UPD
+            if (zcnt == 4) {
+                *reinterpret_cast<float4 *>(k.u1 + gi) = ou;
+                *reinterpret_cast<float4 *>(k.v1 + gi) = ov;
+            } else if (zcnt > 0) {
+                const float tu[4] = {ou.x, ou.y, ou.z, ou.w}, tv[4] = {ov.x, ov.y, ov.z, ov.w};
+                for (int i = 0; i < zcnt; ++i) { k.u1[gi + i] = tu[i]; k.v1[gi + i] = tv[i]; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) b2ptx::mbar_arrive(&empty[it % NB]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_tti_coef(const float *__restrict__ damp, float m_dt2, float inv_dt, float *__restrict__ A, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) A[i] = 1.0f / (m_dt2 + (damp ? damp[i] * inv_dt : 0.f));
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int tti_make_tmap(CUtensorMap *tm, const void *base, const int *a, int tsize, int bz, int by) {
+    static PFN_encodeTiled enc = nullptr;
+    if (!enc) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled entry point not available");
+            return B2_ERR_DEVICE;
+        }
+        enc = reinterpret_cast<PFN_encodeTiled>(fp);
+    }
+    cuuint64_t gdim[4] = {(cuuint64_t)a[2], (cuuint64_t)a[1], (cuuint64_t)a[0], (cuuint64_t)tsize};
+    cuuint64_t gstr[3] = {gdim[0] * 4, gdim[0] * gdim[1] * 4, gdim[0] * gdim[1] * gdim[2] * 4};
+    cuuint32_t box[4] = {(cuuint32_t)bz, (cuuint32_t)by, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), gdim, gstr, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (tti) failed: %d", (int)r); return B2_ERR_DEVICE; }
+    return B2_OK;
+}
+
+template <int R> struct TtiTile;
+template <> struct TtiTile<2> { static constexpr int TY = 32; };
+template <> struct TtiTile<4> { static constexpr int TY = 28; };
+
+// scratch cached across calls
+static float *g_tti_scratch[3] = {nullptr, nullptr, nullptr};
+static size_t g_tti_scratch_elems[3] = {0, 0, 0};
+static int tti_scratch(int which, size_t elems, float **out) {
+    if (g_tti_scratch_elems[which] != elems) {
+        if (g_tti_scratch[which]) cudaFree(g_tti_scratch[which]);
+        g_tti_scratch[which] = nullptr;
+        g_tti_scratch_elems[which] = 0;
+        B2_CUDA(cudaMalloc(&g_tti_scratch[which], elems * sizeof(float)), B2_ERR_MEMORY);
+        g_tti_scratch_elems[which] = elems;
+    }
+    *out = g_tti_scratch[which];
+    return B2_OK;
+}
+
 int tti_plan_init(TtiPlan &p, int kernel) {
     p.kernel = kernel;
     if (p.R % 2 != 0 || p.R < 2 || p.R > B2_MAX_RADIUS) {
         set_error("tti: radius %d unsupported (space_order must be a multiple of 4, <= 16)", p.R);
         return B2_ERR_INVALID;
     }
-    const size_t bytes = p.slot_elems * sizeof(float);
-    B2_CUDA(cudaMalloc(&p.gzu, bytes), B2_ERR_MEMORY);
-    B2_CUDA(cudaMalloc(&p.gzv, bytes), B2_ERR_MEMORY);
+    bool ok = (p.R == 2 || p.R == 4) && (p.a[2] % 4 == 0) && (p.o[2] % 4 == 0) &&
+              ((uintptr_t)p.u % 16 == 0) && ((uintptr_t)p.v % 16 == 0) && (p.slot_elems % 4 == 0) &&
+              p.n[1] >= 8 && p.n[2] >= 16;
+    if (kernel == 1) ok = false;
+    if (kernel == 2 && !ok) {
+        set_error("tti: fused kernel forced but layout does not qualify (radius=%d a2=%d o2=%d)", p.R, p.a[2], p.o[2]);
+        return B2_ERR_INVALID;
+    }
+    p.use_fused = ok;
+    int rc;
+    if (ok) {
+        if ((rc = tti_scratch(0, p.slot_elems, &p.coefA))) return rc;
+        const float inv_dt = 1.0f / p.dt;
+        const float md = (1.0f / (p.vp * p.vp)) * (1.0f / (p.dt * p.dt));
+        k_tti_coef<<<148 * 8, 256, 0, stream()>>>(p.damp, md, inv_dt, p.coefA, p.slot_elems);
+        count_launch();
+        B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+        const int ty = p.R == 2 ? TtiTile<2>::TY : TtiTile<4>::TY;
+        if ((rc = tti_make_tmap(&p.tm_u, p.u, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
+        if ((rc = tti_make_tmap(&p.tm_v, p.v, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
+        return B2_OK;
+    }
+    if ((rc = tti_scratch(1, p.slot_elems, &p.gzu))) return rc;
+    if ((rc = tti_scratch(2, p.slot_elems, &p.gzv))) return rc;
     return B2_OK;
 }
 
 void tti_plan_free(TtiPlan &p) {
-    if (p.gzu) cudaFree(p.gzu);
-    if (p.gzv) cudaFree(p.gzv);
-    p.gzu = p.gzv = nullptr;
+    p.gzu = p.gzv = nullptr;       // scratch is cached in the library
+    p.coefA = nullptr;
+}
+
+static int env_int_tti(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int R>
+static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
+    constexpr int TY = TtiTile<R>::TY;
+    using C = TtiCfg<R, TY>;
+    auto kern = k_tti_fused<R, TY>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM), B2_ERR_LAUNCH);
+        attr_set = true;
+    }
+    TtiFK k;
+    k.u1 = p.u + (size_t)slot1 * p.slot_elems;
+    k.v1 = p.v + (size_t)slot1 * p.slot_elems;
+    k.um = p.u + (size_t)slotm * p.slot_elems;
+    k.vm = p.v + (size_t)slotm * p.slot_elems;
+    k.A = p.coefA;
+    k.sx = p.sx;
+    k.sy = p.sy;
+    k.ny = p.n[1];
+    k.nz = p.n[2];
+    k.ox = p.o[0];
+    k.oy = p.o[1];
+    k.oz = p.o[2];
+    k.xlo = xlo;
+    k.xcount = xcount;
+    k.ntz = (p.n[2] + C::TZ - 1) / C::TZ;
+    k.nty = (p.n[1] + TY - 1) / TY;
+    int lx = env_int_tti("B2_TTI_LX", 0);
+    if (lx <= 0) {
+        const int tiles = k.ntz * k.nty;
+        int nchunks = std::max(1, (148 * 12) / std::max(1, tiles));
+        lx = std::max(48, (xcount + nchunks - 1) / nchunks);
+        lx = std::min(lx, xcount);
+    }
+    k.lx = lx;
+    const int ntx = (xcount + lx - 1) / lx;
+    k.slot0 = slot0;
+    k.m_dt2 = (1.0f / (p.vp * p.vp)) * (1.0f / (p.dt * p.dt));
+    const float st = sinf(p.theta), ct = cosf(p.theta), sp = sinf(p.phi), cp = cosf(p.phi);
+    k.cx = st * cp;
+    k.cy = st * sp;
+    k.cz = ct;
+    k.e2 = 1.0f + 2.0f * p.epsilon;
+    k.sd = sqrtf(1.0f + 2.0f * p.delta);
+    for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
+    for (int i = 0; i < R; ++i) { k.w1x[i] = p.w1[0][i]; k.w1y[i] = p.w1[1][i]; k.w1z[i] = p.w1[2][i]; }
+    timing_begin();
+    kern<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
+    timing_end();
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
 }
 
 int tti_step(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
     if (xcount <= 0) return B2_OK;
+    if (p.use_fused)
+        return p.R == 2 ? tti_launch_fused<2>(p, slot0, slotm, slot1, xlo, xcount)
+                        : tti_launch_fused<4>(p, slot0, slotm, slot1, xlo, xcount);
     TtiK k;
     k.u0 = p.u + (size_t)slot0 * p.slot_elems;
     k.v0 = p.v + (size_t)slot0 * p.slot_elems;

@@ -21,6 +21,10 @@ struct TtiPlan {
     // scratch (two-pass kernel): Gz(u), Gz(v)
     float *gzu = nullptr, *gzv = nullptr;
     int kernel = 0;
+    // fused single-pass kernel
+    bool use_fused = false;
+    CUtensorMap tm_u, tm_v;
+    float *coefA = nullptr;
 };
 
 int tti_plan_init(TtiPlan &p, int kernel);

@@ -50,11 +50,12 @@ def test_iso_array_vp_vs_reference_golden():
 
 
 @pytest.mark.parametrize('name,so', [('tti3d_so8', 8), ('tti3d_so4', 4)])
-def test_tti_vs_reference_golden(name, so):
+@pytest.mark.parametrize('kernel', [1, 2])
+def test_tti_vs_reference_golden(name, so, kernel):
     g = load_golden(name)
     model, geometry, solver = _solver('tti', so, int(g['n']), int(g['nbl']), float(g['tn']))
     assert solver.op_fwd().backend == 'cuda-sm100a'
-    rec, u, v, _ = solver.forward()
+    rec, u, v, _ = solver.forward(kernel=kernel)
     assert rel_linf(u.data, g['u']) < 1e-4
     assert rel_linf(v.data, g['v']) < 1e-4
     assert rel_linf(rec.data, g['rec']) < 1e-4
@@ -102,6 +103,31 @@ def test_iso_tma_vs_oracle_larger(so, n, nbl):
     rec, u, _ = solver.forward(kernel=2)
     assert rel_linf(u.data_with_halo, p['u']) < 1e-5
     assert rel_linf(rec.data, p['rec']['data']) < 1e-5
+
+
+@pytest.mark.parametrize('so,n,nbl', [(8, 72, 12), (4, 60, 10)])
+def test_tti_fused_vs_oracle_larger(so, n, nbl):
+    """Fused TTI kernel vs the oracle with several tiles / partial tiles / several x-chunks."""
+    import os
+    p = iso_problem(n, nbl, so, 100.0)
+    eps, delta, theta, phi = 0.3, 0.2, 0.7, 0.35
+    dt = float(O.critical_dt(so, 3, 10.0, 1.5, eps_max=eps))
+    nt, tv = O.time_axis(0.0, 100.0, dt)
+    src = dict(p['src'], data=O.ricker(0.010, tv).astype(np.float32).reshape(-1, 1))
+    rec = dict(p['rec'], data=np.zeros((nt, n * n), dtype=np.float32))
+    u = np.zeros_like(p['u'])
+    v = np.zeros_like(p['u'])
+    w1 = [O.fd1_half_weights(so, 10.0)] * 3
+    O.tti_forward(u, v, so, p['w'], w1, dt, 1, nt - 2, p['damp'], 1.5, eps, delta, theta, phi, src=src, rec=rec)
+    os.environ['B2_TTI_LX'] = '24'
+    try:
+        model, geometry, solver = _solver('tti', so, n, nbl, 100.0)
+        r, uu, vv, _ = solver.forward(kernel=2)
+    finally:
+        del os.environ['B2_TTI_LX']
+    assert rel_linf(uu.data_with_halo, u) < 1e-4
+    assert rel_linf(vv.data_with_halo, v) < 1e-4
+    assert rel_linf(r.data, rec['data']) < 1e-4
 
 
 def test_host_staged_call_equals_resident_call():
