@@ -46,7 +46,7 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--grid', type=int, default=int(os.environ.get('B2_BENCH_GRID', 1024)),
                     help='grid points per dimension incl. absorbing layers')
-    ap.add_argument('--nt', type=int, default=int(os.environ.get('B2_BENCH_NT', 128)),
+    ap.add_argument('--nt', type=int, default=int(os.environ.get('B2_BENCH_NT', 256)),
                     help='time steps per Operator.apply')
     ap.add_argument('--space-order', type=int, default=8)
     ap.add_argument('--workload', default='iso', choices=['iso', 'tti'],
@@ -109,37 +109,86 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the reference's implementation of the path on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_run(so, grid_n, nt, threads):
-    """Time the reference's CPU code on a bounded sample: grid_n^3 points, nt time steps.
-    Returns (GPts/s, kind, sample description, cores)."""
+def usable_cores():
+    """Host threads this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, per = f.read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+_cpu_problem_cache = {}
+
+
+def _cpu_problem(so, grid_n, nts):
+    key = (so, grid_n, nts)
+    if key in _cpu_problem_cache:
+        return _cpu_problem_cache[key]
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     from oracle import oracle as O
-    from oracle import refrun
     from helpers import iso_problem
     nbl = 40 if grid_n >= 160 else 8
     n = grid_n - 2 * nbl
-    os.environ['OMP_NUM_THREADS'] = str(threads)
-    p = iso_problem(n, nbl, so, tn=1.0)            # geometry; time range overridden below
-    dt = p['dt']
-    nts = nt + 2
+    p = iso_problem(n, nbl, so, tn=1.0)            # geometry; the time range is overridden
     src = dict(p['src'], data=np.ascontiguousarray(np.resize(p['src']['data'], (nts, 1)).astype(np.float32)))
     rec_c = p['rec_coords'][:: max(1, len(p['rec_coords']) // 512)][:512]
     rgp, rw = O.tabulate(rec_c.astype(np.float32), p['origin'], p['spacing'])
     rec = dict(data=np.zeros((nts, len(rec_c)), dtype=np.float32), gp=rgp, w=rw, r=1)
-    pts = float(grid_n) ** 3 * nt
+    _cpu_problem_cache[key] = (p, src, rec)
+    return _cpu_problem_cache[key]
+
+
+def _cpu_run_once(so, grid_n, nt, threads):
+    from oracle import oracle as O
+    from oracle import refrun
+    p, src, rec = _cpu_problem(so, grid_n, 512)
     ref = refrun.load_forward(so)
+    t0 = time.perf_counter()
     if ref is not None:
         kind = 'reference'
-        t0 = time.perf_counter()
-        refrun.run_forward(ref, p['u'], p['damp'], 1.5, dt, 1, nt, src, rec, so, threads)
-        el = time.perf_counter() - t0
+        refrun.run_forward(ref, p['u'], p['damp'], 1.5, p['dt'], 1, nt, src, rec, so, threads)
     else:
         kind = 'port'
-        O.iso_forward(p['u'], so, p['w'], dt, 1, 2, damp=p['damp'], vp=1.5, src=src, rec=rec, fast=True)
-        t0 = time.perf_counter()
-        O.iso_forward(p['u'], so, p['w'], dt, 1, nt, damp=p['damp'], vp=1.5, src=src, rec=rec, fast=True)
-        el = time.perf_counter() - t0
-    sample = f"iso so={so} {grid_n}^3 x {nt} steps (same operator, smaller grid)"
+        os.environ['OMP_NUM_THREADS'] = str(threads)
+        O.iso_forward(p['u'], so, p['w'], p['dt'], 1, nt, damp=p['damp'], vp=1.5, src=src, rec=rec, fast=True)
+    return time.perf_counter() - t0, kind
+
+
+_cpu_threads_choice = {}
+
+
+def cpu_reference_run(so, grid_n, nt, threads=None, budget_s=12.0):
+    """Time the reference's CPU code path on a bounded sample of the workload: the same operator
+    (iso acoustic, same space order, source + 512 receivers) on a grid_n^3 grid. The thread count
+    is the best of a short probe over {all usable cores, 1/2, 1/4, ...} (the reference's own
+    advice is one thread per physical core, benchmarks/user/README.md:22-64); the number of time
+    steps is then sized to ~budget_s seconds. Returns (GPts/s, kind, sample, cores, seconds)."""
+    cores = usable_cores()
+    if threads is None:
+        if so not in _cpu_threads_choice:
+            cands = sorted({max(1, cores), max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8)},
+                           reverse=True)
+            best = None
+            _cpu_run_once(so, grid_n, 1, cands[0])                      # build / first touch
+            for c in cands:
+                el, _ = _cpu_run_once(so, grid_n, 2, c)
+                if best is None or el < best[0]:
+                    best = (el, c)
+            _cpu_threads_choice[so] = best[1], best[0] / 2
+        threads, per_step = _cpu_threads_choice[so]
+        nt = int(max(4, min(500, budget_s / max(per_step, 1e-4))))
+    el, kind = _cpu_run_once(so, grid_n, nt, threads)
+    pts = float(grid_n) ** 3 * nt
+    sample = (f"iso so={so} {grid_n}^3 x {nt} steps (same operator, smaller grid), {threads} of "
+              f"{cores} usable host threads")
     return pts / el / 1e9, kind, sample, threads, el
 
 
@@ -147,24 +196,21 @@ def run_reference_arm(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    gp, kind, sample, cores, el = None, None, None, None, None
     vals = []
-    grid_n, nt = 384, 8
+    budget = max(3.0, min(15.0, 150.0 / max(1, a.warmup + a.steps)))   # whole arm within minutes
     for i in range(a.warmup + a.steps):
-        gp, kind, sample, cores, el = cpu_reference_run(a.space_order, grid_n, nt, threads)
+        gp, kind, sample, cores, el = cpu_reference_run(a.space_order, 384, 8, budget_s=budget)
         if i >= a.warmup:
             vals.append((gp, el))
-        if i == 0 and el > 20:          # keep the whole arm within a few minutes
-            nt = max(2, nt // 2)
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([e for _, e in vals])) * 1e3
-    line = {"impl": "reference", "metric": "GPts/s (3D isotropic acoustic forward, so=%d)" % a.space_order,
+    line = {"impl": "reference", "metric": "GPts/s (3D isotropic acoustic forward, so=%d, 1024^3 per GPU)" % a.space_order,
             "value": value, "unit": "GPts/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"3D iso acoustic so={a.space_order}, CPU sample {sample}",
-                       "l2": "inputs larger than cache"},
+            "config": {"workload": f"3D isotropic acoustic so={a.space_order}; the reference's CPU (OpenMP) "
+                                   f"path on a bounded sample: {sample}",
+                       "l2": "inputs larger than the CPU caches"},
             "cpu_baseline": {"value": value, "unit": "GPts/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "GPts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -264,10 +310,16 @@ def main():
     if nranks > 1:
         pts_launch = None
     roof = None
+    traffic = None
+    try:   # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            traffic = json.load(f).get(f"{a.workload}_so{so}_{G}")
+    except Exception:
+        traffic = None
     if nl.value and k_ms > 0 and nranks == 1:
         ach = b_alg * pts_launch / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                 "kernel": "k_tti_*" if tti else "k_iso_tma", "launch_ms": k_ms, "launches_timed": int(nl.value)}
 
     e2e = None
@@ -287,8 +339,7 @@ def main():
     cpu = None
     if rank == 0 and nranks == 1 and not a.no_cpu:
         try:
-            threads = os.cpu_count() or 1
-            gp, kind, sample, cores, el = cpu_reference_run(so, 384, 8, threads)
+            gp, kind, sample, cores, el = cpu_reference_run(so, 384, 8, budget_s=10.0)
             cpu = {"value": gp, "unit": "GPts/s", "cores": cores, "kind": kind, "sample": sample}
         except Exception as e:                                           # never hide the GPU number
             cpu = {"value": None, "unit": "GPts/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}

@@ -112,6 +112,13 @@ __global__ void __launch_bounds__(256) k_tti_update(TtiK k) {
 //                   queue, y/z taps from the shared plane), the outer half-node derivatives of
 //                   Gz from the shared Gz ring, the coupled update, 16-byte stores.
 // The update uses the tabulated A = 1/(m/dt^2 + damp/dt): f+ = f + A (m/dt^2 (f - f-) + H).
+__device__ __forceinline__ void f4fma_(float4 &acc, float w, const float4 &v) {
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+}
+
 struct TtiFK {
     float *__restrict__ u1;
     float *__restrict__ v1;
@@ -128,7 +135,7 @@ struct TtiFK {
     float cx, cy, cz;          // sin(th)cos(ph), sin(th)sin(ph), cos(th)
     float e2, sd;              // 1+2eps, sqrt(1+2delta)
     float w2x[5], w2y[5], w2z[5];
-    float w1x[4], w1y[4], w1z[4];
+    float w1x[4], w1y[4], w1z[4];      // already multiplied by cx, cy, cz
 };
 
 template <int R, int TY>
@@ -231,94 +238,91 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     for (int i = 0; i <= 2 * R; ++i) uq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float wc = k.w2x[0] + k.w2y[0] + k.w2z[0];
 
-    // prefetched (one iteration ahead) u[t-1], v[t-1], A of the next output plane
-    float4 pf_u = make_float4(0, 0, 0, 0), pf_v = pf_u, pf_a = pf_u;
+    // ring positions of plane x (updated incrementally; x starts at xs - PRE)
+    int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
+        ig = ((xs - PRE) % NG + NG) % NG;
+    auto wrap = [](int v, int n) { return v >= n ? v - n : v; };
 
     for (int it = 0; it < NIT; ++it) {
         const int x = xs - PRE + it;
+        // u[t-1], v[t-1], A of the output plane: issued first so that stage A and most of stage B
+        // hide their latency (profiles/r1c: loads issued one statement before use stalled 28 %)
+        float4 pu = make_float4(0, 0, 0, 0), pv = pu, pa = pu;
+        const long long gi = (long long)(k.ox + x) * k.sx + gidx0;
+        if (x >= xs && zcnt > 0) {
+            if (zcnt == 4) {
+                pu = *reinterpret_cast<const float4 *>(k.um + gi);
+                pv = *reinterpret_cast<const float4 *>(k.vm + gi);
+                pa = *reinterpret_cast<const float4 *>(k.A + gi);
+            } else {
+                float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gi + i]; t[4 + i] = k.vm[gi + i]; t[8 + i] = k.A[gi + i]; }
+                pu = make_float4(t[0], t[1], t[2], t[3]);
+                pv = make_float4(t[4], t[5], t[6], t[7]);
+                pa = make_float4(t[8], t[9], t[10], t[11]);
+            }
+        }
         b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
 
         // queue: uq[i] = u plane x - R + i   (newest = x + R)
 #pragma unroll
         for (int i = 0; i < 2 * R; ++i) uq[i] = uq[i + 1];
-        uq[2 * R] = b2ptx::lds128(s_u + (((x + R) % NUU + NUU) % NUU) * PLANE + my_off);
+        uq[2 * R] = b2ptx::lds128(s_u + wrap(iu + R, NUU) * PLANE + my_off);
 
-        // ---- stage A: Gz(u), Gz(v) at plane g = x + H - 1 ... see below: g = x + H - 1 + ... ----
-        // Gz at plane g needs f planes g-H+1 .. g+H; the newest complete one is g = x + R - H - ... :
-        // u planes up to x+R and v planes up to x+R-1 are present, so g = x + R - 1 - H = x + H - 1.
-        const int g = x + H - 1;
-        if (g >= xs - H) {
+        // ---- stage A: Gz(u), Gz(v) at plane g = x + H - 1 (needs f planes x .. x+R-1) ----
+        // Work items are (field, float4-group) pairs of the tile extended by [-H, H-1], dealt
+        // round-robin so that no thread gets more than one item above the average.
+        if (x + H - 1 >= xs - H) {
             const float *up[R], *vp[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                const int pl = g - H + 1 + j;
-                up[j] = s_u + ((pl % NUU + NUU) % NUU) * PLANE;
-                vp[j] = s_v + ((pl % NUV + NUV) % NUV) * PLANE;
+                up[j] = s_u + wrap(iu + j, NUU) * PLANE;
+                vp[j] = s_v + wrap(iv + j, NUV) * PLANE;
             }
-            float *gu = s_gu + ((g % NG + NG) % NG) * GPLANE;
-            float *gv = s_gv + ((g % NG + NG) % NG) * GPLANE;
-            for (int grp = tid; grp < C::GGROUPS; grp += NCT) {
+            const int sgz = wrap(ig + H - 1, NG) * GPLANE;
+            for (int task = tid; task < 2 * C::GGROUPS; task += NCT) {
+                const bool fv = task >= C::GGROUPS;
+                const int grp = fv ? task - C::GGROUPS : task;
                 const int gr = grp / (BZ / 4);               // Gz row 0..TY+R-2  <-> y = y0 - H + gr
-                const int gc = grp % (BZ / 4);               // float4 column      <-> z = z0 - RZ + 4 gc
+                const int gc = grp - gr * (BZ / 4);          // float4 column      <-> z = z0 - RZ + 4 gc
                 const int poff = (gr + R - H) * BZ + 4 * gc; // same point in a u/v plane box
-                float4 ru = make_float4(0, 0, 0, 0), rv = ru;
-                // x taps
+                float4 rr = make_float4(0, 0, 0, 0);
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const float4 a = b2ptx::lds128(up[j] + poff);
-                    const float4 c = b2ptx::lds128(vp[j] + poff);
-                    const float w = k.cx * k.w1x[j];
-                    ru.x = fmaf(w, a.x, ru.x); ru.y = fmaf(w, a.y, ru.y); ru.z = fmaf(w, a.z, ru.z); ru.w = fmaf(w, a.w, ru.w);
-                    rv.x = fmaf(w, c.x, rv.x); rv.y = fmaf(w, c.y, rv.y); rv.z = fmaf(w, c.z, rv.z); rv.w = fmaf(w, c.w, rv.w);
+                for (int j = 0; j < R; ++j) {                // x taps
+                    const float4 a = b2ptx::lds128((fv ? vp[j] : up[j]) + poff);
+                    f4fma_(rr, k.w1x[j], a);
                 }
-                // y taps (plane g = index H-1 in up/vp)
-                const float *uc = up[H - 1] + poff, *vc = vp[H - 1] + poff;
+                const float *fc = (fv ? vp[H - 1] : up[H - 1]) + poff;     // plane g, this point
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const float4 a = b2ptx::lds128(uc + (j - H + 1) * BZ);
-                    const float4 c = b2ptx::lds128(vc + (j - H + 1) * BZ);
-                    const float w = k.cy * k.w1y[j];
-                    ru.x = fmaf(w, a.x, ru.x); ru.y = fmaf(w, a.y, ru.y); ru.z = fmaf(w, a.z, ru.z); ru.w = fmaf(w, a.w, ru.w);
-                    rv.x = fmaf(w, c.x, rv.x); rv.y = fmaf(w, c.y, rv.y); rv.z = fmaf(w, c.z, rv.z); rv.w = fmaf(w, c.w, rv.w);
+                for (int j = 0; j < R; ++j) {                // y taps
+                    const float4 a = b2ptx::lds128(fc + (j - H + 1) * BZ);
+                    f4fma_(rr, k.w1y[j], a);
                 }
-                // z taps: row segment [-4, 8) around the 4 points (clamped at the box edges)
-                {
-                    float zu[12], zv[12];
-                    const bool hl = gc > 0, hr = gc < BZ / 4 - 1;
-                    const float4 lu = hl ? b2ptx::lds128(uc - 4) : make_float4(0, 0, 0, 0);
-                    const float4 cu = b2ptx::lds128(uc);
-                    const float4 rru = hr ? b2ptx::lds128(uc + 4) : make_float4(0, 0, 0, 0);
-                    const float4 lv = hl ? b2ptx::lds128(vc - 4) : make_float4(0, 0, 0, 0);
-                    const float4 cv = b2ptx::lds128(vc);
-                    const float4 rrv = hr ? b2ptx::lds128(vc + 4) : make_float4(0, 0, 0, 0);
-                    zu[0] = lu.x; zu[1] = lu.y; zu[2] = lu.z; zu[3] = lu.w; zu[4] = cu.x; zu[5] = cu.y; zu[6] = cu.z; zu[7] = cu.w;
-                    zu[8] = rru.x; zu[9] = rru.y; zu[10] = rru.z; zu[11] = rru.w;
-                    zv[0] = lv.x; zv[1] = lv.y; zv[2] = lv.z; zv[3] = lv.w; zv[4] = cv.x; zv[5] = cv.y; zv[6] = cv.z; zv[7] = cv.w;
-                    zv[8] = rrv.x; zv[9] = rrv.y; zv[10] = rrv.z; zv[11] = rrv.w;
+                {                                            // z taps: segment [-4, 8) around the group
+                    const float4 l = gc > 0 ? b2ptx::lds128(fc - 4) : make_float4(0, 0, 0, 0);
+                    const float4 c = b2ptx::lds128(fc);
+                    const float4 r = gc < BZ / 4 - 1 ? b2ptx::lds128(fc + 4) : make_float4(0, 0, 0, 0);
+                    const float zz[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
-                        const float w = k.cz * k.w1z[j];
                         const int o = 4 + j - H + 1;
-                        ru.x = fmaf(w, zu[o + 0], ru.x); ru.y = fmaf(w, zu[o + 1], ru.y);
-                        ru.z = fmaf(w, zu[o + 2], ru.z); ru.w = fmaf(w, zu[o + 3], ru.w);
-                        rv.x = fmaf(w, zv[o + 0], rv.x); rv.y = fmaf(w, zv[o + 1], rv.y);
-                        rv.z = fmaf(w, zv[o + 2], rv.z); rv.w = fmaf(w, zv[o + 3], rv.w);
+                        rr.x = fmaf(k.w1z[j], zz[o + 0], rr.x); rr.y = fmaf(k.w1z[j], zz[o + 1], rr.y);
+                        rr.z = fmaf(k.w1z[j], zz[o + 2], rr.z); rr.w = fmaf(k.w1z[j], zz[o + 3], rr.w);
                     }
                 }
-                *reinterpret_cast<float4 *>(gu + gr * BZ + 4 * gc) = ru;
-                *reinterpret_cast<float4 *>(gv + gr * BZ + 4 * gc) = rv;
+                *reinterpret_cast<float4 *>((fv ? s_gv : s_gu) + sgz + gr * BZ + 4 * gc) = rr;
             }
         }
-        // Gz(plane g) written by all threads must be visible before its y/z neighbours are read
-        // (stage B of iteration x reads plane x = g - H + 1 ... written in an EARLIER iteration when
-        // H > 1; for H == 1 it is this iteration's plane). One CTA-wide barrier among consumers.
+        // Gz written by all threads must be visible before its y/z neighbours are read; one barrier
+        // per iteration among the consumer warps (the Gz ring has R+1 planes so that the next
+        // iteration's stage A never overwrites a plane that stage B of this one still reads).
         asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
 
         // ---- stage B: output plane x ----
         if (x >= xs) {
-            const float *cpl = s_u + ((x % NUU + NUU) % NUU) * PLANE + my_off;   // u plane x, own column
+            const float *cpl = s_u + iu * PLANE + my_off;   // u plane x, own column
             const float4 c = uq[R];
-            const float4 vcn = b2ptx::lds128(s_v + ((x % NUV + NUV) % NUV) * PLANE + my_off);
+            const float4 vcn = b2ptx::lds128(s_v + iv * PLANE + my_off);
             // Laplacian of u
             float4 lap = make_float4(wc * c.x, wc * c.y, wc * c.z, wc * c.w);
             {
@@ -348,19 +352,20 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             float4 zu4 = make_float4(0, 0, 0, 0), zv4 = zu4;
 #pragma unroll
             for (int j = 0; j < R; ++j) {                       // x direction: planes x-H+j
-                const int pl = x - H + j;
-                const int so_ = ((pl % NG + NG) % NG) * GPLANE + my_goff;
+                int sl_ = ig - H + j;
+                sl_ = sl_ < 0 ? sl_ + NG : (sl_ >= NG ? sl_ - NG : sl_);
+                const int so_ = sl_ * GPLANE + my_goff;
                 const float4 a = b2ptx::lds128(s_gu + so_), bb = b2ptx::lds128(s_gv + so_);
-                const float w = k.cx * k.w1x[j];
+                const float w = k.w1x[j];
                 zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
                 zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
             }
-            const float *gpu_ = s_gu + ((x % NG + NG) % NG) * GPLANE + my_goff;
-            const float *gpv_ = s_gv + ((x % NG + NG) % NG) * GPLANE + my_goff;
+            const float *gpu_ = s_gu + ig * GPLANE + my_goff;
+            const float *gpv_ = s_gv + ig * GPLANE + my_goff;
 #pragma unroll
             for (int j = 0; j < R; ++j) {                       // y direction: rows y-H+j
                 const float4 a = b2ptx::lds128(gpu_ + (j - H) * BZ), bb = b2ptx::lds128(gpv_ + (j - H) * BZ);
-                const float w = k.cy * k.w1y[j];
+                const float w = k.w1y[j];
                 zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
                 zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
             }
@@ -371,41 +376,12 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 float av[12] = {lv.x, lv.y, lv.z, lv.w, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y, rv_.z, rv_.w};
 #pragma unroll
                 for (int j = 0; j < R; ++j) {                   // z direction: offsets j-H
-                    const float w = k.cz * k.w1z[j];
+                    const float w = k.w1z[j];
                     const int o = 4 + j - H;
                     zu4.x = fmaf(w, au[o + 0], zu4.x); zu4.y = fmaf(w, au[o + 1], zu4.y);
                     zu4.z = fmaf(w, au[o + 2], zu4.z); zu4.w = fmaf(w, au[o + 3], zu4.w);
                     zv4.x = fmaf(w, av[o + 0], zv4.x); zv4.y = fmaf(w, av[o + 1], zv4.y);
                     zv4.z = fmaf(w, av[o + 2], zv4.z); zv4.w = fmaf(w, av[o + 3], zv4.w);
-                }
-            }
-            const long long gi = (long long)(k.ox + x) * k.sx + gidx0;
-            float4 pu = pf_u, pv = pf_v, pa = pf_a;
-            if (x == xs && zcnt > 0) {      // first output plane of the chunk: nothing prefetched yet
-                if (zcnt == 4) {
-                    pu = *reinterpret_cast<const float4 *>(k.um + gi);
-                    pv = *reinterpret_cast<const float4 *>(k.vm + gi);
-                    pa = *reinterpret_cast<const float4 *>(k.A + gi);
-                } else {
-                    float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gi + i]; t[4 + i] = k.vm[gi + i]; t[8 + i] = k.A[gi + i]; }
-                    pu = make_float4(t[0], t[1], t[2], t[3]);
-                    pv = make_float4(t[4], t[5], t[6], t[7]);
-                    pa = make_float4(t[8], t[9], t[10], t[11]);
-                }
-            }
-            if (x + 1 < xe && zcnt > 0) {   // prefetch for the next plane
-                const long long gn = gi + k.sx;
-                if (zcnt == 4) {
-                    pf_u = *reinterpret_cast<const float4 *>(k.um + gn);
-                    pf_v = *reinterpret_cast<const float4 *>(k.vm + gn);
-                    pf_a = *reinterpret_cast<const float4 *>(k.A + gn);
-                } else {
-                    float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gn + i]; t[4 + i] = k.vm[gn + i]; t[8 + i] = k.A[gn + i]; }
-                    pf_u = make_float4(t[0], t[1], t[2], t[3]);
-                    pf_v = make_float4(t[4], t[5], t[6], t[7]);
-                    pf_a = make_float4(t[8], t[9], t[10], t[11]);
                 }
             }
             float4 ou, ov;
@@ -429,6 +405,9 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         }
         __syncwarp();
         if (lane == 0) b2ptx::mbar_arrive(&empty[it % NB]);
+        iu = wrap(iu + 1, NUU);
+        iv = wrap(iv + 1, NUV);
+        ig = wrap(ig + 1, NG);
     }
 }
 
@@ -574,7 +553,7 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     k.e2 = 1.0f + 2.0f * p.epsilon;
     k.sd = sqrtf(1.0f + 2.0f * p.delta);
     for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
-    for (int i = 0; i < R; ++i) { k.w1x[i] = p.w1[0][i]; k.w1y[i] = p.w1[1][i]; k.w1z[i] = p.w1[2][i]; }
+    for (int i = 0; i < R; ++i) { k.w1x[i] = k.cx * p.w1[0][i]; k.w1y[i] = k.cy * p.w1[1][i]; k.w1z[i] = k.cz * p.w1[2][i]; }
     timing_begin();
     kern<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
     timing_end();
