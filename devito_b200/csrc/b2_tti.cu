@@ -238,6 +238,23 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     for (int i = 0; i <= 2 * R; ++i) uq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float wc = k.w2x[0] + k.w2y[0] + k.w2z[0];
 
+    // stage-A work items of this thread: (field, float4-group) pairs of the tile extended by
+    // [-H, H-1], dealt round-robin; packed as poff | fv<<16 | has_left<<17 | has_right<<18 | valid<<19
+    constexpr int NTASK = (2 * C::GGROUPS + NCT - 1) / NCT;
+    int tdesc[NTASK];
+#pragma unroll
+    for (int t = 0; t < NTASK; ++t) {
+        const int task = tid + t * NCT;
+        const bool valid = task < 2 * C::GGROUPS;
+        const bool fv = task >= C::GGROUPS;
+        const int grp = fv ? task - C::GGROUPS : task;
+        const int gr = grp / (BZ / 4), gc = grp - gr * (BZ / 4);
+        const int poff = (gr + R - H) * BZ + 4 * gc;
+        tdesc[t] = poff | (fv ? 1 << 16 : 0) | (gc > 0 ? 1 << 17 : 0) | (gc < BZ / 4 - 1 ? 1 << 18 : 0) |
+                   (valid ? 1 << 19 : 0);
+    }
+    long long gi = (long long)(k.ox + xs - PRE) * k.sx + gidx0;
+
     // ring positions of plane x (updated incrementally; x starts at xs - PRE)
     int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
         ig = ((xs - PRE) % NG + NG) % NG;
@@ -248,7 +265,6 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         // u[t-1], v[t-1], A of the output plane: issued first so that stage A and most of stage B
         // hide their latency (profiles/r1c: loads issued one statement before use stalled 28 %)
         float4 pu = make_float4(0, 0, 0, 0), pv = pu, pa = pu;
-        const long long gi = (long long)(k.ox + x) * k.sx + gidx0;
         if (x >= xs && zcnt > 0) {
             if (zcnt == 4) {
                 pu = *reinterpret_cast<const float4 *>(k.um + gi);
@@ -280,12 +296,12 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 vp[j] = s_v + wrap(iv + j, NUV) * PLANE;
             }
             const int sgz = wrap(ig + H - 1, NG) * GPLANE;
-            for (int task = tid; task < 2 * C::GGROUPS; task += NCT) {
-                const bool fv = task >= C::GGROUPS;
-                const int grp = fv ? task - C::GGROUPS : task;
-                const int gr = grp / (BZ / 4);               // Gz row 0..TY+R-2  <-> y = y0 - H + gr
-                const int gc = grp - gr * (BZ / 4);          // float4 column      <-> z = z0 - RZ + 4 gc
-                const int poff = (gr + R - H) * BZ + 4 * gc; // same point in a u/v plane box
+#pragma unroll
+            for (int t = 0; t < NTASK; ++t) {
+                const int d = tdesc[t];
+                if (!(d & (1 << 19))) continue;
+                const bool fv = d & (1 << 16);
+                const int poff = d & 0xffff;
                 float4 rr = make_float4(0, 0, 0, 0);
 #pragma unroll
                 for (int j = 0; j < R; ++j) {                // x taps
@@ -299,9 +315,9 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                     f4fma_(rr, k.w1y[j], a);
                 }
                 {                                            // z taps: segment [-4, 8) around the group
-                    const float4 l = gc > 0 ? b2ptx::lds128(fc - 4) : make_float4(0, 0, 0, 0);
+                    const float4 l = (d & (1 << 17)) ? b2ptx::lds128(fc - 4) : make_float4(0, 0, 0, 0);
                     const float4 c = b2ptx::lds128(fc);
-                    const float4 r = gc < BZ / 4 - 1 ? b2ptx::lds128(fc + 4) : make_float4(0, 0, 0, 0);
+                    const float4 r = (d & (1 << 18)) ? b2ptx::lds128(fc + 4) : make_float4(0, 0, 0, 0);
                     const float zz[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
@@ -310,7 +326,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                         rr.z = fmaf(k.w1z[j], zz[o + 2], rr.z); rr.w = fmaf(k.w1z[j], zz[o + 3], rr.w);
                     }
                 }
-                *reinterpret_cast<float4 *>((fv ? s_gv : s_gu) + sgz + gr * BZ + 4 * gc) = rr;
+                *reinterpret_cast<float4 *>((fv ? s_gv : s_gu) + sgz + poff - (R - H) * BZ) = rr;
             }
         }
         // Gz written by all threads must be visible before its y/z neighbours are read; one barrier
@@ -408,6 +424,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         iu = wrap(iu + 1, NUU);
         iv = wrap(iv + 1, NUV);
         ig = wrap(ig + 1, NG);
+        gi += k.sx;
     }
 }
 
