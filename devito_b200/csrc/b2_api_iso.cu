@@ -172,10 +172,12 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (timing && !per_step_events) ev_begin = se.next();
 
-    for (int time = a->time_m; time <= a->time_M; ++time) {
+    const int dir = a->adjoint ? -1 : 1;
+    for (int time = a->adjoint ? a->time_M : a->time_m; a->adjoint ? time >= a->time_m : time <= a->time_M;
+         time += dir) {
         const int t0 = ((time % T) + T) % T;
-        const int t1 = (((time + 1) % T) + T) % T;
-        const int t2 = (((time - 1) % T) + T) % T;
+        const int t1 = (((time + dir) % T) + T) % T;     // written
+        const int t2 = (((time - dir) % T) + T) % T;     // the other time level read
         if (per_step_events) se.next();
         if (a->halo) {
             if ((rc = halo_exchange_and_step_iso(a->halo, p, t0, t2, t1))) return cleanup(rc);
@@ -190,7 +192,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         const float *fr = p.u + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
         if ((rc = launch_interp(rec, g, fr, nullptr, time))) return cleanup(rc);
         if (per_step_events) se.next();
-        if (a->errctl && ((time - a->time_m) % 100 == 99 || time == a->time_M)) {
+        if (a->errctl && ((time - a->time_m) % 100 == 99 || time == (a->adjoint ? a->time_m : a->time_M))) {
             bool bad = false;
             if ((rc = check_finite(f1, p.slot_elems, bad))) return cleanup(rc);
             if (bad) { set_error("NaN/Inf detected in u at time=%d", time); return cleanup(B2_ERR_NAN); }

@@ -171,6 +171,7 @@ class Operator:
         self._subs = {as_expr(k): v for k, v in (subs or {}).items()}
         self._plan = None
         self._why_not = None
+        self._dirn = 1
         try:
             self._plan = self._recognise()
         except _Unrecognised as e:
@@ -198,8 +199,9 @@ class Operator:
                 raise _Unrecognised("lhs is not a TimeFunction")
             f = lhs.function
             so = _space_offsets(lhs, None)
-            if so is None or so[0] != 1 or any(so[1]):
-                raise _Unrecognised("lhs is not `f.forward`")
+            if so is None or so[0] not in (1, -1) or any(so[1]):
+                raise _Unrecognised("lhs is not `f.forward` / `f.backward`")
+            self._dirn = so[0]
             if f.time_order != 2:
                 raise _Unrecognised("time_order != 2")
             if e.subdomain is not None and any(d.is_Sub for d in e.subdomain.dimensions):
@@ -210,6 +212,8 @@ class Operator:
         if len(updates) == 1:
             return self._recognise_iso(updates[0], injs, itps)
         if len(updates) == 2:
+            if self._dirn != 1:
+                raise _Unrecognised("adjoint TTI is not on the fast path")
             return self._recognise_tti(updates, injs, itps)
         raise _Unrecognised("unsupported number of update equations")
 
@@ -293,7 +297,8 @@ class Operator:
                     o = [0] * nd
                     o[d] = s
                     star.add((0, tuple(o)))
-        if set(keyed) != star | {(-1, zero)}:
+        dirn = self._dirn
+        if set(keyed) != star | {(-dirn, zero)}:
             raise _Unrecognised("stencil support is not the isotropic star")
         funcs, consts, syms = self._leaves(keyed.values())
         for a in funcs:
@@ -317,7 +322,7 @@ class Operator:
             if cz == 0:
                 raise _Unrecognised("degenerate stencil")
             den = w[-1][1] / cz
-            m_eff = -c[(-1, zero)] * dt * dt * den
+            m_eff = -c[(-dirn, zero)] * dt * dt * den
             d_eff = (den - m_eff / (dt * dt)) * dt
             if roles is None:
                 roles = self._iso_roles(m_eff, d_eff, den, vals, funcs, consts)
@@ -326,7 +331,7 @@ class Operator:
             m_chk = self._role_value(m_role, vals)
             d_chk = self._role_value(d_role, vals) if d_role is not None else 0.0
             den_chk = m_chk / (dt * dt) + d_chk / dt
-            pred = {(-1, zero): -m_chk / (dt * dt) / den_chk,
+            pred = {(-dirn, zero): -m_chk / (dt * dt) / den_chk,
                     (0, zero): (2 * m_chk / (dt * dt) + d_chk / dt + sum(wd[0] for wd in w)) / den_chk}
             for d in range(nd):
                 for k in range(1, R + 1):
@@ -340,7 +345,7 @@ class Operator:
         m_role, d_role = roles
         plan = {'kind': 'iso', 'u': u, 'grid': grid, 'so': so, 'R': R, 'w': w,
                 'm_role': m_role, 'damp': d_role[1] if d_role is not None else None,
-                'dt': dtsym, 'src': None, 'rec': None, 'rec_toff': 0}
+                'dt': dtsym, 'src': None, 'rec': None, 'rec_toff': 0, 'adjoint': dirn == -1}
         self._attach_sparse(plan, injs, itps, [u], funcs, consts, syms, m_role)
         return plan
 
@@ -406,8 +411,8 @@ class Operator:
                 raise _Unrecognised("injection targets differ from the updated fields")
             for a, ex in zip(inj.fields, inj.exprs):
                 k = _space_offsets(a, None)
-                if k is None or k[0] != 1 or any(k[1]):
-                    raise _Unrecognised("injection must target `f.forward`")
+                if k is None or k[0] != self._dirn or any(k[1]):
+                    raise _Unrecognised("injection must target the updated time level")
                 ex = ex.evaluate.subs(self._subs) if self._subs else ex.evaluate
                 f2, c2, s2 = self._leaves([ex])
                 for probe in range(2):
@@ -445,8 +450,8 @@ class Operator:
             toffs = set()
             for a in accs:
                 k = _space_offsets(a, None)
-                if k is None or any(k[1]) or k[0] not in (0, 1):
-                    raise _Unrecognised("interpolated access must be f or f.forward")
+                if k is None or any(k[1]) or k[0] not in (0, self._dirn):
+                    raise _Unrecognised("interpolated access must be f or the updated time level")
                 toffs.add(k[0])
             if len(toffs) != 1:
                 raise _Unrecognised("mixed time offsets in the interpolated expression")
@@ -456,7 +461,7 @@ class Operator:
             if abs(got - sum(vals.values())) > 1e-12:
                 raise _Unrecognised("interpolated expression is not a plain sum")
             plan['rec'] = sf
-            plan['rec_toff'] = toffs.pop()
+            plan['rec_toff'] = 1 if toffs.pop() != 0 else 0
 
     # -- TTI -------------------------------------------------------------------------------------
     def _recognise_tti(self, updates, injs, itps):
@@ -911,6 +916,7 @@ class Operator:
         a.halo = distributed.halo_context(dev) if grid.distributor.is_parallel else None
         timers = L_.Profiler()
         a.timers = ctypes.pointer(timers)
+        a.adjoint = 1 if p.get('adjoint') else 0
         if p.get('inject_literal'):
             # injection used a literal dt**2 (not the `dt` symbol): it must agree with runtime dt
             if abs(p['inject_dt2'] - a.dt * a.dt) > 1e-5 * p['inject_dt2']:

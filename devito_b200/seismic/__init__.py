@@ -5,5 +5,6 @@ from .source import (TimeAxis, PointSource, Receiver, Shot, WaveletSource, Ricke
 from .geometry import AcquisitionGeometry, setup_geometry, setup_rec_coords  # noqa: F401
 from .acoustic import AcousticWaveSolver, iso_stencil  # noqa: F401
 from .acoustic import ForwardOperator as AcousticForwardOperator  # noqa: F401
+from .acoustic import AdjointOperator as AcousticAdjointOperator  # noqa: F401
 from .tti import AnisotropicWaveSolver, kernel_centered  # noqa: F401
 from .tti import ForwardOperator as TTIForwardOperator  # noqa: F401

@@ -1,18 +1,19 @@
-"""Isotropic acoustic forward modelling (mirror of examples/seismic/acoustic/operators.py:50-150
-and wavesolver.py:11-120, forward operator only — adjoint/gradient are SURVEY §8f)."""
+"""Isotropic acoustic modelling (mirror of examples/seismic/acoustic/operators.py:50-187 and
+wavesolver.py:11-156): forward and adjoint operators (gradient/Born are SURVEY §8f)."""
 from .. import Eq, Operator, TimeFunction, solve
 from ..tools import memoized_meth
 
-__all__ = ['iso_stencil', 'ForwardOperator', 'AcousticWaveSolver']
+__all__ = ['iso_stencil', 'ForwardOperator', 'AdjointOperator', 'AcousticWaveSolver']
 
 
 def iso_stencil(field, model, kernel='OT2', **kwargs):
     """u.dt2 * m - laplace(u) + damp * u.dt = 0 solved for u.forward (operators.py:71-107)."""
     if kernel != 'OT2':
         raise NotImplementedError("only the OT2 kernel is on this backend's path")
-    unext = field.forward
-    eq_time = solve(model.m * field.dt2 - field.laplace - kwargs.get('q', 0) + model.damp * field.dt,
-                    unext)
+    forward = kwargs.get('forward', True)
+    unext = field.forward if forward else field.backward
+    udt = field.dt if forward else field.dt.T
+    eq_time = solve(model.m * field.dt2 - field.laplace - kwargs.get('q', 0) + model.damp * udt, unext)
     return [Eq(unext, eq_time, subdomain=model.grid.subdomains['physdomain'])]
 
 
@@ -27,6 +28,20 @@ def ForwardOperator(model, geometry, space_order=4, save=False, kernel='OT2', **
     src_term = src.inject(field=u.forward, expr=src * s ** 2 / m)
     rec_term = rec.interpolate(expr=u)
     return Operator(eqn + src_term + rec_term, subs=model.spacing_map, name='Forward', **kwargs)
+
+
+def AdjointOperator(model, geometry, space_order=4, kernel='OT2', save=None, **kwargs):
+    """operators.py:153-187: the update solved for v.backward, receivers injected, adjoint source
+    sampled at the source position."""
+    m = model.m
+    v = TimeFunction(name='v', grid=model.grid, save=None, time_order=2, space_order=space_order)
+    srca = geometry.new_src(name='srca', src_type=None)
+    rec = geometry.rec
+    s = model.grid.stepping_dim.spacing
+    eqn = iso_stencil(v, model, kernel, forward=False)
+    receivers = rec.inject(field=v.backward, expr=rec * s ** 2 / m)
+    source_a = srca.interpolate(expr=v)
+    return Operator(eqn + receivers + source_a, subs=model.spacing_map, name='Adjoint', **kwargs)
 
 
 class AcousticWaveSolver:
@@ -48,6 +63,20 @@ class AcousticWaveSolver:
     def op_fwd(self, save=None):
         return ForwardOperator(self.model, save=save, geometry=self.geometry, kernel=self.kernel,
                                space_order=self.space_order, **self._kwargs)
+
+    @memoized_meth
+    def op_adj(self):
+        return AdjointOperator(self.model, save=None, geometry=self.geometry, kernel=self.kernel,
+                               space_order=self.space_order, **self._kwargs)
+
+    def adjoint(self, rec, srca=None, v=None, model=None, **kwargs):
+        """wavesolver.py:118-156"""
+        srca = srca or self.geometry.new_src(name='srca', src_type=None)
+        v = v or TimeFunction(name='v', grid=self.model.grid, time_order=2, space_order=self.space_order)
+        model = model or self.model
+        kwargs.update(model.physical_params(**kwargs))
+        summary = self.op_adj().apply(srca=srca, rec=rec, v=v, dt=kwargs.pop('dt', self.dt), **kwargs)
+        return srca, v, summary
 
     def forward(self, src=None, rec=None, u=None, model=None, save=None, **kwargs):
         src = src or self.geometry.src

@@ -107,9 +107,8 @@ class SeismicModel:
         dist = self.grid.distributor
         if dist.is_parallel:
             # the profile depends on global indices: evaluate on the global shape, keep our slab
-            prof = damp_profile(self.grid.shape_global, self.padsizes, self.grid.spacing, bcs)
-            lo, hi = dist.x_range
-            self.damp.data[:] = prof[lo:hi]
+            self.damp.data[:] = damp_profile(self.grid.shape_global, self.padsizes, self.grid.spacing, bcs,
+                                             x_range=dist.x_range)
         else:
             initialize_damp(self.damp, self.padsizes, self.spacing, abc_type=bcs, fs=self.fs)
 
@@ -217,10 +216,13 @@ class SeismicModel:
 Model = SeismicModel
 
 
-def damp_profile(shape, padsizes, spacing, abc_type="damp"):
-    """NumPy evaluation of the same profile as `initialize_damp` (used for slab-decomposed grids,
-    where the profile must follow global indices)."""
-    out = np.full(shape, 1.0 if abc_type == "mask" else 0.0, dtype=np.float64)
+def damp_profile(shape, padsizes, spacing, abc_type="damp", x_range=None):
+    """NumPy evaluation of the same profile as `initialize_damp`: the sum over dimensions of 1-D
+    layer profiles in GLOBAL indices. `x_range=(lo, hi)` returns only that x-slab (used under
+    slab decomposition, where each rank must not materialise the global array)."""
+    lo, hi = x_range if x_range is not None else (0, shape[0])
+    lshape = (hi - lo,) + tuple(shape[1:])
+    out = np.full(lshape, 1.0 if abc_type == "mask" else 0.0, dtype=np.float32)
     for ax, ((nbl, nbr), h) in enumerate(zip(padsizes, spacing)):
         n = shape[ax]
         prof = np.zeros(n)
@@ -230,10 +232,12 @@ def damp_profile(shape, padsizes, spacing, abc_type="damp"):
         j = np.arange(n - nbr, n)
         pos = np.abs((nbr - (n - 1 - j) + 1) / float(nbr))
         prof[n - nbr:] += 1.5 * np.log(1000.0) / nbr * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / float(h)
+        if ax == 0:
+            prof = prof[lo:hi]
         sh = [1] * len(shape)
-        sh[ax] = n
-        out = out + (-prof if abc_type == "mask" else prof).reshape(sh)
-    return out.astype(np.float32)
+        sh[ax] = len(prof)
+        out += (-prof if abc_type == "mask" else prof).astype(np.float32).reshape(sh)
+    return out
 
 
 def demo_model(preset, **kwargs):

@@ -110,6 +110,12 @@ struct b2_iso_args {
     int kernel;                       /* 0 auto, 1 force generic kernel, 2 force TMA kernel */
     b2_halo_ctx *halo;                /* NULL -> single device                              */
     struct b2_profiler *timers;       /* may be NULL                                        */
+    int adjoint;                      /* 0: forward in time. 1: the reference's `Adjoint`    *
+                                       * operator (acoustic/operators.py:153-187): time runs *
+                                       * from time_M down to time_m, u[t-1] is written from   *
+                                       * u[t], u[t+1]; `src` is injected into u[t-1] (the     *
+                                       * receiver data), `rec` samples u[t + rec_toff]        *
+                                       * (rec_toff in {0,-1})                                 */
 };
 int b2_iso_forward(const struct b2_iso_args *a);
 

@@ -73,6 +73,22 @@ def acoustic(name, so, n, nbl, tn, preset='constant-isotropic', interpolation='l
          u=np.array(u.data), norm_rec=np.float32(norm(rec)), norm_u=np.float32(norm(u)), **extra)
 
 
+def adjoint(name, so, n, nbl, tn):
+    """Forward then adjoint (acoustic/wavesolver.py:118-156): receiver data back-propagated."""
+    from devito import norm
+    from examples.seismic import demo_model, setup_geometry
+    from examples.seismic.acoustic import AcousticWaveSolver
+    model = demo_model('constant-isotropic', spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl,
+                       space_order=so, dtype=np.float32)
+    geometry = setup_geometry(model, tn)
+    solver = AcousticWaveSolver(model, geometry, space_order=so)
+    rec, u, _ = solver.forward()
+    srca, v, _ = solver.adjoint(rec)
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(model.critical_dt), nt=geometry.nt,
+         rec=np.array(rec.data), srca=np.array(srca.data), v=np.array(v.data),
+         src=np.array(geometry.src.data), norm_v=np.float32(norm(v)))
+
+
 def tti(name, so, n, nbl, tn):
     from devito import norm
     from examples.seismic import demo_model, setup_geometry
@@ -109,7 +125,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'tti8', 'tti4', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'tti8', 'tti4', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'iso8' in which:
@@ -120,6 +136,8 @@ if __name__ == '__main__':
         acoustic('iso3d_so4_layers', so=4, n=20, nbl=8, tn=150.0, preset='layers-isotropic', nlayers=3)
     if 'iso8sinc' in which:
         acoustic('iso3d_so8_sinc', so=8, n=20, nbl=8, tn=100.0, interpolation='sinc')
+    if 'adj8' in which:
+        adjoint('adj3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'tti8' in which:
         tti('tti3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'tti4' in which:

@@ -127,7 +127,9 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                        const float *wx, const float *wy, const float *wz, const float *damp,
                        int param_kind, const float *param, float vp, float dt, const int *lo,
                        const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
-                       int rec_toff) {
+                       int rec_toff, int adjoint) {
+    /* adjoint != 0: the reference's `Adjoint` operator (acoustic/operators.py:153-187) — the same
+     * update with the roles of t+1 / t-1 exchanged, time running from time_M down to time_m */
     const int R = radius;
     size_t sx, sy, slot;
     if (ndim == 3) {
@@ -142,10 +144,11 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
     const float r2 = 1.0f / (dt * dt);
     const float r3 = 1.0f / dt;
     const float r1s = 1.0f / (vp * vp);
-    for (int time = time_m; time <= time_M; ++time) {
+    const int dir = adjoint ? -1 : 1;
+    for (int time = adjoint ? time_M : time_m; adjoint ? time >= time_m : time <= time_M; time += dir) {
         const int t0 = ((time % tsize) + tsize) % tsize;
-        const int t1 = (((time + 1) % tsize) + tsize) % tsize;
-        const int t2 = (((time - 1) % tsize) + tsize) % tsize;
+        const int t1 = (((time + dir) % tsize) + tsize) % tsize;
+        const int t2 = (((time - dir) % tsize) + tsize) % tsize;
         const float *u0 = u + (size_t)t0 * slot;
         const float *um = u + (size_t)t2 * slot;
         float *u1 = u + (size_t)t1 * slot;

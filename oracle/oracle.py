@@ -39,7 +39,7 @@ def load(fast=False):
     fp, ip = POINTER(c_float), POINTER(c_int)
     L.oracle_iso_forward.argtypes = [c_int, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, c_int, fp,
                                      c_float, c_float, ip, ip, c_int, c_int, POINTER(OSparse),
-                                     POINTER(OSparse), c_int]
+                                     POINTER(OSparse), c_int, c_int]
     L.oracle_iso_forward.restype = c_int
     L.oracle_tti_forward.argtypes = [fp, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, fp, fp, fp,
                                      c_float, c_float, c_float, c_float, c_float, c_float, ip, ip,
@@ -75,7 +75,7 @@ def _sparse(data, gp, ws, r, keep):
 
 
 def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, param_kind=0,
-                src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False):
+                src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False, adjoint=False):
     """u: (T, [nx+2so,] ny+2so, nz+2so) float32 C-contiguous, updated in place.
     w: list (per dim) of weights [0..R] incl. 1/h^2. src/rec: dict(data, gp, w, r)."""
     L = load(fast)
@@ -91,7 +91,8 @@ def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, par
     rc = L.oracle_iso_forward(nd, _fp(u), u.shape[0], _ip(alloc), so, R, _fp(wa[0]), _fp(wa[1]),
                               _fp(wa[2]) if wa[2] is not None else None, _fp(damp), param_kind,
                               _fp(param), vp, dt, _ip(lo), _ip(hi), time_m, time_M,
-                              ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, rec_toff)
+                              ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, rec_toff,
+                              1 if adjoint else 0)
     assert rc == 0
     return u
 

@@ -32,7 +32,11 @@ def host_mode():
     # damping profile and padded parameter follow GLOBAL indices
     full = damp_profile(model.grid.shape_global, [(nbl, nbl)] * 3, model.grid.spacing)
     lo, hi = d.x_range
-    assert np.array_equal(np.asarray(model.damp.data), full[lo:hi])
+    assert np.allclose(np.asarray(model.damp.data), full[lo:hi], rtol=1e-6, atol=1e-9)
+    # ... and equals the serial DSL-built profile (initialize_damp through the interpreter)
+    from devito_b200 import configuration
+    serial = damp_profile(model.grid.shape_global, [(nbl, nbl)] * 3, model.grid.spacing, x_range=(lo, hi))
+    assert np.array_equal(np.asarray(model.damp.data), serial)
     vp_full = np.pad(np.pad(vp, nbl, mode='edge'), so, mode='edge')
     assert np.array_equal(np.asarray(model.vp.data_with_halo), vp_full[lo:hi + 2 * so])
     # reductions agree with the serial values on every rank

@@ -176,3 +176,21 @@ def test_error_code_on_nan():
     src.data[3, 0] = np.nan
     with pytest.raises(ExecutionError):
         solver.forward(src=src, errctl=1)
+
+
+def test_adjoint_vs_reference_golden_and_dot_product():
+    """Adjoint operator (acoustic/operators.py:153-187) on the same kernels run
+    backward in time; plus the reference's adjoint identity <A x, y> = <x, A^T y>
+    (tests/test_adjoint.py:21-121, there in float64 with 1e-11; float32 here)."""
+    from devito_b200 import norm, inner
+    g = load_golden('adj3d_so8')
+    model, geometry, solver = _solver('iso', 8, int(g['n']), int(g['nbl']), float(g['tn']))
+    assert solver.op_adj().backend == 'cuda-sm100a'
+    rec, u, _ = solver.forward()
+    srca, v, _ = solver.adjoint(rec)
+    assert rel_linf(v.data, g['v']) < 1e-4          # atomics order, see tests/test_oracle_golden.py
+    assert rel_linf(srca.data, g['srca']) < 1e-4
+    src = geometry.src
+    term1 = float(np.sum(np.asarray(srca.data, dtype=np.float64) * np.asarray(src.data, dtype=np.float64)))
+    term2 = float(np.sum(np.asarray(rec.data, dtype=np.float64) ** 2))
+    assert abs(term1 - term2) / abs(term2) < 1e-4
