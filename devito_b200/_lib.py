@@ -61,7 +61,10 @@ class TtiArgs(Structure):
                 ('z_m', c_int), ('z_M', c_int), ('time_m', c_int), ('time_M', c_int),
                 ('src', POINTER(Sparse)), ('rec', POINTER(Sparse)), ('rec_toff', c_int),
                 ('errctl', c_int), ('deviceid', c_int), ('kernel', c_int),
-                ('halo', c_void_p), ('timers', POINTER(Profiler))]
+                ('halo', c_void_p), ('timers', POINTER(Profiler)),
+                ('vp_arr', POINTER(Dataobj)), ('epsilon_arr', POINTER(Dataobj)),
+                ('delta_arr', POINTER(Dataobj)), ('theta_arr', POINTER(Dataobj)),
+                ('phi_arr', POINTER(Dataobj))]
 
 
 _lib = None

@@ -19,7 +19,8 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
     const int so = a->space_order;
     int rc = B2_OK;
 
-    DevArray u, v, damp;
+    DevArray u, v, damp, parr[5];
+    bool sparr[5] = {false, false, false, false, false};
     SparseDev src, rec;
     TtiPlan p;
     FieldGeom g;
@@ -30,6 +31,7 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
         int r1 = su ? stage_out(u, back) : B2_OK;
         int r2 = sv ? stage_out(v, back) : B2_OK;
         if (sd) stage_out(damp, false);
+        for (int i = 0; i < 5; ++i) if (sparr[i]) stage_out(parr[i], false);
         sparse_stage_out(src, false);
         int r3 = sparse_stage_out(rec, back);
         tti_plan_free(p);
@@ -44,6 +46,14 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
     if (a->damp) {
         if ((rc = stage_in(a->damp, 3, damp, true))) return cleanup(rc);
         sd = true;
+    }
+    {
+        const b2_dataobj *pa[5] = {a->vp_arr, a->epsilon_arr, a->delta_arr, a->theta_arr, a->phi_arr};
+        for (int i = 0; i < 5; ++i)
+            if (pa[i]) {
+                if ((rc = stage_in(pa[i], 3, parr[i], true))) return cleanup(rc);
+                sparr[i] = true;
+            }
     }
     if ((rc = sparse_stage_in(a->src, 3, src, true))) return cleanup(rc);
     if ((rc = sparse_stage_in(a->rec, 3, rec, true))) return cleanup(rc);
@@ -76,6 +86,11 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
     p.delta = a->delta;
     p.theta = a->theta;
     p.phi = a->phi;
+    p.vp_a = sparr[0] ? (const float *)parr[0].d : nullptr;
+    p.eps_a = sparr[1] ? (const float *)parr[1].d : nullptr;
+    p.delta_a = sparr[2] ? (const float *)parr[2].d : nullptr;
+    p.theta_a = sparr[3] ? (const float *)parr[3].d : nullptr;
+    p.phi_a = sparr[4] ? (const float *)parr[4].d : nullptr;
     for (int d = 0; d < 3; ++d) {
         if (!a->w2[d] || !a->w1[d]) { set_error("b2_tti_forward: weights missing"); return cleanup(B2_ERR_INVALID); }
         for (int i = 0; i <= a->radius; ++i) p.w2[d][i] = a->w2[d][i];
@@ -110,7 +125,8 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
         }
         float *fu = p.u + (size_t)t1 * p.slot_elems;
         float *fv = p.v + (size_t)t1 * p.slot_elems;
-        if ((rc = launch_inject(src, g, fu, fv, time, B2_PARAM_SCALAR, nullptr, scalar_scale, dt2)))
+        if ((rc = launch_inject(src, g, fu, fv, time, p.vp_a ? B2_PARAM_VP : B2_PARAM_SCALAR, p.vp_a,
+                                scalar_scale, dt2)))
             return cleanup(rc);
         const size_t ro = (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
         if ((rc = launch_interp(rec, g, p.u + ro, p.v + ro, time))) return cleanup(rc);

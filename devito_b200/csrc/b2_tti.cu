@@ -40,7 +40,36 @@ struct TtiK {
     float e2, sd;              // 1+2eps, sqrt(1+2delta)
     float w2[3][B2_MAX_RADIUS + 1];
     float w1[3][B2_MAX_RADIUS];
+    // per-point coefficient tables (nullptr -> the scalars above)
+    const float *__restrict__ tCx;
+    const float *__restrict__ tCy;
+    const float *__restrict__ tCz;
+    const float *__restrict__ tE2;
+    const float *__restrict__ tSD;
+    const float *__restrict__ tMD;
 };
+
+// time-invariant tables for array-valued parameters (the reference hoists the same quantities:
+// r2..r5 of the generated ForwardTTI for `layers-tti`)
+__global__ void __launch_bounds__(256)
+k_tti_tables(const float *__restrict__ vp, const float *__restrict__ eps, const float *__restrict__ delta,
+             const float *__restrict__ theta, const float *__restrict__ phi, float vp_s, float eps_s,
+             float delta_s, float theta_s, float phi_s, float inv_dt2, float *Cx, float *Cy, float *Cz,
+             float *E2, float *SD, float *MD, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const float th = theta ? theta[i] : theta_s, ph = phi ? phi[i] : phi_s;
+        const float st = sinf(th), ct = cosf(th);
+        Cx[i] = st * cosf(ph);
+        Cy[i] = st * sinf(ph);
+        Cz[i] = ct;
+        E2[i] = 2.0f * (eps ? eps[i] : eps_s) + 1.0f;
+        SD[i] = sqrtf(2.0f * (delta ? delta[i] : delta_s) + 1.0f);
+        const float v = vp ? vp[i] : vp_s;
+        MD[i] = inv_dt2 / (v * v);
+    }
+}
 
 // pass A: Gz over the box extended by [-R/2, R/2-1]
 __global__ void __launch_bounds__(256) k_tti_gz(TtiK k) {
@@ -60,8 +89,10 @@ __global__ void __launch_bounds__(256) k_tti_gz(TtiK k) {
             dyv = fmaf(k.w1[1][j], k.v0[idx + off * k.sy], dyv);
             dzv = fmaf(k.w1[2][j], k.v0[idx + off], dzv);
         }
-        k.gzu[idx] = k.cx * dxu + k.cy * dyu + k.cz * dzu;
-        k.gzv[idx] = k.cx * dxv + k.cy * dyv + k.cz * dzv;
+        const float cx = k.tCx ? k.tCx[idx] : k.cx, cy = k.tCy ? k.tCy[idx] : k.cy,
+                    cz = k.tCz ? k.tCz[idx] : k.cz;
+        k.gzu[idx] = cx * dxu + cy * dyu + cz * dzu;
+        k.gzv[idx] = cx * dxv + cy * dyv + cz * dzv;
     }
 }
 
@@ -82,20 +113,25 @@ __global__ void __launch_bounds__(256) k_tti_update(TtiK k) {
         float gu = 0.f, gv = 0.f;
         for (int j = 0; j < k.R; ++j) {
             const int off = j - h;
-            gu = fmaf(k.cx * k.w1[0][j], k.gzu[idx + off * k.sx], gu);
-            gu = fmaf(k.cy * k.w1[1][j], k.gzu[idx + off * k.sy], gu);
-            gu = fmaf(k.cz * k.w1[2][j], k.gzu[idx + off], gu);
-            gv = fmaf(k.cx * k.w1[0][j], k.gzv[idx + off * k.sx], gv);
-            gv = fmaf(k.cy * k.w1[1][j], k.gzv[idx + off * k.sy], gv);
-            gv = fmaf(k.cz * k.w1[2][j], k.gzv[idx + off], gv);
+            const long long ix = idx + off * k.sx, iy = idx + off * k.sy, iz = idx + off;
+            const float cx = k.tCx ? k.tCx[ix] : k.cx, cy = k.tCy ? k.tCy[iy] : k.cy,
+                        cz = k.tCz ? k.tCz[iz] : k.cz;
+            gu = fmaf(cx * k.w1[0][j], k.gzu[ix], gu);
+            gu = fmaf(cy * k.w1[1][j], k.gzu[iy], gu);
+            gu = fmaf(cz * k.w1[2][j], k.gzu[iz], gu);
+            gv = fmaf(cx * k.w1[0][j], k.gzv[ix], gv);
+            gv = fmaf(cy * k.w1[1][j], k.gzv[iy], gv);
+            gv = fmaf(cz * k.w1[2][j], k.gzv[iz], gv);
         }
         const float gh = lap - gu;                  // Gxx + Gyy applied to u
-        const float H0 = k.e2 * gh + k.sd * gv;
-        const float Hz = k.sd * gh + gv;
+        const float e2 = k.tE2 ? k.tE2[idx] : k.e2, sd = k.tSD ? k.tSD[idx] : k.sd;
+        const float md = k.tMD ? k.tMD[idx] : k.m_dt2;
+        const float H0 = e2 * gh + sd * gv;
+        const float Hz = sd * gh + gv;
         const float d = k.damp ? k.damp[idx] * k.inv_dt : 0.f;
-        const float den = k.m_dt2 + d;
-        k.u1[idx] = (k.m_dt2 * (2.f * uc - k.um[idx]) + d * uc + H0) / den;
-        k.v1[idx] = (k.m_dt2 * (2.f * vc - k.vm[idx]) + d * vc + Hz) / den;
+        const float den = md + d;
+        k.u1[idx] = (md * (2.f * uc - k.um[idx]) + d * uc + H0) / den;
+        k.v1[idx] = (md * (2.f * vc - k.vm[idx]) + d * vc + Hz) / den;
     }
 }
 
@@ -468,8 +504,8 @@ template <> struct TtiTile<2> { static constexpr int TY = 32; };
 template <> struct TtiTile<4> { static constexpr int TY = 28; };
 
 // scratch cached across calls
-static float *g_tti_scratch[3] = {nullptr, nullptr, nullptr};
-static size_t g_tti_scratch_elems[3] = {0, 0, 0};
+static float *g_tti_scratch[9] = {};
+static size_t g_tti_scratch_elems[9] = {};
 static int tti_scratch(int which, size_t elems, float **out) {
     if (g_tti_scratch_elems[which] != elems) {
         if (g_tti_scratch[which]) cudaFree(g_tti_scratch[which]);
@@ -488,7 +524,8 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         set_error("tti: radius %d unsupported (space_order must be a multiple of 4, <= 16)", p.R);
         return B2_ERR_INVALID;
     }
-    bool ok = (p.R == 2 || p.R == 4) && (p.a[2] % 4 == 0) && (p.o[2] % 4 == 0) &&
+    p.has_arrays = p.vp_a || p.eps_a || p.delta_a || p.theta_a || p.phi_a;
+    bool ok = !p.has_arrays && (p.R == 2 || p.R == 4) && (p.a[2] % 4 == 0) && (p.o[2] % 4 == 0) &&
               ((uintptr_t)p.u % 16 == 0) && ((uintptr_t)p.v % 16 == 0) && (p.slot_elems % 4 == 0) &&
               p.n[1] >= 8 && p.n[2] >= 16;
     if (kernel == 1) ok = false;
@@ -512,12 +549,24 @@ int tti_plan_init(TtiPlan &p, int kernel) {
     }
     if ((rc = tti_scratch(1, p.slot_elems, &p.gzu))) return rc;
     if ((rc = tti_scratch(2, p.slot_elems, &p.gzv))) return rc;
+    if (p.has_arrays) {
+        float **t[6] = {&p.tCx, &p.tCy, &p.tCz, &p.tE2, &p.tSD, &p.tMD};
+        for (int i = 0; i < 6; ++i)
+            if ((rc = tti_scratch(3 + i, p.slot_elems, t[i]))) return rc;
+        k_tti_tables<<<148 * 8, 256, 0, stream()>>>(p.vp_a, p.eps_a, p.delta_a, p.theta_a, p.phi_a, p.vp,
+                                                     p.epsilon, p.delta, p.theta, p.phi,
+                                                     1.0f / (p.dt * p.dt), p.tCx, p.tCy, p.tCz, p.tE2,
+                                                     p.tSD, p.tMD, p.slot_elems);
+        count_launch();
+        B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    }
     return B2_OK;
 }
 
 void tti_plan_free(TtiPlan &p) {
     p.gzu = p.gzv = nullptr;       // scratch is cached in the library
     p.coefA = nullptr;
+    p.tCx = p.tCy = p.tCz = p.tE2 = p.tSD = p.tMD = nullptr;
 }
 
 static int env_int_tti(const char *name, int dflt) {
@@ -613,6 +662,7 @@ int tti_step(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xco
     k.sd = sqrtf(1.0f + 2.0f * p.delta);
     memcpy(k.w2, p.w2, sizeof(k.w2));
     memcpy(k.w1, p.w1, sizeof(k.w1));
+    k.tCx = p.tCx; k.tCy = p.tCy; k.tCz = p.tCz; k.tE2 = p.tE2; k.tSD = p.tSD; k.tMD = p.tMD;
     dim3 block(64, 4, 1);
     dim3 gridA((k.n2 + k.R + 63) / 64, (k.n1 + k.R + 3) / 4, (unsigned)std::min(xcount + k.R, 65535));
     timing_begin();

@@ -25,6 +25,11 @@ struct TtiPlan {
     bool use_fused = false;
     CUtensorMap tm_u, tm_v;
     float *coefA = nullptr;
+    // array-valued parameters (device pointers, nullptr -> scalar)
+    const float *vp_a = nullptr, *eps_a = nullptr, *delta_a = nullptr, *theta_a = nullptr, *phi_a = nullptr;
+    // tabulated per-point coefficients (library scratch) when any parameter is an array
+    float *tCx = nullptr, *tCy = nullptr, *tCz = nullptr, *tE2 = nullptr, *tSD = nullptr, *tMD = nullptr;
+    bool has_arrays = false;
 };
 
 int tti_plan_init(TtiPlan &p, int kernel);

@@ -486,30 +486,70 @@ class Operator:
             return out
         ku, kv = keyed(tu), keyed(tv)
         funcs, consts, syms = self._leaves(list(ku.values()) + list(kv.values()))
-        byname = {c.name: c for c in consts}
-        need = ('vp', 'epsilon', 'delta', 'theta')
-        if any(n not in byname for n in need):
-            raise _Unrecognised("TTI fast path needs scalar vp/epsilon/delta/theta[/phi] Constants")
+        pnames = ('vp', 'epsilon', 'delta', 'theta', 'phi')
+        byname = {c.name: c for c in consts if c.name in pnames}
         damp = None
         for a in funcs:
-            k = _space_offsets(a, None)
-            if getattr(a.function, 'is_TimeFunction', False) or k is None or any(k[1]):
-                raise _Unrecognised("parameter field accessed off-centre")
-            if damp is not None:
-                raise _Unrecognised("array-valued Thomsen parameters are not on the fast path yet")
-            damp = a.function
+            f = a.function
+            if getattr(f, 'is_TimeFunction', False):
+                raise _Unrecognised("unexpected time-varying coefficient")
+            if f.name in pnames:
+                if f.space_order != so:
+                    raise _Unrecognised("array-valued TTI parameters must share the wavefield's space_order")
+                byname[f.name] = f
+            elif damp is None or damp is f:
+                damp = f
+            else:
+                raise _Unrecognised(f"unknown coefficient field {f.name}")
+        if any(n not in byname for n in ('vp', 'epsilon', 'delta', 'theta')):
+            raise _Unrecognised("TTI fast path needs vp/epsilon/delta/theta[/phi] (Constants or Functions)")
+        for n in (c for c in consts if c.name not in pnames):
+            raise _Unrecognised(f"unknown Constant {n.name} in the TTI update")
+        # every access of damp must be at the centre
+        for ex in list(ku.values()) + list(kv.values()):
+            for n in ex.preorder():
+                if n.is_Access and n.function is damp:
+                    k = _space_offsets(n, None)
+                    if k is None or any(k[1]):
+                        raise _Unrecognised("damp accessed off-centre")
         dtsym = grid.stepping_dim.spacing
         hs = self._spacing_values(grid)
         w2 = [second_derivative_weights(so, h) for h in hs]
         w1 = [half_node_first_derivative_weights(so, h) for h in hs]
         rng = np.random.default_rng(99)
         for probe in range(2):
-            vals, leaf = self._probe_env(rng, funcs, consts, syms, grid)
-            dt = vals[('s', dtsym.name)]
-            par = {n: vals[('c', id(byname[n]))] for n in byname}
-            dval = vals[('f', id(damp))] if damp is not None else 0.0
-            pu, pv = predict_tti(w2, w1, R, par['vp'], par['epsilon'], par['delta'], par['theta'],
-                                 par.get('phi', 0.0), dval, dt)
+            # parameters get a random value AND a random spatial gradient, so that the comparison
+            # also checks WHERE each factor is sampled (the reference samples the rotation factors
+            # at the shifted points of the outer derivative, tti/operators.py:92-102)
+            base = {n: rng.uniform(0.2, 0.8) for n in pnames}
+            gradv = {n: (rng.uniform(-0.02, 0.02, size=3) if isinstance(byname.get(n), Function) else np.zeros(3))
+                     for n in pnames}
+            if 'phi' not in byname:
+                base['phi'] = 0.0
+            dt = rng.uniform(0.5, 2.0)
+            dval = rng.uniform(0.5, 2.0) if damp is not None else 0.0
+            spv = {sp.name: float(v) for sp, v in grid.spacing_map.items()}
+
+            def P(name, off):
+                return float(base[name] + np.dot(gradv[name], off))
+
+            def leaf(n):
+                if n.is_Access:
+                    f = n.function
+                    if f is damp:
+                        return dval
+                    k = _space_offsets(n, None)
+                    if k is None:
+                        raise _Unrecognised("non-affine parameter access")
+                    return P(f.name, k[1])
+                if n.is_Constant:
+                    return P(n.name, (0, 0, 0))
+                if n.name == dtsym.name:
+                    return dt
+                if n.name in spv:
+                    return spv[n.name]
+                raise _Unrecognised(f"unknown symbol {n.name}")
+            pu, pv = predict_tti(w2, w1, R, P, dval, dt)
             for got, pred, nm in ((ku, pu, 'u'), (kv, pv, 'v')):
                 keys = set(got) | set(pred)
                 for k in keys:
@@ -517,9 +557,10 @@ class Operator:
                     p = pred.get(k, 0.0)
                     if abs(g - p) > 1e-8 * max(1.0, abs(p)):
                         raise _Unrecognised(f"TTI coefficient mismatch in {nm} at {k}: {g} vs {p}")
+        m_role = ('vp_f', byname['vp']) if isinstance(byname['vp'], Function) else ('vp_c', byname['vp'])
         plan = {'kind': 'tti', 'u': u, 'v': v, 'grid': grid, 'so': so, 'R': R, 'w2': w2, 'w1': w1,
                 'consts': byname, 'damp': damp, 'dt': dtsym, 'src': None, 'rec': None, 'rec_toff': 0,
-                'm_role': ('vp_c', byname['vp'])}
+                'm_role': m_role}
         self._attach_sparse(plan, injs, itps, [u, v], funcs, consts, syms, plan['m_role'])
         return plan
 
@@ -687,12 +728,21 @@ class Operator:
                     sval = float(val.data if isinstance(val, Constant) else val)
                     args['vp'] = sval if kind.startswith('vp') else 1.0 / np.sqrt(sval)
         else:
+            args['tti_arrays'] = {}
             for n, c in p['consts'].items():
                 val = kwargs.pop(n, c)
-                if isinstance(val, Function):
-                    raise InvalidArgument(f"array-valued `{n}` needs an Operator built with a Function")
-                args[n] = float(val.data if isinstance(val, Constant) else val)
+                if isinstance(c, Function):
+                    if not isinstance(val, Function) or val.space_order != p['so']:
+                        raise InvalidArgument(f"`{n}` must be overridden by a Function of the same space_order")
+                    args['tti_arrays'][n] = val
+                    args[n] = 0.0
+                else:
+                    if isinstance(val, Function):
+                        raise InvalidArgument(f"array-valued `{n}` needs an Operator built with a Function")
+                    args[n] = float(val.data if isinstance(val, Constant) else val)
             args.setdefault('phi', 0.0)
+            if 'vp' in args['tti_arrays']:
+                args['vp'] = 1.0
         # spacing / dt
         dt = kwargs.pop('dt', None)
         if dt is None:
@@ -946,6 +996,8 @@ class Operator:
         a.damp = self._field_obj(args['damp'], dev, res, hold, so=p['so']).ptr if args['damp'] is not None else None
         a.vp, a.epsilon, a.delta = args['vp'], args['epsilon'], args['delta']
         a.theta, a.phi = args['theta'], args['phi']
+        for n, fn in args['tti_arrays'].items():
+            setattr(a, n + '_arr', self._field_obj(fn, dev, res, hold, so=p['so']).ptr)
         a.dt = args['dt']
         lo, hi = args['lo'], args['hi']
         a.x_m, a.x_M, a.y_m, a.y_M, a.z_m, a.z_M = lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]
@@ -974,12 +1026,18 @@ class Operator:
 # the stencil the TTI kernels implement, as linear coefficients (float64) — used only by the
 # recogniser to confirm that a user's equations are this scheme.
 # ---------------------------------------------------------------------------------------------
-def predict_tti(w2, w1, R, vp, eps, delta, theta, phi, damp, dt):
+def predict_tti(w2, w1, R, P, damp, dt):
+    """`P(name, offset)` -> value of parameter `name` sampled `offset` grid points from the output
+    point (constants ignore the offset)."""
     h = R // 2
-    st, ct, sp, cp = np.sin(theta), np.cos(theta), np.sin(phi), np.cos(phi)
-    c = [st * cp, st * sp, ct]
-    e2 = 1 + 2 * eps
-    sd = np.sqrt(1 + 2 * delta)
+    z3 = (0, 0, 0)
+
+    def C(off):
+        th, ph = P('theta', off), P('phi', off)
+        st, ct, sp, cp = np.sin(th), np.cos(th), np.sin(ph), np.cos(ph)
+        return [st * cp, st * sp, ct]
+    e2 = 1 + 2 * P('epsilon', z3)
+    sd = np.sqrt(1 + 2 * P('delta', z3))
 
     def unit(d, o):
         v = [0, 0, 0]
@@ -989,24 +1047,23 @@ def predict_tti(w2, w1, R, vp, eps, delta, theta, phi, damp, dt):
     def add(dst, key, val):
         dst[key] = dst.get(key, 0.0) + val
 
-    # Gz as offset -> coefficient
-    gz = {}
-    for d in range(3):
-        for j in range(R):
-            add(gz, unit(d, j - h + 1), c[d] * w1[d][j])
-    # Gzz = sum_d D-_d (c_d * Gz)
+    # Gzz = sum_d D-_d ( C_d(q) * Gz(q) ),  Gz(q) = sum_e C_e(q) D+_e f(q)
     gzz = {}
     for d in range(3):
         for j in range(R):
-            o = unit(d, j - h)
-            for k, val in gz.items():
-                add(gzz, tuple(a + b for a, b in zip(o, k)), c[d] * w1[d][j] * val)
+            q = unit(d, j - h)
+            cq = C(q)
+            for e in range(3):
+                for i in range(R):
+                    off = tuple(a + b for a, b in zip(q, unit(e, i - h + 1)))
+                    add(gzz, off, w1[d][j] * cq[d] * cq[e] * w1[e][i])
     lap = {}
-    add(lap, (0, 0, 0), sum(w[0] for w in w2))
+    add(lap, z3, sum(w[0] for w in w2))
     for d in range(3):
         for k in range(1, R + 1):
             add(lap, unit(d, k), w2[d][k])
             add(lap, unit(d, -k), w2[d][k])
+    vp = P('vp', z3)
     m_dt2 = 1.0 / (vp * vp) / (dt * dt)
     den = m_dt2 + damp / dt
     pu, pv = {}, {}
@@ -1018,12 +1075,10 @@ def predict_tti(w2, w1, R, vp, eps, delta, theta, phi, damp, dt):
         add(pu, ('v', 0) + (k,), sd * val / den)
         add(pv, ('u', 0) + (k,), -sd * val / den)
         add(pv, ('v', 0) + (k,), val / den)
-    z = (0, 0, 0)
-    add(pu, ('u', 0, z), (2 * m_dt2 + damp / dt) / den)
-    add(pu, ('u', -1, z), -m_dt2 / den)
-    add(pv, ('v', 0, z), (2 * m_dt2 + damp / dt) / den)
-    add(pv, ('v', -1, z), -m_dt2 / den)
-    # drop exact zeros produced by cancellation
+    add(pu, ('u', 0, z3), (2 * m_dt2 + damp / dt) / den)
+    add(pu, ('u', -1, z3), -m_dt2 / den)
+    add(pv, ('v', 0, z3), (2 * m_dt2 + damp / dt) / den)
+    add(pv, ('v', -1, z3), -m_dt2 / den)
     pu = {k: v for k, v in pu.items() if abs(v) > 1e-14}
     pv = {k: v for k, v in pv.items() if abs(v) > 1e-14}
     return pu, pv

@@ -272,4 +272,16 @@ def demo_model(preset, **kwargs):
             v[..., i * int(shape[-1] / nlayers):] = vp_i[i]
         return SeismicModel(space_order=space_order, vp=v, origin=origin, shape=shape, dtype=dtype,
                             spacing=spacing, nbl=nbl, bcs="damp", **kwargs)
+    if p in ('layers-tti', 'layers-tti-noazimuth'):
+        vp_top = kwargs.pop('vp_top', 1.5)
+        vp_bottom = kwargs.pop('vp_bottom', 3.5)
+        v = np.empty(shape, dtype=dtype)
+        v[:] = vp_top
+        vp_i = np.linspace(vp_top, vp_bottom, nlayers)
+        for i in range(1, nlayers):
+            v[..., i * int(shape[-1] / nlayers):] = vp_i[i]
+        phi = .25 * (v - vp_top) if (len(shape) > 2 and p != 'layers-tti-noazimuth') else None
+        return SeismicModel(space_order=space_order, vp=v, origin=origin, shape=shape, dtype=dtype,
+                            spacing=spacing, nbl=nbl, epsilon=.1 * (v - vp_top), delta=.05 * (v - vp_top),
+                            theta=.5 * (v - vp_top), phi=phi, bcs="damp", **kwargs)
     raise ValueError(f"unknown or unsupported preset {preset!r}")

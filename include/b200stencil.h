@@ -142,6 +142,11 @@ struct b2_tti_args {
     int kernel;
     b2_halo_ctx *halo;
     struct b2_profiler *timers;
+    /* array-valued parameters (preset `layers-tti`, examples/seismic/preset_models.py:210-238):
+     * each NULL -> the scalar above. Same allocated layout (halo = space_order) as u. The rotation
+     * factors are sampled where the reference samples them: at the Gz point inside Gz, at the
+     * shifted point in the outer derivative `(Gz*cos(theta)).dz(...)` (tti/operators.py:92-102). */
+    struct b2_dataobj *vp_arr, *epsilon_arr, *delta_arr, *theta_arr, *phi_arr;
 };
 int b2_tti_forward(const struct b2_tti_args *a);
 

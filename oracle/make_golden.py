@@ -89,12 +89,12 @@ def adjoint(name, so, n, nbl, tn):
          src=np.array(geometry.src.data), norm_v=np.float32(norm(v)))
 
 
-def tti(name, so, n, nbl, tn):
+def tti(name, so, n, nbl, tn, preset='constant-tti', **kw):
     from devito import norm
     from examples.seismic import demo_model, setup_geometry
     from examples.seismic.tti import AnisotropicWaveSolver
-    model = demo_model('constant-tti', spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl,
-                       space_order=so, dtype=np.float32)
+    model = demo_model(preset, spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl,
+                       space_order=so, dtype=np.float32, **kw)
     geometry = setup_geometry(model, tn)
     solver = AnisotropicWaveSolver(model, geometry, space_order=so)
     rec, u, v, _ = solver.forward()
@@ -104,8 +104,9 @@ def tti(name, so, n, nbl, tn):
          rec_coords=np.array(geometry.rec.coordinates.data), rec=np.array(rec.data),
          u=np.array(u.data), v=np.array(v.data), norm_rec=np.float32(norm(rec)),
          norm_u=np.float32(norm(u)), norm_v=np.float32(norm(v)),
-         epsilon=np.float32(model.epsilon.data), delta=np.float32(model.delta.data),
-         theta=np.float32(model.theta.data), phi=np.float32(model.phi.data))
+         epsilon=np.array(model.epsilon.data, dtype=np.float32), delta=np.array(model.delta.data, dtype=np.float32),
+         theta=np.array(model.theta.data, dtype=np.float32), phi=np.array(model.phi.data, dtype=np.float32),
+         vp=np.array(model.vp.data, dtype=np.float32))
 
 
 def coefficients():
@@ -125,7 +126,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'tti8', 'tti4', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'tti8', 'tti4', 'tti4layers', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'iso8' in which:
@@ -140,6 +141,8 @@ if __name__ == '__main__':
         adjoint('adj3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'tti8' in which:
         tti('tti3d_so8', so=8, n=20, nbl=8, tn=150.0)
+    if 'tti4layers' in which:
+        tti('tti3d_so4_layers', so=4, n=20, nbl=8, tn=100.0, preset='layers-tti', nlayers=3)
     if 'tti4' in which:
         tti('tti3d_so4', so=4, n=20, nbl=8, tn=120.0)
     if 'coef' in which:

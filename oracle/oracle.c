@@ -203,18 +203,38 @@ int oracle_tti_forward(float *u, float *v, int tsize, const int *alloc, int so, 
                        const float *w1y, const float *w1z, const float *damp, float vp,
                        float epsilon, float delta, float theta, float phi, float dt, const int *lo,
                        const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
-                       int rec_toff) {
+                       int rec_toff, const float *vp_a, const float *eps_a, const float *delta_a,
+                       const float *theta_a, const float *phi_a) {
+    /* *_a: array-valued parameters (NULL -> scalar), preset `layers-tti`. Rotation factors are
+     * sampled at the Gz point inside Gz and at the shifted point in the outer derivative, exactly
+     * like the reference's generated code (time-invariant tables r2..r5). */
     const int R = radius, h = radius / 2;
     const size_t sy = (size_t)alloc[2], sx = (size_t)alloc[1] * alloc[2];
     const size_t slot = (size_t)alloc[0] * sx;
     float *gzu = (float *)calloc(slot, sizeof(float));
     float *gzv = (float *)calloc(slot, sizeof(float));
     if (!gzu || !gzv) return 202;
-    const float r18 = sqrtf(2 * delta + 1);
+    const int arrays = vp_a || eps_a || delta_a || theta_a || phi_a;
+    float *tcx = NULL, *tcy = NULL, *tcz = NULL, *tsd = NULL;
+    if (arrays) {
+        tcx = (float *)malloc(slot * sizeof(float));
+        tcy = (float *)malloc(slot * sizeof(float));
+        tcz = (float *)malloc(slot * sizeof(float));
+        tsd = (float *)malloc(slot * sizeof(float));
+        for (size_t i = 0; i < slot; ++i) {
+            const float th = theta_a ? theta_a[i] : theta, ph = phi_a ? phi_a[i] : phi;
+            const float s_ = sinf(th);
+            tcz[i] = cosf(th);
+            tcy[i] = s_ * sinf(ph);
+            tcx[i] = s_ * cosf(ph);
+            tsd[i] = sqrtf(2 * (delta_a ? delta_a[i] : delta) + 1);
+        }
+    }
+    const float r18s = sqrtf(2 * delta + 1);
     const float ct = cosf(theta), st = sinf(theta), sp = sinf(phi), cp = cosf(phi);
-    const float cz = ct, cy = sp * st, cx = st * cp;
-    const float e2 = 2 * epsilon + 1;
-    const float r9 = 1.0f / (vp * vp), r10 = 1.0f / (dt * dt), r11 = 1.0f / dt;
+    const float czs = ct, cys = sp * st, cxs = st * cp;
+    const float e2s = 2 * epsilon + 1;
+    const float r9s = 1.0f / (vp * vp), r10 = 1.0f / (dt * dt), r11 = 1.0f / dt;
     for (int time = time_m; time <= time_M; ++time) {
         const int t0 = ((time % tsize) + tsize) % tsize;
         const int t1 = (((time + 1) % tsize) + tsize) % tsize;
@@ -237,6 +257,7 @@ int oracle_tti_forward(float *u, float *v, int tsize, const int *alloc, int so, 
                         dyv += w1y[j] * v0[i + o * (ptrdiff_t)sy];
                         dzv += w1z[j] * v0[i + o];
                     }
+                    const float cx = arrays ? tcx[i] : cxs, cy = arrays ? tcy[i] : cys, cz = arrays ? tcz[i] : czs;
                     gzu[i] = cz * dzu + cy * dyu + cx * dxu;
                     gzv[i] = cz * dzv + cy * dyv + cx * dxv;
                 }
@@ -252,9 +273,14 @@ int oracle_tti_forward(float *u, float *v, int tsize, const int *alloc, int so, 
                                w2z[k] * (u0[i - k] + u0[i + k]);
                     /* outer half-node derivatives of (r12,r13,r14) and (r15,r16,r17) */
                     float H0 = 0, Hz = 0;
+                    const float r18 = arrays ? tsd[i] : r18s;
+                    const float e2 = eps_a ? 2 * eps_a[i] + 1 : e2s;
+                    const float r9 = vp_a ? 1.0f / (vp_a[i] * vp_a[i]) : r9s;
                     for (int j = 0; j < R; ++j) {
                         const ptrdiff_t o = j - h;
                         const size_t iz = i + o, iy = i + o * (ptrdiff_t)sy, ix = i + o * (ptrdiff_t)sx;
+                        const float cz = arrays ? tcz[iz] : czs, cy = arrays ? tcy[iy] : cys,
+                                    cx = arrays ? tcx[ix] : cxs;
                         H0 += w1z[j] * (gzv[iz] * (r18 * cz) - gzu[iz] * e2 * cz) +
                               w1x[j] * (gzv[ix] * (r18 * cx) - gzu[ix] * e2 * cx) +
                               w1y[j] * (gzv[iy] * (r18 * cy) - gzu[iy] * e2 * cy);
@@ -267,10 +293,11 @@ int oracle_tti_forward(float *u, float *v, int tsize, const int *alloc, int so, 
                     u1[i] = r26 * (e2 * lap + r10 * r9 * (2.0f * u0[i] - um[i]) + r11 * d * u0[i] + H0);
                     v1[i] = r26 * (r11 * d * v0[i] + r18 * lap - r9 * (-2.0f * r10 * v0[i] + r10 * vm[i]) + Hz);
                 }
-        inject(src, 3, u1, v1, sx, sy, so, lo, hi, time, 0, NULL, vp, dt);
+        inject(src, 3, u1, v1, sx, sy, so, lo, hi, time, vp_a ? 1 : 0, vp_a, vp, dt);
         interp(rec, 3, rec_toff ? u1 : u0, rec_toff ? v1 : v0, sx, sy, so, lo, hi, time);
     }
     free(gzu);
     free(gzv);
+    free(tcx); free(tcy); free(tcz); free(tsd);
     return 0;
 }

@@ -43,7 +43,8 @@ def load(fast=False):
     L.oracle_iso_forward.restype = c_int
     L.oracle_tti_forward.argtypes = [fp, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, fp, fp, fp,
                                      c_float, c_float, c_float, c_float, c_float, c_float, ip, ip,
-                                     c_int, c_int, POINTER(OSparse), POINTER(OSparse), c_int]
+                                     c_int, c_int, POINTER(OSparse), POINTER(OSparse), c_int,
+                                     fp, fp, fp, fp, fp]
     L.oracle_tti_forward.restype = c_int
     _libs[fast] = L
     return L
@@ -98,8 +99,10 @@ def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, par
 
 
 def tti_forward(u, v, so, w2, w1, dt, time_m, time_M, damp, vp, epsilon, delta, theta, phi,
-                src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False):
+                src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False, arrays=None):
+    """arrays: optional dict name -> (allocated-layout f32 array) for vp/epsilon/delta/theta/phi."""
     L = load(fast)
+    arrays = arrays or {}
     R = len(w2[0]) - 1
     alloc = np.array(u.shape[1:], dtype=np.int32)
     lo = np.array(lo if lo is not None else [0] * 3, dtype=np.int32)
@@ -112,7 +115,9 @@ def tti_forward(u, v, so, w2, w1, dt, time_m, time_M, damp, vp, epsilon, delta, 
     rc = L.oracle_tti_forward(_fp(u), _fp(v), u.shape[0], _ip(alloc), so, R, _fp(w2a[0]), _fp(w2a[1]),
                               _fp(w2a[2]), _fp(w1a[0]), _fp(w1a[1]), _fp(w1a[2]), _fp(damp), vp,
                               epsilon, delta, theta, phi, dt, _ip(lo), _ip(hi), time_m, time_M,
-                              ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, rec_toff)
+                              ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, rec_toff,
+                              _fp(arrays.get('vp')), _fp(arrays.get('epsilon')), _fp(arrays.get('delta')),
+                              _fp(arrays.get('theta')), _fp(arrays.get('phi')))
     assert rc == 0
     return u, v
 

@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# The CPU oracle uses OpenMP: keep its thread team small and make idle threads sleep instead of
+# spinning (busy-waiting teams made the small 2-D cases 10x slower on shared build hosts).
+os.environ.setdefault('OMP_NUM_THREADS', str(min(4, os.cpu_count() or 1)))
+os.environ.setdefault('OMP_WAIT_POLICY', 'passive')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -194,3 +194,32 @@ def test_adjoint_vs_reference_golden_and_dot_product():
     term1 = float(np.sum(np.asarray(srca.data, dtype=np.float64) * np.asarray(src.data, dtype=np.float64)))
     term2 = float(np.sum(np.asarray(rec.data, dtype=np.float64) ** 2))
     assert abs(term1 - term2) / abs(term2) < 1e-4
+
+
+def test_tti_array_parameters_vs_reference_golden():
+    """Preset `layers-tti` (vp, epsilon, delta, theta, phi arrays; SURVEY §8a a2, 48 B/point variant)."""
+    g = load_golden('tti3d_so4_layers')
+    from devito_b200.seismic import demo_model, setup_geometry, AnisotropicWaveSolver
+    model = demo_model('layers-tti', spacing=(10., 10., 10.), shape=(20, 20, 20), nbl=8, space_order=4,
+                       nlayers=3)
+    geometry = setup_geometry(model, float(g['tn']))
+    solver = AnisotropicWaveSolver(model, geometry, space_order=4)
+    assert solver.op_fwd().backend == 'cuda-sm100a'
+    rec, u, v, _ = solver.forward()
+    assert rel_linf(u.data, g['u']) < 1e-4
+    assert rel_linf(v.data, g['v']) < 1e-4
+    assert rel_linf(rec.data, g['rec']) < 1e-4
+
+
+def test_saved_wavefield():
+    """`save=nt` (time slot == time index, no modulo): the saved history ends with the same three
+    time levels as the buffered run."""
+    from devito_b200 import TimeFunction
+    model, geometry, solver = _solver('iso', 8, 24, 8, 100.0)
+    rec1, u1, _ = solver.forward()
+    rec2, u2, _ = solver.forward(save=True)
+    nt = geometry.nt
+    assert u2.data.shape[0] == nt
+    for t in range(nt - 3, nt):
+        assert np.array_equal(np.asarray(u2.data[t]), np.asarray(u1.data[t % 3]))
+    assert np.array_equal(np.asarray(rec1.data), np.asarray(rec2.data))
