@@ -464,6 +464,341 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 3 (fused, warp-specialised, radius 4): same data flow as k_tti_fused, reorganised so that
+// every x-direction tap comes from registers and the extended-tile (halo) part of Gz is produced
+// by helper warps instead of unbalancing the main warps.
+//   warpgroups 0-2 (384 threads): one float4 column each (24 x 64 tile). Register queues hold the
+//       x-history of u (9 planes), v (4 planes) and of the thread's own Gz(u), Gz(v) (4 planes):
+//       D+x, the x-taps of the Laplacian and D-x cost no shared-memory traffic at all.
+//   warpgroup 3: warp 0 = TMA producer; warps 1-3 = helpers computing Gz on the 102 halo groups of
+//       the extended tile (rows -2,-1,+TY and the float4 columns left/right of the tile).
+// 512 threads x 128 registers; the main path fits in 128 registers (ptxas: 4 bytes spilled), so no
+// `setmaxnreg` rebalancing is needed.
+// ------------------------------------------------------------------------------------------
+template <int TY>
+struct TtiWsCfg {
+    static constexpr int R = 4, H = 2, TZ = 64, RZ = 4;
+    static constexpr int PR = TY + 2 * R, BZ = TZ + 2 * RZ, GR = TY + R;
+    static constexpr int NUU = R + 3, NUV = R + 3, NG = 4, NB = 4;
+    static constexpr int PLANE = ((PR * BZ + 31) / 32) * 32;
+    static constexpr int GPLANE = ((GR * BZ + 31) / 32) * 32;
+    static constexpr int NMAIN = TY * 16;               // 384 for TY = 24
+    static constexpr int NHELP = 96;
+    static constexpr int NHALO = 3 * (BZ / 4) + 2 * TY; // 54 + 48
+    static constexpr size_t SMEM = (size_t)((NUU + NUV) * PLANE + 2 * NG * GPLANE) * 4 + 2 * NB * 8 + 128;
+};
+
+template <int TY>
+__global__ void __launch_bounds__(TY * 16 + 128, 1)
+k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v, const TtiFK k) {
+    using C = TtiWsCfg<TY>;
+    constexpr int R = 4, H = 2, TZ = C::TZ, RZ = C::RZ, BZ = C::BZ, PR = C::PR;
+    constexpr int NUU = C::NUU, NUV = C::NUV, NG = C::NG, NB = C::NB;
+    constexpr int PLANE = C::PLANE, GPLANE = C::GPLANE, NMAIN = C::NMAIN;
+    constexpr int PRE = 2 * R;
+    constexpr int NSYNC = NMAIN + C::NHELP;            // threads in the per-iteration barrier
+    constexpr int NARR = NMAIN / 32 + C::NHELP / 32;   // warps releasing a stage
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_u = reinterpret_cast<float *>(smem_raw);
+    float *s_v = s_u + NUU * PLANE;
+    float *s_gu = s_v + NUV * PLANE;
+    float *s_gv = s_gu + NG * GPLANE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_gv + NG * GPLANE);
+    uint64_t *empty = full + NB;
+
+    int b = blockIdx.x;
+    const int iz = b % k.ntz;
+    b /= k.ntz;
+    const int iy = b % k.nty;
+    const int ix = b / k.nty;
+    const int z0 = iz * TZ, y0 = iy * TY;
+    const int xs = k.xlo + ix * k.lx;
+    const int xe = min(xs + k.lx, k.xlo + k.xcount);
+    const int NIT = (xe - xs) + PRE;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) {
+            b2ptx::mbar_init(&full[i], 1);
+            b2ptx::mbar_init(&empty[i], NARR);
+        }
+        b2ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    auto wrap = [](int v, int n) { return v >= n ? v - n : v; };
+
+    if (tid >= NMAIN) {
+        // =================== warpgroup 3: producer + helpers ===================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int wtid = tid - NMAIN;
+        if (wtid < 32) {
+            if (lane == 0) {
+                b2ptx::tma_prefetch_desc(&tm_u);
+                b2ptx::tma_prefetch_desc(&tm_v);
+                for (int it = 0; it < NIT; ++it) {
+                    const int x = xs - PRE + it;
+                    if (it >= 3) {
+                        const int w = it - 3;
+                        b2ptx::mbar_wait(&empty[w % NB], (w / NB) & 1);
+                    }
+                    const int pu = x + R, pv = x + R;          // helpers run one plane ahead: v too
+                    const bool hv = pv >= xs - (R - 1);
+                    b2ptx::mbar_arrive_expect_tx(&full[it % NB], (uint32_t)(PR * BZ * 4) * (hv ? 2u : 1u));
+                    b2ptx::tma_load_4d(s_u + ((pu % NUU + NUU) % NUU) * PLANE, &tm_u, &full[it % NB],
+                                       k.oz + z0 - RZ, k.oy + y0 - R, k.ox + pu, k.slot0);
+                    if (hv)
+                        b2ptx::tma_load_4d(s_v + ((pv % NUV + NUV) % NUV) * PLANE, &tm_v, &full[it % NB],
+                                           k.oz + z0 - RZ, k.oy + y0 - R, k.ox + pv, k.slot0);
+                }
+            }
+            return;
+        }
+        // ---- helpers: Gz on the halo groups of the extended tile ----
+        const int hid = wtid - 32;
+        int hoff[2], hflag[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int g = hid + t * C::NHELP;
+            int gr, gc;
+            if (g < 3 * (BZ / 4)) {
+                const int rr = g / (BZ / 4);
+                gr = rr < 2 ? rr : TY + 2;
+                gc = g - rr * (BZ / 4);
+            } else {
+                const int kx = g - 3 * (BZ / 4);
+                gr = 2 + (kx >> 1);
+                gc = (kx & 1) ? BZ / 4 - 1 : 0;
+            }
+            hoff[t] = (gr + R - H) * BZ + 4 * gc;
+            hflag[t] = (g < C::NHALO ? 1 : 0) | (gc > 0 ? 2 : 0) | (gc < BZ / 4 - 1 ? 4 : 0);
+        }
+        int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
+            ig = ((xs - PRE) % NG + NG) % NG;
+        // Helpers run ONE PLANE AHEAD of the main warps: in iteration `it` they first join the
+        // barrier (which certifies their halo of plane x+1, computed last iteration), then produce
+        // the halo of plane x+2 while the main warps do stage B — they never sit on the critical path.
+        for (int it = 0; it < NIT; ++it) {
+            const int x = xs - PRE + it;
+            b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
+            asm volatile("bar.sync 1, %0;" ::"n"(NSYNC) : "memory");
+            if (x + 2 >= xs - H) {
+                const int sgz = wrap(ig + 2, NG) * GPLANE;
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (!(hflag[t] & 1)) continue;
+                    const int poff = hoff[t];
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        const float *ring = f ? s_v : s_u;
+                        const int nr = f ? NUV : NUU;
+                        const int i0 = f ? iv : iu;
+                        float4 rr = make_float4(0, 0, 0, 0);
+#pragma unroll
+                        for (int j = 0; j < R; ++j)         // planes x+1 .. x+4
+                            f4fma_(rr, k.w1x[j], b2ptx::lds128(ring + wrap(i0 + 1 + j, nr) * PLANE + poff));
+                        const float *fc = ring + wrap(i0 + 2, nr) * PLANE + poff;     // plane x+2
+#pragma unroll
+                        for (int j = 0; j < R; ++j)
+                            f4fma_(rr, k.w1y[j], b2ptx::lds128(fc + (j - H + 1) * BZ));
+                        const float4 l = (hflag[t] & 2) ? b2ptx::lds128(fc - 4) : make_float4(0, 0, 0, 0);
+                        const float4 c = b2ptx::lds128(fc);
+                        const float4 r = (hflag[t] & 4) ? b2ptx::lds128(fc + 4) : make_float4(0, 0, 0, 0);
+                        const float zz[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int j = 0; j < R; ++j) {
+                            const int o = 4 + j - H + 1;
+                            rr.x = fmaf(k.w1z[j], zz[o + 0], rr.x); rr.y = fmaf(k.w1z[j], zz[o + 1], rr.y);
+                            rr.z = fmaf(k.w1z[j], zz[o + 2], rr.z); rr.w = fmaf(k.w1z[j], zz[o + 3], rr.w);
+                        }
+                        *reinterpret_cast<float4 *>((f ? s_gv : s_gu) + sgz + poff - (R - H) * BZ) = rr;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) b2ptx::mbar_arrive(&empty[it % NB]);
+            iu = wrap(iu + 1, NUU);
+            iv = wrap(iv + 1, NUV);
+            ig = wrap(ig + 1, NG);
+        }
+        return;
+    }
+
+    // =================== main warpgroups ===================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int ty = tid / 16, tz4 = tid % 16;
+    const int gy = y0 + ty, gz = z0 + 4 * tz4;
+    const bool yok = gy < k.ny;
+    const int zcnt = yok ? min(max(k.nz - gz, 0), 4) : 0;
+    const int my_off = (ty + R) * BZ + RZ + 4 * tz4;
+    const int my_goff = (ty + H) * BZ + RZ + 4 * tz4;
+    const long long gidx0 = (long long)(k.oy + gy) * k.sy + (k.oz + gz);
+
+    float4 uq[2 * R + 1], vq[R], gqu[R], gqv[R];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i <= 2 * R; ++i) uq[i] = zero4;
+#pragma unroll
+    for (int i = 0; i < R; ++i) { vq[i] = zero4; gqu[i] = zero4; gqv[i] = zero4; }
+    const float wc = k.w2x[0] + k.w2y[0] + k.w2z[0];
+    long long gi = (long long)(k.ox + xs - PRE) * k.sx + gidx0;
+    int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
+        ig = ((xs - PRE) % NG + NG) % NG;
+
+    for (int it = 0; it < NIT; ++it) {
+        const int x = xs - PRE + it;
+        b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
+        // queues: uq[i] = u plane x-R+i, vq[i] = v plane x+i, gq*[i] = Gz plane x-H+i
+#pragma unroll
+        for (int i = 0; i < 2 * R; ++i) uq[i] = uq[i + 1];
+#pragma unroll
+        for (int i = 0; i < R - 1; ++i) { vq[i] = vq[i + 1]; gqu[i] = gqu[i + 1]; gqv[i] = gqv[i + 1]; }
+        uq[2 * R] = b2ptx::lds128(s_u + wrap(iu + R, NUU) * PLANE + my_off);
+        vq[R - 1] = b2ptx::lds128(s_v + wrap(iv + R - 1, NUV) * PLANE + my_off);
+
+        // ---- stage A: own-column Gz(u), Gz(v) at plane g = x + 1 ----
+        {
+            float4 ru = zero4, rv = zero4;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // x taps: planes x+j, from registers
+                f4fma_(ru, k.w1x[j], uq[R + j]);
+                f4fma_(rv, k.w1x[j], vq[j]);
+            }
+            const float *uc = s_u + wrap(iu + 1, NUU) * PLANE + my_off;
+            const float *vc = s_v + wrap(iv + 1, NUV) * PLANE + my_off;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // y taps: rows y-1..y+2 (own row from registers)
+                const float4 a = (j == H - 1) ? uq[R + 1] : b2ptx::lds128(uc + (j - H + 1) * BZ);
+                const float4 c = (j == H - 1) ? vq[1] : b2ptx::lds128(vc + (j - H + 1) * BZ);
+                f4fma_(ru, k.w1y[j], a);
+                f4fma_(rv, k.w1y[j], c);
+            }
+            {
+                const float4 lu = b2ptx::lds128(uc - 4), ru_ = b2ptx::lds128(uc + 4);
+                const float4 lv = b2ptx::lds128(vc - 4), rv_ = b2ptx::lds128(vc + 4);
+                const float4 cu = uq[R + 1], cv = vq[1];
+                const float zu[12] = {lu.x, lu.y, lu.z, lu.w, cu.x, cu.y, cu.z, cu.w, ru_.x, ru_.y, ru_.z, ru_.w};
+                const float zv[12] = {lv.x, lv.y, lv.z, lv.w, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y, rv_.z, rv_.w};
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int o = 4 + j - H + 1;
+                    ru.x = fmaf(k.w1z[j], zu[o + 0], ru.x); ru.y = fmaf(k.w1z[j], zu[o + 1], ru.y);
+                    ru.z = fmaf(k.w1z[j], zu[o + 2], ru.z); ru.w = fmaf(k.w1z[j], zu[o + 3], ru.w);
+                    rv.x = fmaf(k.w1z[j], zv[o + 0], rv.x); rv.y = fmaf(k.w1z[j], zv[o + 1], rv.y);
+                    rv.z = fmaf(k.w1z[j], zv[o + 2], rv.z); rv.w = fmaf(k.w1z[j], zv[o + 3], rv.w);
+                }
+            }
+            gqu[R - 1] = ru;
+            gqv[R - 1] = rv;
+            const int sgz = wrap(ig + 1, NG) * GPLANE + my_goff;
+            *reinterpret_cast<float4 *>(s_gu + sgz) = ru;
+            *reinterpret_cast<float4 *>(s_gv + sgz) = rv;
+        }
+        // u[t-1], v[t-1], A of the output plane: in flight across the barrier and the Laplacian
+        float4 pu = zero4, pv = zero4, pa = zero4;
+        if (x >= xs && zcnt == 4) {
+            pu = *reinterpret_cast<const float4 *>(k.um + gi);
+            pv = *reinterpret_cast<const float4 *>(k.vm + gi);
+            pa = *reinterpret_cast<const float4 *>(k.A + gi);
+        } else if (x >= xs && zcnt > 0) {
+            float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gi + i]; t[4 + i] = k.vm[gi + i]; t[8 + i] = k.A[gi + i]; }
+            pu = make_float4(t[0], t[1], t[2], t[3]);
+            pv = make_float4(t[4], t[5], t[6], t[7]);
+            pa = make_float4(t[8], t[9], t[10], t[11]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NSYNC) : "memory");
+
+        // ---- stage B: output plane x ----
+        if (x >= xs) {
+            const float *cpl = s_u + iu * PLANE + my_off;
+            const float4 c = uq[R];
+            const float4 vcn = vq[0];
+            float4 lap = make_float4(wc * c.x, wc * c.y, wc * c.z, wc * c.w);
+            {
+                const float4 l = b2ptx::lds128(cpl - 4), r = b2ptx::lds128(cpl + 4);
+                const float zr[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int i = 1; i <= R; ++i) {
+                    lap.x = fmaf(k.w2z[i], zr[4 - i] + zr[4 + i], lap.x);
+                    lap.y = fmaf(k.w2z[i], zr[5 - i] + zr[5 + i], lap.y);
+                    lap.z = fmaf(k.w2z[i], zr[6 - i] + zr[6 + i], lap.z);
+                    lap.w = fmaf(k.w2z[i], zr[7 - i] + zr[7 + i], lap.w);
+                }
+            }
+#pragma unroll
+            for (int i = 1; i <= R; ++i) {
+                const float4 a = b2ptx::lds128(cpl - i * BZ), bb = b2ptx::lds128(cpl + i * BZ);
+                lap.x = fmaf(k.w2y[i], a.x + bb.x, lap.x); lap.y = fmaf(k.w2y[i], a.y + bb.y, lap.y);
+                lap.z = fmaf(k.w2y[i], a.z + bb.z, lap.z); lap.w = fmaf(k.w2y[i], a.w + bb.w, lap.w);
+            }
+#pragma unroll
+            for (int i = 1; i <= R; ++i) {
+                const float4 a = uq[R - i], bb = uq[R + i];
+                lap.x = fmaf(k.w2x[i], a.x + bb.x, lap.x); lap.y = fmaf(k.w2x[i], a.y + bb.y, lap.y);
+                lap.z = fmaf(k.w2x[i], a.z + bb.z, lap.z); lap.w = fmaf(k.w2x[i], a.w + bb.w, lap.w);
+            }
+            float4 zu4 = zero4, zv4 = zero4;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // x direction: own Gz history (registers)
+                f4fma_(zu4, k.w1x[j], gqu[j]);
+                f4fma_(zv4, k.w1x[j], gqv[j]);
+            }
+            const float *gpu_ = s_gu + ig * GPLANE + my_goff;
+            const float *gpv_ = s_gv + ig * GPLANE + my_goff;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // y direction: rows y-2..y+1 (own row from registers)
+                const float4 a = (j == H) ? gqu[H] : b2ptx::lds128(gpu_ + (j - H) * BZ);
+                const float4 bb = (j == H) ? gqv[H] : b2ptx::lds128(gpv_ + (j - H) * BZ);
+                f4fma_(zu4, k.w1y[j], a);
+                f4fma_(zv4, k.w1y[j], bb);
+            }
+            {
+                const float4 lu = b2ptx::lds128(gpu_ - 4), ru_ = b2ptx::lds128(gpu_ + 4);
+                const float4 lv = b2ptx::lds128(gpv_ - 4), rv_ = b2ptx::lds128(gpv_ + 4);
+                const float4 cu = gqu[H], cv = gqv[H];
+                const float au[12] = {lu.x, lu.y, lu.z, lu.w, cu.x, cu.y, cu.z, cu.w, ru_.x, ru_.y, ru_.z, ru_.w};
+                const float av[12] = {lv.x, lv.y, lv.z, lv.w, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y, rv_.z, rv_.w};
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int o = 4 + j - H;
+                    zu4.x = fmaf(k.w1z[j], au[o + 0], zu4.x); zu4.y = fmaf(k.w1z[j], au[o + 1], zu4.y);
+                    zu4.z = fmaf(k.w1z[j], au[o + 2], zu4.z); zu4.w = fmaf(k.w1z[j], au[o + 3], zu4.w);
+                    zv4.x = fmaf(k.w1z[j], av[o + 0], zv4.x); zv4.y = fmaf(k.w1z[j], av[o + 1], zv4.y);
+                    zv4.z = fmaf(k.w1z[j], av[o + 2], zv4.z); zv4.w = fmaf(k.w1z[j], av[o + 3], zv4.w);
+                }
+            }
+            float4 ou, ov;
+#define B2_TTI_UPD(F)                                                              \
+            {                                                                      \
+                const float gh = lap.F - zu4.F;                                    \
+                const float H0 = fmaf(k.e2, gh, k.sd * zv4.F);                     \
+                const float Hz = fmaf(k.sd, gh, zv4.F);                            \
+                ou.F = fmaf(pa.F, fmaf(k.m_dt2, c.F - pu.F, H0), c.F);             \
+                ov.F = fmaf(pa.F, fmaf(k.m_dt2, vcn.F - pv.F, Hz), vcn.F);         \
+            }
+            B2_TTI_UPD(x) B2_TTI_UPD(y) B2_TTI_UPD(z) B2_TTI_UPD(w)
+#undef B2_TTI_UPD
+            if (zcnt == 4) {
+                *reinterpret_cast<float4 *>(k.u1 + gi) = ou;
+                *reinterpret_cast<float4 *>(k.v1 + gi) = ov;
+            } else if (zcnt > 0) {
+                const float tu[4] = {ou.x, ou.y, ou.z, ou.w}, tv[4] = {ov.x, ov.y, ov.z, ov.w};
+                for (int i = 0; i < zcnt; ++i) { k.u1[gi + i] = tu[i]; k.v1[gi + i] = tv[i]; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) b2ptx::mbar_arrive(&empty[it % NB]);
+        iu = wrap(iu + 1, NUU);
+        iv = wrap(iv + 1, NUV);
+        ig = wrap(ig + 1, NG);
+        gi += k.sx;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_tti_coef(const float *__restrict__ damp, float m_dt2, float inv_dt, float *__restrict__ A, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -499,6 +834,8 @@ static int tti_make_tmap(CUtensorMap *tm, const void *base, const int *a, int ts
     return B2_OK;
 }
 
+static bool tti_use_ws(int R);
+constexpr int kTtiWsTY = 24;
 template <int R> struct TtiTile;
 template <> struct TtiTile<2> { static constexpr int TY = 32; };
 template <> struct TtiTile<4> { static constexpr int TY = 28; };
@@ -542,7 +879,7 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         k_tti_coef<<<148 * 8, 256, 0, stream()>>>(p.damp, md, inv_dt, p.coefA, p.slot_elems);
         count_launch();
         B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
-        const int ty = p.R == 2 ? TtiTile<2>::TY : TtiTile<4>::TY;
+        const int ty = p.R == 2 ? TtiTile<2>::TY : (tti_use_ws(4) ? kTtiWsTY : TtiTile<4>::TY);
         if ((rc = tti_make_tmap(&p.tm_u, p.u, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
         if ((rc = tti_make_tmap(&p.tm_v, p.v, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
         return B2_OK;
@@ -574,14 +911,20 @@ static int env_int_tti(const char *name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+static bool tti_use_ws(int R) { return R == 4 && env_int_tti("B2_TTI_KERNEL", 3) == 3; }
 template <int R>
 static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
-    constexpr int TY = TtiTile<R>::TY;
-    using C = TtiCfg<R, TY>;
-    auto kern = k_tti_fused<R, TY>;
+    const bool ws = tti_use_ws(R);
+    constexpr int TYF = TtiTile<R>::TY;
+    const int TY = ws ? kTtiWsTY : TYF;
+    using C = TtiCfg<R, TYF>;
+    using CW = TtiWsCfg<kTtiWsTY>;
+    auto kern = k_tti_fused<R, TYF>;
+    auto kern_ws = k_tti_ws<kTtiWsTY>;
     static bool attr_set = false;
     if (!attr_set) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM), B2_ERR_LAUNCH);
+        B2_CUDA(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM), B2_ERR_LAUNCH);
         attr_set = true;
     }
     TtiFK k;
@@ -621,7 +964,10 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
     for (int i = 0; i < R; ++i) { k.w1x[i] = k.cx * p.w1[0][i]; k.w1y[i] = k.cy * p.w1[1][i]; k.w1z[i] = k.cz * p.w1[2][i]; }
     timing_begin();
-    kern<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
+    if (ws)
+        kern_ws<<<(unsigned)(k.ntz * k.nty * ntx), kTtiWsTY * 16 + 128, CW::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
+    else
+        kern<<<(unsigned)(k.ntz * k.nty * ntx), TYF * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
     timing_end();
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
@@ -677,3 +1023,4 @@ int tti_step(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xco
 }
 
 }  // namespace b2
+
