@@ -604,15 +604,14 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
 #pragma unroll
                         for (int j = 0; j < R; ++j)
                             f4fma_(rr, k.w1y[j], b2ptx::lds128(fc + (j - H + 1) * BZ));
-                        const float4 l = (hflag[t] & 2) ? b2ptx::lds128(fc - 4) : make_float4(0, 0, 0, 0);
+                        const float l = (hflag[t] & 2) ? fc[-1] : 0.f;
                         const float4 c = b2ptx::lds128(fc);
-                        const float4 r = (hflag[t] & 4) ? b2ptx::lds128(fc + 4) : make_float4(0, 0, 0, 0);
-                        const float zz[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
+                        const float2 r = (hflag[t] & 4) ? *reinterpret_cast<const float2 *>(fc + 4) : make_float2(0.f, 0.f);
+                        const float zz[7] = {l, c.x, c.y, c.z, c.w, r.x, r.y};
 #pragma unroll
                         for (int j = 0; j < R; ++j) {
-                            const int o = 4 + j - H + 1;
-                            rr.x = fmaf(k.w1z[j], zz[o + 0], rr.x); rr.y = fmaf(k.w1z[j], zz[o + 1], rr.y);
-                            rr.z = fmaf(k.w1z[j], zz[o + 2], rr.z); rr.w = fmaf(k.w1z[j], zz[o + 3], rr.w);
+                            rr.x = fmaf(k.w1z[j], zz[j + 0], rr.x); rr.y = fmaf(k.w1z[j], zz[j + 1], rr.y);
+                            rr.z = fmaf(k.w1z[j], zz[j + 2], rr.z); rr.w = fmaf(k.w1z[j], zz[j + 3], rr.w);
                         }
                         *reinterpret_cast<float4 *>((f ? s_gv : s_gu) + sgz + poff - (R - H) * BZ) = rr;
                     }
@@ -647,6 +646,7 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
     long long gi = (long long)(k.ox + xs - PRE) * k.sx + gidx0;
     int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
         ig = ((xs - PRE) % NG + NG) % NG;
+    float4 nu = zero4, nv = zero4, na = zero4;      // prefetched u[t-1], v[t-1], A of plane x+1
 
     for (int it = 0; it < NIT; ++it) {
         const int x = xs - PRE + it;
@@ -677,18 +677,20 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
                 f4fma_(rv, k.w1y[j], c);
             }
             {
-                const float4 lu = b2ptx::lds128(uc - 4), ru_ = b2ptx::lds128(uc + 4);
-                const float4 lv = b2ptx::lds128(vc - 4), rv_ = b2ptx::lds128(vc + 4);
+                // D+z needs z-1 .. z+5 of the row: one float left, two floats right (4-byte and
+                // 8-byte shared loads cost 1 and 2 wavefronts per warp instead of 4)
+                const float lu = uc[-1], lv = vc[-1];
+                const float2 ru_ = *reinterpret_cast<const float2 *>(uc + 4);
+                const float2 rv_ = *reinterpret_cast<const float2 *>(vc + 4);
                 const float4 cu = uq[R + 1], cv = vq[1];
-                const float zu[12] = {lu.x, lu.y, lu.z, lu.w, cu.x, cu.y, cu.z, cu.w, ru_.x, ru_.y, ru_.z, ru_.w};
-                const float zv[12] = {lv.x, lv.y, lv.z, lv.w, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y, rv_.z, rv_.w};
+                const float zu[7] = {lu, cu.x, cu.y, cu.z, cu.w, ru_.x, ru_.y};
+                const float zv[7] = {lv, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y};
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int o = 4 + j - H + 1;
-                    ru.x = fmaf(k.w1z[j], zu[o + 0], ru.x); ru.y = fmaf(k.w1z[j], zu[o + 1], ru.y);
-                    ru.z = fmaf(k.w1z[j], zu[o + 2], ru.z); ru.w = fmaf(k.w1z[j], zu[o + 3], ru.w);
-                    rv.x = fmaf(k.w1z[j], zv[o + 0], rv.x); rv.y = fmaf(k.w1z[j], zv[o + 1], rv.y);
-                    rv.z = fmaf(k.w1z[j], zv[o + 2], rv.z); rv.w = fmaf(k.w1z[j], zv[o + 3], rv.w);
+                for (int j = 0; j < R; ++j) {          // offsets j-1 relative to each of the 4 points
+                    ru.x = fmaf(k.w1z[j], zu[j + 0], ru.x); ru.y = fmaf(k.w1z[j], zu[j + 1], ru.y);
+                    ru.z = fmaf(k.w1z[j], zu[j + 2], ru.z); ru.w = fmaf(k.w1z[j], zu[j + 3], ru.w);
+                    rv.x = fmaf(k.w1z[j], zv[j + 0], rv.x); rv.y = fmaf(k.w1z[j], zv[j + 1], rv.y);
+                    rv.z = fmaf(k.w1z[j], zv[j + 2], rv.z); rv.w = fmaf(k.w1z[j], zv[j + 3], rv.w);
                 }
             }
             gqu[R - 1] = ru;
@@ -697,18 +699,22 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
             *reinterpret_cast<float4 *>(s_gu + sgz) = ru;
             *reinterpret_cast<float4 *>(s_gv + sgz) = rv;
         }
-        // u[t-1], v[t-1], A of the output plane: in flight across the barrier and the Laplacian
-        float4 pu = zero4, pv = zero4, pa = zero4;
-        if (x >= xs && zcnt == 4) {
-            pu = *reinterpret_cast<const float4 *>(k.um + gi);
-            pv = *reinterpret_cast<const float4 *>(k.vm + gi);
-            pa = *reinterpret_cast<const float4 *>(k.A + gi);
-        } else if (x >= xs && zcnt > 0) {
-            float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gi + i]; t[4 + i] = k.vm[gi + i]; t[8 + i] = k.A[gi + i]; }
-            pu = make_float4(t[0], t[1], t[2], t[3]);
-            pv = make_float4(t[4], t[5], t[6], t[7]);
-            pa = make_float4(t[8], t[9], t[10], t[11]);
+        // u[t-1], v[t-1], A: loaded one full iteration before they are used (the registers are
+        // there: the main warpgroups own 152 each after setmaxnreg)
+        const float4 pu = nu, pv = nv, pa = na;
+        {
+            const long long gn = gi + k.sx;                 // plane x + 1
+            if (x + 1 >= xs && x + 1 < xe && zcnt == 4) {
+                nu = *reinterpret_cast<const float4 *>(k.um + gn);
+                nv = *reinterpret_cast<const float4 *>(k.vm + gn);
+                na = *reinterpret_cast<const float4 *>(k.A + gn);
+            } else if (x + 1 >= xs && x + 1 < xe && zcnt > 0) {
+                float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gn + i]; t[4 + i] = k.vm[gn + i]; t[8 + i] = k.A[gn + i]; }
+                nu = make_float4(t[0], t[1], t[2], t[3]);
+                nv = make_float4(t[4], t[5], t[6], t[7]);
+                na = make_float4(t[8], t[9], t[10], t[11]);
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NSYNC) : "memory");
 
@@ -757,18 +763,19 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
                 f4fma_(zv4, k.w1y[j], bb);
             }
             {
-                const float4 lu = b2ptx::lds128(gpu_ - 4), ru_ = b2ptx::lds128(gpu_ + 4);
-                const float4 lv = b2ptx::lds128(gpv_ - 4), rv_ = b2ptx::lds128(gpv_ + 4);
+                // D-z needs z-2 .. z+4: two floats left, one float right
+                const float2 lu = *reinterpret_cast<const float2 *>(gpu_ - 2);
+                const float2 lv = *reinterpret_cast<const float2 *>(gpv_ - 2);
+                const float ru_ = gpu_[4], rv_ = gpv_[4];
                 const float4 cu = gqu[H], cv = gqv[H];
-                const float au[12] = {lu.x, lu.y, lu.z, lu.w, cu.x, cu.y, cu.z, cu.w, ru_.x, ru_.y, ru_.z, ru_.w};
-                const float av[12] = {lv.x, lv.y, lv.z, lv.w, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y, rv_.z, rv_.w};
+                const float au[7] = {lu.x, lu.y, cu.x, cu.y, cu.z, cu.w, ru_};
+                const float av[7] = {lv.x, lv.y, cv.x, cv.y, cv.z, cv.w, rv_};
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const int o = 4 + j - H;
-                    zu4.x = fmaf(k.w1z[j], au[o + 0], zu4.x); zu4.y = fmaf(k.w1z[j], au[o + 1], zu4.y);
-                    zu4.z = fmaf(k.w1z[j], au[o + 2], zu4.z); zu4.w = fmaf(k.w1z[j], au[o + 3], zu4.w);
-                    zv4.x = fmaf(k.w1z[j], av[o + 0], zv4.x); zv4.y = fmaf(k.w1z[j], av[o + 1], zv4.y);
-                    zv4.z = fmaf(k.w1z[j], av[o + 2], zv4.z); zv4.w = fmaf(k.w1z[j], av[o + 3], zv4.w);
+                for (int j = 0; j < R; ++j) {          // offsets j-2
+                    zu4.x = fmaf(k.w1z[j], au[j + 0], zu4.x); zu4.y = fmaf(k.w1z[j], au[j + 1], zu4.y);
+                    zu4.z = fmaf(k.w1z[j], au[j + 2], zu4.z); zu4.w = fmaf(k.w1z[j], au[j + 3], zu4.w);
+                    zv4.x = fmaf(k.w1z[j], av[j + 0], zv4.x); zv4.y = fmaf(k.w1z[j], av[j + 1], zv4.y);
+                    zv4.z = fmaf(k.w1z[j], av[j + 2], zv4.z); zv4.w = fmaf(k.w1z[j], av[j + 3], zv4.w);
                 }
             }
             float4 ou, ov;
