@@ -35,6 +35,26 @@ void timing_end();
 
 inline void count_launch() { ++g_launches; }
 
+// Length of the x-chunks a 2.5-D sweep is cut into. With `tiles` yz-tiles and one CTA per SM the
+// grid runs in ceil(tiles*nchunks/148) rounds; each chunk re-reads `prime` priming planes. Pick the
+// chunk count that minimises (wave quantisation) x (priming overhead) among chunks of at most 256
+// planes (longer chunks measured slower on B200: the kernel tail — the last CTAs running alone
+// cannot saturate HBM — grows with the CTA duration; profiles/README.md).
+inline int choose_chunk_len(int tiles, int xcount, int prime, int min_len) {
+    double best = 1e30;
+    int best_n = 1;
+    for (int n = 1; n <= 64; ++n) {
+        const int lx = (xcount + n - 1) / n;
+        if (n > 1 && lx < min_len) break;
+        if (lx > 256 && (xcount + n) / (n + 1) >= min_len) continue;
+        const double ctas = (double)tiles * n;
+        const double rounds = (double)((long long)((ctas + 147) / 148));
+        const double cost = rounds * 148.0 / ctas * (1.0 + (double)prime / lx);
+        if (cost < best - 1e-9) { best = cost; best_n = n; }
+    }
+    return (xcount + best_n - 1) / best_n;
+}
+
 #define B2_CUDA(call, code)                                                        \
     do {                                                                           \
         cudaError_t _e = (call);                                                   \

@@ -239,11 +239,24 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
                 float zr[4 + 2 * RZ];
 #pragma unroll
                 for (int m = 0; m < RZ / 4; ++m) {
-                    const float4 l = b2ptx::lds128(cp - RZ + 4 * m);
-                    zr[4 * m + 0] = l.x; zr[4 * m + 1] = l.y; zr[4 * m + 2] = l.z; zr[4 * m + 3] = l.w;
-                    const float4 r = b2ptx::lds128(cp + 4 + 4 * m);
-                    zr[RZ + 4 + 4 * m + 0] = r.x; zr[RZ + 4 + 4 * m + 1] = r.y;
-                    zr[RZ + 4 + 4 * m + 2] = r.z; zr[RZ + 4 + 4 * m + 3] = r.w;
+                    // the outermost segments are only partly used when R is not a multiple of 4
+                    // (R = 6: two floats each side): 8-byte loads halve their shared-memory wavefronts
+                    if (R % 4 == 2 && m == 0) {
+                        const float2 l = *reinterpret_cast<const float2 *>(cp - RZ + 2);
+                        zr[0] = 0.f; zr[1] = 0.f; zr[2] = l.x; zr[3] = l.y;
+                    } else {
+                        const float4 l = b2ptx::lds128(cp - RZ + 4 * m);
+                        zr[4 * m + 0] = l.x; zr[4 * m + 1] = l.y; zr[4 * m + 2] = l.z; zr[4 * m + 3] = l.w;
+                    }
+                    if (R % 4 == 2 && m == RZ / 4 - 1) {
+                        const float2 r = *reinterpret_cast<const float2 *>(cp + 4 + 4 * m);
+                        zr[RZ + 4 + 4 * m + 0] = r.x; zr[RZ + 4 + 4 * m + 1] = r.y;
+                        zr[RZ + 4 + 4 * m + 2] = 0.f; zr[RZ + 4 + 4 * m + 3] = 0.f;
+                    } else {
+                        const float4 r = b2ptx::lds128(cp + 4 + 4 * m);
+                        zr[RZ + 4 + 4 * m + 0] = r.x; zr[RZ + 4 + 4 * m + 1] = r.y;
+                        zr[RZ + 4 + 4 * m + 2] = r.z; zr[RZ + 4 + 4 * m + 3] = r.w;
+                    }
                 }
                 zr[RZ + 0] = c.x; zr[RZ + 1] = c.y; zr[RZ + 2] = c.z; zr[RZ + 3] = c.w;
                 float4 acc = make_float4(wc * c.x, wc * c.y, wc * c.z, wc * c.w);
@@ -484,13 +497,8 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     k.nty = (p.n[1] + T::TY - 1) / T::TY;
     // x-chunk length: enough CTAs for ~16 waves of 148 SMs, but chunks of at least 32 planes
     int lx = env_int("B2_ISO_LX", 0);
-    if (lx <= 0) {
-        const int tiles = k.ntz * k.nty;
-        const int want = 148 * 16;
-        int nchunks = std::max(1, want / std::max(1, tiles));
-        lx = std::max(32, (xcount + nchunks - 1) / nchunks);
-        lx = std::min(lx, xcount);
-    }
+    if (lx <= 0) lx = choose_chunk_len(k.ntz * k.nty, xcount, 2 * R, 32);
+    lx = std::min(lx, xcount);
     k.lx = lx;
     const int ntx = (xcount + lx - 1) / lx;
     k.slot0 = slot0;

@@ -952,12 +952,8 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     k.ntz = (p.n[2] + C::TZ - 1) / C::TZ;
     k.nty = (p.n[1] + TY - 1) / TY;
     int lx = env_int_tti("B2_TTI_LX", 0);
-    if (lx <= 0) {
-        const int tiles = k.ntz * k.nty;
-        int nchunks = std::max(1, (148 * 12) / std::max(1, tiles));
-        lx = std::max(48, (xcount + nchunks - 1) / nchunks);
-        lx = std::min(lx, xcount);
-    }
+    if (lx <= 0) lx = choose_chunk_len(k.ntz * k.nty, xcount, 2 * R, 32);
+    lx = std::min(lx, xcount);
     k.lx = lx;
     const int ntx = (xcount + lx - 1) / lx;
     k.slot0 = slot0;
