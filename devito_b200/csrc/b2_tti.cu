@@ -647,6 +647,7 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
     int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
         ig = ((xs - PRE) % NG + NG) % NG;
     float4 nu = zero4, nv = zero4, na = zero4;      // prefetched u[t-1], v[t-1], A of plane x+1
+    float4 mu = zero4, mv = zero4, ma = zero4;      // ... and of plane x+2
 
     for (int it = 0; it < NIT; ++it) {
         const int x = xs - PRE + it;
@@ -702,18 +703,15 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
         // u[t-1], v[t-1], A: loaded one full iteration before they are used (the registers are
         // there: the main warpgroups own 152 each after setmaxnreg)
         const float4 pu = nu, pv = nv, pa = na;
+        nu = mu; nv = mv; na = ma;
         {
-            const long long gn = gi + k.sx;                 // plane x + 1
-            if (x + 1 >= xs && x + 1 < xe && zcnt == 4) {
-                nu = *reinterpret_cast<const float4 *>(k.um + gn);
-                nv = *reinterpret_cast<const float4 *>(k.vm + gn);
-                na = *reinterpret_cast<const float4 *>(k.A + gn);
-            } else if (x + 1 >= xs && x + 1 < xe && zcnt > 0) {
-                float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-                for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gn + i]; t[4 + i] = k.vm[gn + i]; t[8 + i] = k.A[gn + i]; }
-                nu = make_float4(t[0], t[1], t[2], t[3]);
-                nv = make_float4(t[4], t[5], t[6], t[7]);
-                na = make_float4(t[8], t[9], t[10], t[11]);
+            // two-deep register prefetch; full 16-byte loads even on overhanging tiles (the row's
+            // halo makes them safe, stores are masked)
+            const long long gn = gi + 2 * k.sx;             // plane x + 2
+            if (x + 2 >= xs && x + 2 < xe && zcnt > 0) {
+                mu = *reinterpret_cast<const float4 *>(k.um + gn);
+                mv = *reinterpret_cast<const float4 *>(k.vm + gn);
+                ma = *reinterpret_cast<const float4 *>(k.A + gn);
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NSYNC) : "memory");
