@@ -48,7 +48,8 @@ class IsoArgs(Structure):
                 ('z_m', c_int), ('z_M', c_int), ('time_m', c_int), ('time_M', c_int),
                 ('src', POINTER(Sparse)), ('rec', POINTER(Sparse)), ('rec_toff', c_int),
                 ('errctl', c_int), ('deviceid', c_int), ('kernel', c_int),
-                ('halo', c_void_p), ('timers', POINTER(Profiler)), ('adjoint', c_int)]
+                ('halo', c_void_p), ('timers', POINTER(Profiler)), ('adjoint', c_int),
+                ('grad', POINTER(Dataobj)), ('usave', POINTER(Dataobj))]
 
 
 class TtiArgs(Structure):

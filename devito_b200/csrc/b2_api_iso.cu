@@ -40,6 +40,31 @@ int check_finite(const float *f, size_t n, bool &bad) {
     return B2_OK;
 }
 
+// Imaging condition (reference: `Inc(grad, -u * v.dt2)`, acoustic/operators.py:222):
+// grad[p] -= usave[time][p] * (v[t+1][p] - 2 v[t][p] + v[t-1][p]) / dt^2 over the iterated box.
+struct ImgK {
+    float *__restrict__ grad;
+    const float *__restrict__ us;
+    const float *__restrict__ v0;
+    const float *__restrict__ v1;
+    const float *__restrict__ v2;
+    long long sx, sy, gsx, gsy;      // strides of the wavefields / of grad
+    int n0, n1, n2, o0, o1, o2, g0, g1, g2;
+    float inv_dt2;
+};
+
+__global__ void __launch_bounds__(256) k_imaging(ImgK k) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (z >= k.n2 || y >= k.n1) return;
+    for (int x = blockIdx.z; x < k.n0; x += gridDim.z) {
+        const long long i = (long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z);
+        const long long g = (long long)(k.g0 + x) * k.gsx + (long long)(k.g1 + y) * k.gsy + (k.g2 + z);
+        const float d2 = (k.v1[i] - 2.0f * k.v0[i] + k.v2[i]) * k.inv_dt2;
+        k.grad[g] = k.grad[g] - k.us[i] * d2;
+    }
+}
+
 // Section timing with a reusable pool of CUDA events: 4 events per time step.
 struct StepEvents {
     std::vector<cudaEvent_t> ev;
@@ -74,7 +99,8 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     const int so = a->space_order;
     int rc = B2_OK;
 
-    DevArray u, damp, param;
+    DevArray u, damp, param, grad, usave;
+    bool staged_grad = false, staged_usave = false;
     SparseDev src, rec;
     IsoPlan p;
     FieldGeom g;
@@ -85,6 +111,9 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         int r1 = staged_u ? stage_out(u, code == B2_OK || code == B2_ERR_NAN) : B2_OK;
         if (staged_damp) stage_out(damp, false);
         if (staged_param) stage_out(param, false);
+        if (staged_usave) stage_out(usave, false);
+        int r3 = staged_grad ? stage_out(grad, code == B2_OK) : B2_OK;
+        if (code == B2_OK && r3) return r3;
         sparse_stage_out(src, false);
         int r2 = sparse_stage_out(rec, code == B2_OK || code == B2_ERR_NAN);
         if (code != B2_OK) return code;
@@ -104,6 +133,16 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     }
     if ((rc = sparse_stage_in(a->src, nd, src, true))) return cleanup(rc);
     if ((rc = sparse_stage_in(a->rec, nd, rec, true))) return cleanup(rc);
+    if (a->grad || a->usave) {
+        if (!a->grad || !a->usave || nd != 3) {
+            set_error("b2_iso_forward: the imaging condition needs both grad and usave (3-D)");
+            return cleanup(B2_ERR_INVALID);
+        }
+        if ((rc = stage_in(a->grad, 3, grad, true))) return cleanup(rc);
+        staged_grad = true;
+        if ((rc = stage_in(a->usave, 4, usave, true))) return cleanup(rc);
+        staged_usave = true;
+    }
 
     // ---- geometry in the internal 3-dim convention ----
     const int lo_in[3] = {a->x_m, a->y_m, a->z_m};
@@ -191,6 +230,30 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         if (per_step_events) se.next();
         const float *fr = p.u + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
         if ((rc = launch_interp(rec, g, fr, nullptr, time))) return cleanup(rc);
+        if (staged_grad) {
+            if (time < 0 || time >= usave.size[0]) {
+                set_error("b2_iso_forward: time=%d outside the saved wavefield (nt=%d)", time, usave.size[0]);
+                return cleanup(B2_ERR_INVALID);
+            }
+            ImgK ik;
+            ik.grad = (float *)grad.d;
+            ik.us = (const float *)usave.d + (size_t)time * p.slot_elems;
+            ik.v0 = p.u + (size_t)t0 * p.slot_elems;
+            ik.v1 = p.u + (size_t)t1 * p.slot_elems;
+            ik.v2 = p.u + (size_t)t2 * p.slot_elems;
+            ik.sx = p.sx; ik.sy = p.sy;
+            ik.gsy = grad.size[2];
+            ik.gsx = (long long)grad.size[1] * grad.size[2];
+            const int gh = a->grad->hsize ? a->grad->hsize[0] : (grad.size[0] - (u.size[1] - 2 * so)) / 2;
+            ik.n0 = p.n[0]; ik.n1 = p.n[1]; ik.n2 = p.n[2];
+            ik.o0 = p.o[0]; ik.o1 = p.o[1]; ik.o2 = p.o[2];
+            ik.g0 = a->x_m + gh; ik.g1 = a->y_m + gh; ik.g2 = a->z_m + gh;
+            ik.inv_dt2 = 1.0f / (a->dt * a->dt);
+            dim3 blk(64, 4, 1), grd((ik.n2 + 63) / 64, (ik.n1 + 3) / 4, (unsigned)(ik.n0 < 65535 ? ik.n0 : 65535));
+            k_imaging<<<grd, blk, 0, stream()>>>(ik);
+            count_launch();
+            B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+        }
         if (per_step_events) se.next();
         if (a->errctl && ((time - a->time_m) % 100 == 99 || time == (a->adjoint ? a->time_m : a->time_M))) {
             bool bad = false;

@@ -190,7 +190,9 @@ class Operator:
         eqs = [o for k, o in self._items if k == 'eq']
         injs = [o for k, o in self._items if k == 'inject']
         itps = [o for k, o in self._items if k == 'interp']
-        if not eqs or any(e.is_Increment for e in eqs):
+        incs = [e for e in eqs if e.is_Increment]
+        eqs = [e for e in eqs if not e.is_Increment]
+        if not eqs:
             raise _Unrecognised("no plain time-update equations")
         updates = []
         for e in eqs:
@@ -209,8 +211,15 @@ class Operator:
             updates.append((f, e))
         if len(injs) > 1 or len(itps) > 1:
             raise _Unrecognised("more than one injection/interpolation")
+        if incs and len(updates) != 1:
+            raise _Unrecognised("increments are only supported next to a single acoustic update")
+        if len(incs) > 1:
+            raise _Unrecognised("more than one increment")
         if len(updates) == 1:
-            return self._recognise_iso(updates[0], injs, itps)
+            plan = self._recognise_iso(updates[0], injs, itps)
+            if incs:
+                self._attach_imaging(plan, incs[0])
+            return plan
         if len(updates) == 2:
             if self._dirn != 1:
                 raise _Unrecognised("adjoint TTI is not on the fast path")
@@ -463,6 +472,64 @@ class Operator:
             plan['rec'] = sf
             plan['rec_toff'] = 1 if toffs.pop() != 0 else 0
 
+    def _attach_imaging(self, plan, inc):
+        """`Inc(grad, -u * v.dt2)` next to the adjoint update = the reference's Gradient operator
+        (examples/seismic/acoustic/operators.py:190-232)."""
+        v = plan['u']
+        grid = plan['grid']
+        lhs = inc.lhs
+        if not (lhs.is_Access and isinstance(lhs.function, Function) and not lhs.function.is_TimeFunction):
+            raise _Unrecognised("increment target is not a Function")
+        if grid.dim != 3 or lhs.function.grid is not grid:
+            raise _Unrecognised("imaging condition is 3-D only")
+        k = _space_offsets(lhs, None)
+        if k is None or any(k[1]):
+            raise _Unrecognised("increment target accessed off-centre")
+        rhs = inc.rhs.evaluate
+        if self._subs:
+            rhs = rhs.subs(self._subs)
+        try:
+            terms, rest = linear_terms(rhs, lambda a: a.function is v)
+        except NonLinear as e:
+            raise _Unrecognised(f"increment is not linear in the adjoint wavefield: {e}") from None
+        if not (rest.is_Number and float(rest.value) == 0.0):
+            raise _Unrecognised("increment has terms without the adjoint wavefield")
+        keyed = {}
+        for acc, coef in terms.items():
+            kk = _space_offsets(acc, None)
+            if kk is None or any(kk[1]):
+                raise _Unrecognised("increment reads the adjoint wavefield off-centre")
+            keyed[kk[0]] = coef
+        if set(keyed) != {-1, 0, 1}:
+            raise _Unrecognised("increment is not u * v.dt2")
+        funcs, consts, syms = self._leaves(keyed.values())
+        saved = [a for a in funcs if getattr(a.function, 'is_TimeFunction', False)]
+        if len(saved) != 1 or len(funcs) != 1 or consts:
+            raise _Unrecognised("increment must multiply v.dt2 by one saved wavefield")
+        us = saved[0]
+        ku = _space_offsets(us, None)
+        if us.function.is_buffered or ku is None or ku[0] != 0 or any(ku[1]) or \
+                us.function.space_order != v.space_order:
+            raise _Unrecognised("the forward wavefield must be saved (save=nt) and read at (time, x, y, z)")
+        rng = np.random.default_rng(7)
+        dtname = plan['dt'].name
+        for probe in range(2):
+            uval, dt = rng.uniform(0.5, 2.0), rng.uniform(0.5, 2.0)
+
+            def leaf(n):
+                if n.is_Access:
+                    return uval
+                if n.name == dtname:
+                    return dt
+                raise _Unrecognised(f"unknown symbol {n.name} in the increment")
+            c = {t: eval_scalar(e, leaf) for t, e in keyed.items()}
+            want = {-1: -uval / dt ** 2, 0: 2 * uval / dt ** 2, 1: -uval / dt ** 2}
+            for t in want:
+                if abs(c[t] - want[t]) > 1e-9 * abs(want[t]):
+                    raise _Unrecognised("increment is not -u * v.dt2")
+        plan['grad'] = lhs.function
+        plan['usave'] = us.function
+
     # -- TTI -------------------------------------------------------------------------------------
     def _recognise_tti(self, updates, injs, itps):
         (u, equ), (v, eqv) = updates
@@ -711,6 +778,12 @@ class Operator:
         if damp is not None and not isinstance(damp, Function):
             raise InvalidArgument("`damp` override must be a Function")
         args['damp'] = damp
+        args['grad'] = self._resolve(kwargs, p.get('grad'))
+        args['usave'] = self._resolve(kwargs, p.get('usave'))
+        if args['usave'] is not None:
+            us = args['usave']
+            if not isinstance(us, TimeFunction) or us.is_buffered or us.space_order != p['so']:
+                raise InvalidArgument("the forward wavefield override must be a saved TimeFunction")
         # parameters
         if p['kind'] == 'iso':
             kind, obj = p['m_role']
@@ -772,6 +845,8 @@ class Operator:
         # time range (devito/types/dimension.py:279-331)
         sized = [s for s in (src, rec) if s is not None]
         sized += [f for f in fields if not f.is_buffered]
+        if args.get('usave') is not None:
+            sized.append(args['usave'])
         time_m = kwargs.pop('time_m', None)
         time_M = kwargs.pop('time_M', kwargs.pop('time', None))
         if time_m is None:
@@ -967,6 +1042,9 @@ class Operator:
         timers = L_.Profiler()
         a.timers = ctypes.pointer(timers)
         a.adjoint = 1 if p.get('adjoint') else 0
+        if args.get('grad') is not None:
+            a.grad = self._field_obj(args['grad'], dev, res, hold, written=True).ptr
+            a.usave = self._field_obj(args['usave'], dev, res, hold).ptr
         if p.get('inject_literal'):
             # injection used a literal dt**2 (not the `dt` symbol): it must agree with runtime dt
             if abs(p['inject_dt2'] - a.dt * a.dt) > 1e-5 * p['inject_dt2']:

@@ -1,9 +1,9 @@
 """Isotropic acoustic modelling (mirror of examples/seismic/acoustic/operators.py:50-187 and
 wavesolver.py:11-156): forward and adjoint operators (gradient/Born are SURVEY §8f)."""
-from .. import Eq, Operator, TimeFunction, solve
+from .. import Eq, Inc, Function, Operator, TimeFunction, solve
 from ..tools import memoized_meth
 
-__all__ = ['iso_stencil', 'ForwardOperator', 'AdjointOperator', 'AcousticWaveSolver']
+__all__ = ['iso_stencil', 'ForwardOperator', 'AdjointOperator', 'GradientOperator', 'AcousticWaveSolver']
 
 
 def iso_stencil(field, model, kernel='OT2', **kwargs):
@@ -44,6 +44,23 @@ def AdjointOperator(model, geometry, space_order=4, kernel='OT2', save=None, **k
     return Operator(eqn + receivers + source_a, subs=model.spacing_map, name='Adjoint', **kwargs)
 
 
+def GradientOperator(model, geometry, space_order=4, save=True, kernel='OT2', **kwargs):
+    """operators.py:190-232: adjoint propagation of the data + imaging condition grad -= u * v.dt2."""
+    if kernel != 'OT2':
+        raise NotImplementedError("only the OT2 kernel is on this backend's path")
+    m = model.m
+    grad = Function(name='grad', grid=model.grid)
+    u = TimeFunction(name='u', grid=model.grid, save=geometry.nt if save else None, time_order=2,
+                     space_order=space_order)
+    v = TimeFunction(name='v', grid=model.grid, save=None, time_order=2, space_order=space_order)
+    rec = geometry.rec
+    s = model.grid.stepping_dim.spacing
+    eqn = iso_stencil(v, model, kernel, forward=False)
+    gradient_update = Inc(grad, -u * v.dt2)
+    receivers = rec.inject(field=v.backward, expr=rec * s ** 2 / m)
+    return Operator(eqn + receivers + [gradient_update], subs=model.spacing_map, name='Gradient', **kwargs)
+
+
 class AcousticWaveSolver:
     """wavesolver.py:11-120 (`forward` only)."""
 
@@ -77,6 +94,24 @@ class AcousticWaveSolver:
         kwargs.update(model.physical_params(**kwargs))
         summary = self.op_adj().apply(srca=srca, rec=rec, v=v, dt=kwargs.pop('dt', self.dt), **kwargs)
         return srca, v, summary
+
+    @memoized_meth
+    def op_grad(self, save=True):
+        return GradientOperator(self.model, save=save, geometry=self.geometry, kernel=self.kernel,
+                                space_order=self.space_order, **self._kwargs)
+
+    def jacobian_adjoint(self, rec, u, src=None, v=None, grad=None, model=None, **kwargs):
+        """wavesolver.py:158-230 (without checkpointing): gradient of the data misfit w.r.t. m."""
+        dt = kwargs.pop('dt', self.dt)
+        grad = grad or Function(name='grad', grid=self.model.grid)
+        v = v or TimeFunction(name='v', grid=self.model.grid, time_order=2, space_order=self.space_order)
+        model = model or self.model
+        kwargs.update(model.physical_params(**kwargs))
+        summary = self.op_grad().apply(rec=rec, grad=grad, v=v, u=u, dt=dt, **kwargs)
+        return grad, summary
+
+    jacobian_adjoint.__name__ = 'jacobian_adjoint'
+    gradient = jacobian_adjoint
 
     def forward(self, src=None, rec=None, u=None, model=None, save=None, **kwargs):
         src = src or self.geometry.src

@@ -116,6 +116,12 @@ struct b2_iso_args {
                                        * u[t], u[t+1]; `src` is injected into u[t-1] (the     *
                                        * receiver data), `rec` samples u[t + rec_toff]        *
                                        * (rec_toff in {0,-1})                                 */
+    /* imaging condition of the reference's `Gradient` operator (acoustic/operators.py:190-232):
+     * after each (adjoint) step   grad -= usave[time] * (u[t+1] - 2 u[t] + u[t-1]) / dt^2.
+     * `usave` is the forward wavefield saved with save=nt (same layout as u, nt time slots);
+     * `grad` may have its own halo width (hsize). Both NULL -> no imaging condition.          */
+    struct b2_dataobj *grad;
+    struct b2_dataobj *usave;
 };
 int b2_iso_forward(const struct b2_iso_args *a);
 

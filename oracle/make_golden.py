@@ -89,6 +89,23 @@ def adjoint(name, so, n, nbl, tn):
          src=np.array(geometry.src.data), norm_v=np.float32(norm(v)))
 
 
+def gradient(name, so, n, nbl, tn):
+    """Forward with the saved wavefield, then the Gradient operator (acoustic/operators.py:190-232,
+    wavesolver.py:158-230): adjoint propagation of the data + imaging condition."""
+    from devito import norm
+    from examples.seismic import demo_model, setup_geometry
+    from examples.seismic.acoustic import AcousticWaveSolver
+    model = demo_model('constant-isotropic', spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl,
+                       space_order=so, dtype=np.float32)
+    geometry = setup_geometry(model, tn)
+    solver = AcousticWaveSolver(model, geometry, space_order=so)
+    rec, u, _ = solver.forward(save=True)
+    grad, _ = solver.jacobian_adjoint(rec, u)
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(model.critical_dt), nt=geometry.nt,
+         rec=np.array(rec.data), grad=np.array(grad.data), norm_grad=np.float32(norm(grad)),
+         u_last=np.array(u.data[geometry.nt - 1]))
+
+
 def tti(name, so, n, nbl, tn, preset='constant-tti', **kw):
     from devito import norm
     from examples.seismic import demo_model, setup_geometry
@@ -126,7 +143,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'tti8', 'tti4', 'tti4layers', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'iso8' in which:
@@ -139,6 +156,8 @@ if __name__ == '__main__':
         acoustic('iso3d_so8_sinc', so=8, n=20, nbl=8, tn=100.0, interpolation='sinc')
     if 'adj8' in which:
         adjoint('adj3d_so8', so=8, n=20, nbl=8, tn=150.0)
+    if 'grad8' in which:
+        gradient('grad3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'tti8' in which:
         tti('tti3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'tti4layers' in which:

@@ -127,8 +127,11 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                        const float *wx, const float *wy, const float *wz, const float *damp,
                        int param_kind, const float *param, float vp, float dt, const int *lo,
                        const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
-                       int rec_toff, int adjoint) {
-    /* adjoint != 0: the reference's `Adjoint` operator (acoustic/operators.py:153-187) — the same
+                       int rec_toff, int adjoint, float *grad, const int *galloc, int ghalo,
+                       const float *usave) {
+    /* grad/usave != NULL: imaging condition of the reference's `Gradient` operator
+     * (acoustic/operators.py:222): after each step grad -= usave[time] * u.dt2 (3-D only).
+     * adjoint != 0: the reference's `Adjoint` operator (acoustic/operators.py:153-187) — the same
      * update with the roles of t+1 / t-1 exchanged, time running from time_M down to time_m */
     const int R = radius;
     size_t sx, sy, slot;
@@ -188,6 +191,18 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
         }
         inject(src, ndim, u1, NULL, sx, sy, so, lo, hi, time, param_kind, param, vp, dt);
         interp(rec, ndim, rec_toff ? u1 : u0, NULL, sx, sy, so, lo, hi, time);
+        if (grad && usave && ndim == 3) {
+            const float *us = usave + (size_t)time * slot;
+            const size_t gsy = (size_t)galloc[2], gsx = (size_t)galloc[1] * galloc[2];
+#pragma omp parallel for collapse(2) schedule(static)
+            for (int x = lo[0]; x <= hi[0]; ++x)
+                for (int y = lo[1]; y <= hi[1]; ++y)
+                    for (int z = lo[2]; z <= hi[2]; ++z) {
+                        const size_t i = IDX3(x + so, y + so, z + so);
+                        const size_t g = (size_t)(x + ghalo) * gsx + (size_t)(y + ghalo) * gsy + (z + ghalo);
+                        grad[g] += -us[i] * (r2 * u1[i] - 2.0f * r2 * u0[i] + r2 * um[i]);
+                    }
+        }
     }
     return 0;
 }

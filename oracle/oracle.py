@@ -39,7 +39,7 @@ def load(fast=False):
     fp, ip = POINTER(c_float), POINTER(c_int)
     L.oracle_iso_forward.argtypes = [c_int, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, c_int, fp,
                                      c_float, c_float, ip, ip, c_int, c_int, POINTER(OSparse),
-                                     POINTER(OSparse), c_int, c_int]
+                                     POINTER(OSparse), c_int, c_int, fp, ip, c_int, fp]
     L.oracle_iso_forward.restype = c_int
     L.oracle_tti_forward.argtypes = [fp, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, fp, fp, fp,
                                      c_float, c_float, c_float, c_float, c_float, c_float, ip, ip,
@@ -76,8 +76,10 @@ def _sparse(data, gp, ws, r, keep):
 
 
 def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, param_kind=0,
-                src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False, adjoint=False):
-    """u: (T, [nx+2so,] ny+2so, nz+2so) float32 C-contiguous, updated in place.
+                src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False, adjoint=False,
+                grad=None, ghalo=0, usave=None):
+    """grad (3-D, halo `ghalo`) / usave (nt, ...) enable the Gradient operator's imaging condition.
+    u: (T, [nx+2so,] ny+2so, nz+2so) float32 C-contiguous, updated in place.
     w: list (per dim) of weights [0..R] incl. 1/h^2. src/rec: dict(data, gp, w, r)."""
     L = load(fast)
     nd = u.ndim - 1
@@ -89,11 +91,14 @@ def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, par
     keep = []
     s = _sparse(src['data'], src['gp'], src['w'], src['r'], keep) if src else None
     r = _sparse(rec['data'], rec['gp'], rec['w'], rec['r'], keep) if rec else None
+    galloc = np.array(grad.shape, dtype=np.int32) if grad is not None else None
     rc = L.oracle_iso_forward(nd, _fp(u), u.shape[0], _ip(alloc), so, R, _fp(wa[0]), _fp(wa[1]),
                               _fp(wa[2]) if wa[2] is not None else None, _fp(damp), param_kind,
                               _fp(param), vp, dt, _ip(lo), _ip(hi), time_m, time_M,
                               ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, rec_toff,
-                              1 if adjoint else 0)
+                              1 if adjoint else 0, _fp(grad),
+                              _ip(galloc) if galloc is not None else None,
+                              ghalo, _fp(usave))
     assert rc == 0
     return u
 

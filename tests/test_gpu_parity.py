@@ -223,3 +223,17 @@ def test_saved_wavefield():
     for t in range(nt - 3, nt):
         assert np.array_equal(np.asarray(u2.data[t]), np.asarray(u1.data[t % 3]))
     assert np.array_equal(np.asarray(rec1.data), np.asarray(rec2.data))
+
+
+def test_gradient_vs_reference_golden():
+    """Gradient operator (acoustic/operators.py:190-232): saved forward wavefield,
+    adjoint propagation of the data, imaging condition grad -= u * v.dt2."""
+    from devito_b200 import norm
+    g = load_golden('grad3d_so8')
+    model, geometry, solver = _solver('iso', 8, int(g['n']), int(g['nbl']), float(g['tn']))
+    assert solver.op_grad().backend == 'cuda-sm100a'
+    rec, u, _ = solver.forward(save=True)
+    assert rel_linf(u.data[geometry.nt - 1], g['u_last']) < 1e-5
+    grad, _ = solver.jacobian_adjoint(rec, u)
+    assert rel_linf(grad.data, g['grad']) < 1e-4
+    assert abs(float(norm(grad)) - float(g['norm_grad'])) < 1e-4 * float(g['norm_grad'])
