@@ -47,18 +47,20 @@ def setup_geometry(model, tn, f0=0.010, interpolation='linear', **kwargs):
 
 
 class AcquisitionGeometry:
+    """Source/receiver positions plus the time axis of one shot (examples/seismic/utils.py:56-209).
+    `.src` / `.rec` build fresh sparse functions on every access, like the reference."""
+
     def __init__(self, model, rec_positions, src_positions, t0, tn, **kwargs):
-        self.src_positions = np.reshape(src_positions, (-1, model.dim))
-        self.rec_positions = np.reshape(rec_positions, (-1, model.dim))
-        self._nrec = self.rec_positions.shape[0]
-        self._nsrc = self.src_positions.shape[0]
+        ndim = model.dim
+        self.rec_positions = np.asarray(rec_positions, dtype=np.float64).reshape(-1, ndim)
+        self.src_positions = np.asarray(src_positions, dtype=np.float64).reshape(-1, ndim)
         self._src_type = kwargs.get('src_type')
-        assert self._src_type in sources or self._src_type is None
-        self._f0 = kwargs.get('f0')
-        self._a = kwargs.get('a')
-        self._t0w = kwargs.get('t0w')
-        self._grid = model.grid
-        self._model = model
+        if self._src_type is not None and self._src_type not in sources:
+            raise ValueError(f"unknown source type {self._src_type!r}")
+        self._f0, self._a, self._t0w = kwargs.get('f0'), kwargs.get('a'), kwargs.get('t0w')
+        if self._src_type is not None and self._f0 is None:
+            raise ValueError(f"Peak frequency must be provided in KHz for source of type {self._src_type}")
+        self._model, self._grid = model, model.grid
         self._dt = model.critical_dt
         self._t0, self._tn = t0, tn
         self._interpolation = kwargs.get('interpolation', 'linear')
@@ -68,49 +70,41 @@ class AcquisitionGeometry:
         self._dt = dt
         return self
 
-    @property
-    def time_axis(self): return TimeAxis(start=self.t0, stop=self.tn, step=self.dt)
-    @property
-    def src_type(self): return self._src_type
-    @property
-    def grid(self): return self._grid
-    @property
-    def f0(self): return self._f0
-    @property
-    def tn(self): return self._tn
-    @property
-    def t0(self): return self._t0
-    @property
-    def dt(self): return self._dt
-    @property
-    def nt(self): return self.time_axis.num
-    @property
-    def nrec(self): return self._nrec
-    @property
-    def nsrc(self): return self._nsrc
-    @property
-    def dtype(self): return self.grid.dtype
-    @property
-    def r(self): return self._r
-    @property
-    def interpolation(self): return self._interpolation
+    # read-only views -------------------------------------------------------------------------------
+    grid = property(lambda self: self._grid)
+    src_type = property(lambda self: self._src_type)
+    f0 = property(lambda self: self._f0)
+    t0 = property(lambda self: self._t0)
+    tn = property(lambda self: self._tn)
+    dt = property(lambda self: self._dt)
+    r = property(lambda self: self._r)
+    interpolation = property(lambda self: self._interpolation)
+    dtype = property(lambda self: self._grid.dtype)
+    nrec = property(lambda self: self.rec_positions.shape[0])
+    nsrc = property(lambda self: self.src_positions.shape[0])
 
     @property
-    def rec(self): return self.new_rec()
+    def time_axis(self):
+        return TimeAxis(start=self._t0, stop=self._tn, step=self._dt)
+
+    @property
+    def nt(self):
+        return self.time_axis.num
+
+    # sparse functions ------------------------------------------------------------------------------
+    def _common(self):
+        return dict(grid=self._grid, time_range=self.time_axis, interpolation=self._interpolation, r=self._r)
 
     def new_rec(self, name='rec', coordinates=None):
-        coords = coordinates if coordinates is not None else self.rec_positions
-        return Receiver(name=name, grid=self.grid, time_range=self.time_axis, npoint=self.nrec,
-                        interpolation=self.interpolation, r=self._r, coordinates=coords)
-
-    @property
-    def src(self): return self.new_src()
+        pos = self.rec_positions if coordinates is None else coordinates
+        return Receiver(name=name, npoint=self.nrec, coordinates=pos, **self._common())
 
     def new_src(self, name='src', src_type='self', coordinates=None):
-        coords = coordinates if coordinates is not None else self.src_positions
-        if self.src_type is None or src_type is None:
-            return PointSource(name=name, grid=self.grid, time_range=self.time_axis, npoint=self.nsrc,
-                               coordinates=coords, interpolation=self.interpolation, r=self._r)
-        return sources[self.src_type](name=name, grid=self.grid, f0=self.f0, time_range=self.time_axis,
-                                      npoint=self.nsrc, coordinates=coords, t0=self._t0w, a=self._a,
-                                      interpolation=self.interpolation, r=self._r)
+        pos = self.src_positions if coordinates is None else coordinates
+        if self._src_type is None or src_type is None:
+            return PointSource(name=name, npoint=self.nsrc, coordinates=pos, **self._common())
+        return sources[self._src_type](name=name, npoint=self.nsrc, coordinates=pos, f0=self._f0,
+                                       t0=self._t0w, a=self._a, **self._common())
+
+    rec = property(lambda self: self.new_rec())
+    src = property(lambda self: self.new_src())

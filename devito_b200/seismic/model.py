@@ -40,6 +40,8 @@ def initialize_damp(damp, padsizes, spacing, abc_type="damp", fs=False):
 
 
 class PhysicalDomain(SubDomain):
+    """The whole grid (no free surface on this backend's path) — kept so that equations written
+    with `subdomain=model.grid.subdomains['physdomain']` work unchanged."""
     name = 'physdomain'
 
     def __init__(self, so, fs=False):
@@ -47,170 +49,168 @@ class PhysicalDomain(SubDomain):
         self.so, self.fs = so, fs
 
     def define(self, dimensions):
-        out = {d: d for d in dimensions}
+        spec = dict.fromkeys(dimensions)
+        for d in dimensions:
+            spec[d] = d
         if self.fs:
-            out[dimensions[-1]] = ('middle', self.so, 0)
-        return out
+            spec[dimensions[-1]] = ('middle', self.so, 0)
+        return spec
+
+
+_PARAMETER_NAMES = ('vp', 'damp', 'vs', 'b', 'epsilon', 'delta', 'theta', 'phi', 'qp', 'qs', 'lam', 'mu')
 
 
 class SeismicModel:
-    """Velocity model + absorbing layers on a `Grid` that includes `nbl` points per side."""
-    _known_parameters = ['vp', 'damp', 'vs', 'b', 'epsilon', 'delta', 'theta', 'phi', 'qp', 'qs',
-                         'lam', 'mu']
+    """Physical model on a grid extended by `nbl` absorbing points per side.
 
-    def __init__(self, origin, spacing, shape, space_order, vp, nbl=20, fs=False,
-                 dtype=np.float32, subdomains=(), bcs="mask", grid=None, topology=None, **kwargs):
-        self.shape = tuple(shape)
-        self.space_order = space_order
-        self.nbl = int(nbl)
-        self.origin = tuple(dtype(o) for o in origin)
-        self.fs = fs
+    Same constructor as the reference's `SeismicModel` (examples/seismic/model.py:238-322):
+    `origin, spacing, shape, space_order, vp, nbl, dtype, bcs, **parameters` where every physical
+    parameter is either a scalar (-> `Constant`) or an ndarray over the physical `shape`
+    (-> `Function`, edge-padded into the absorbing layers and the halo)."""
+    _known_parameters = list(_PARAMETER_NAMES)
+
+    def __init__(self, origin, spacing, shape, space_order, vp, nbl=20, fs=False, dtype=np.float32,
+                 subdomains=(), bcs="mask", grid=None, topology=None, **kwargs):
         if fs:
             raise NotImplementedError("free-surface models are outside this backend's scope (SURVEY §8f)")
-        origin_pml = [dtype(o - s * nbl) for o, s in zip(origin, spacing)]
-        shape_pml = np.array(shape) + 2 * self.nbl
-        subdomains = tuple(subdomains) + (PhysicalDomain(space_order, fs=fs),)
-        if grid is None:
-            extent = tuple(np.array(spacing) * (shape_pml - 1))
-            self.grid = Grid(extent=extent, shape=tuple(int(s) for s in shape_pml), origin=origin_pml,
-                             dtype=dtype, subdomains=subdomains, topology=topology)
-        else:
+        if 'vs' in kwargs:
+            raise NotImplementedError("elastic models are outside this backend's scope (SURVEY §8f)")
+        self.shape = tuple(int(n) for n in shape)
+        self.space_order = int(space_order)
+        self.nbl = int(nbl)
+        self.fs = False
+        self.origin = tuple(dtype(o) for o in origin)
+        ext_shape = tuple(n + 2 * self.nbl for n in self.shape)
+        if grid is not None:
             self.grid = grid
+        else:
+            h = np.asarray(spacing, dtype=np.float64)
+            self.grid = Grid(shape=ext_shape, extent=tuple(h * (np.asarray(ext_shape) - 1)),
+                             origin=tuple(dtype(o - hh * self.nbl) for o, hh in zip(origin, spacing)),
+                             dtype=dtype, topology=topology,
+                             subdomains=tuple(subdomains) + (PhysicalDomain(space_order),))
         self._physical_parameters = set()
-        self.damp = None
-        self._initialize_bcs(bcs=bcs)
-        self._initialize_physics(vp, space_order, **kwargs)
         self._dt = kwargs.get('dt')
         self._dt_scale = 1
+        self.damp = None
+        self._initialize_bcs(bcs=bcs)
+        self.vp = self._gen_phys_param(vp, 'vp', space_order)
+        for name in _PARAMETER_NAMES:
+            value = kwargs.get(name)
+            if value is not None and name not in ('vp', 'damp'):
+                setattr(self, name, self._gen_phys_param(value, name, space_order))
 
-    # -- boundary conditions ----------------------------------------------------------------------
+    # -- absorbing boundary -------------------------------------------------------------------------
     def _initialize_bcs(self, bcs="damp"):
+        """(Re-)build the damping field; wave solvers ask for the `"damp"` profile even when the
+        model was created with the `"mask"` default (examples/seismic/model.py:138-162)."""
         if self.nbl == 0:
             self.damp = 1 if bcs == "mask" else 0
             return
-        init = self.damp is None
-        if init:
+        fresh = self.damp is None
+        if fresh:
             self.damp = Function(name="damp", grid=self.grid, space_order=self.space_order)
         if callable(bcs):
             bcs(self.damp, self.nbl)
         else:
-            re_init = ((bcs == "mask" and mmin(self.damp) == 0) or
-                       (bcs == "damp" and mmax(self.damp) == 1))
-            if init or re_init:
-                if re_init and not init:
-                    other = "damp" if bcs == "mask" else "mask"
-                    warning(f"Re-initializing damp profile from {other} to {bcs}")
+            wrong_kind = (mmin(self.damp) == 0) if bcs == "mask" else (mmax(self.damp) == 1)
+            if fresh or wrong_kind:
+                if not fresh:
+                    warning(f"Re-initializing damp profile from {'damp' if bcs == 'mask' else 'mask'} to {bcs}")
                 self._fill_damp(bcs)
-        self._physical_parameters.update(['damp'])
+        self._physical_parameters.add('damp')
 
     def _fill_damp(self, bcs):
         dist = self.grid.distributor
         if dist.is_parallel:
-            # the profile depends on global indices: evaluate on the global shape, keep our slab
+            # the profile follows GLOBAL indices: evaluate only this rank's x-slab
             self.damp.data[:] = damp_profile(self.grid.shape_global, self.padsizes, self.grid.spacing, bcs,
                                              x_range=dist.x_range)
         else:
-            initialize_damp(self.damp, self.padsizes, self.spacing, abc_type=bcs, fs=self.fs)
+            initialize_damp(self.damp, self.padsizes, self.spacing, abc_type=bcs, fs=False)
 
     @property
     def padsizes(self):
-        return [(self.nbl, self.nbl) for _ in range(self.dim)]
+        return [(self.nbl, self.nbl)] * self.dim
 
-    # -- physics ----------------------------------------------------------------------------------
+    # -- parameters ------------------------------------------------------------------------------------
     def _gen_phys_param(self, field, name, space_order, default_value=0, **kwargs):
         if field is None:
             return default_value
         if isinstance(field, np.ndarray):
-            function = Function(name=name, grid=self.grid, space_order=space_order)
-            initialize_function(function, field, self.padsizes)
+            obj = Function(name=name, grid=self.grid, space_order=space_order)
+            initialize_function(obj, field, self.padsizes)
         else:
-            function = Constant(name=name, value=field, dtype=self.grid.dtype)
-        self._physical_parameters.update([name])
-        return function
-
-    def _initialize_physics(self, vp, space_order, **kwargs):
-        if 'vs' in kwargs:
-            raise NotImplementedError("elastic models are outside this backend's scope (SURVEY §8f)")
-        self.vp = self._gen_phys_param(vp, 'vp', space_order)
-        for name in self._known_parameters:
-            if kwargs.get(name) is not None:
-                setattr(self, name, self._gen_phys_param(kwargs.get(name), name, space_order))
-
-    def physical_params(self, **kwargs):
-        known = [getattr(self, i) for i in self.physical_parameters]
-        return {i.name: kwargs.get(i.name, i) or i for i in known}
+            obj = Constant(name=name, value=field, dtype=self.grid.dtype)
+        self._physical_parameters.add(name)
+        return obj
 
     @property
     def physical_parameters(self):
         return tuple(self._physical_parameters)
 
-    @property
-    def dim(self): return self.grid.dim
-    @property
-    def spacing(self): return self.grid.spacing
-    @property
-    def space_dimensions(self): return self.grid.dimensions
-    @property
-    def spacing_map(self): return self.grid.spacing_map
-    @property
-    def dtype(self): return self.grid.dtype
+    def physical_params(self, **overrides):
+        """{name: object} of all parameters, with user overrides by name."""
+        out = {}
+        for name in self._physical_parameters:
+            obj = getattr(self, name)
+            out[obj.name] = overrides.get(obj.name, obj) or obj
+        return out
+
+    def update(self, name, value):
+        if not hasattr(self, name):
+            setattr(self, name, self._gen_phys_param(value, name, self.space_order))
+            return
+        param = getattr(self, name)
+        if not isinstance(value, np.ndarray):
+            param.data = value
+        elif value.shape == param.shape:
+            param.data[:] = value
+        elif value.shape == self.shape:
+            initialize_function(param, value, self.nbl)
+        else:
+            raise ValueError(f"Incorrect input size {value.shape} for model {self.shape}")
+
+    def smooth(self, physical_parameters, sigma=5.0):
+        objs = self.physical_params()
+        for name in physical_parameters:
+            gaussian_smooth(objs[name], sigma=sigma)
+
+    # -- geometry shortcuts ------------------------------------------------------------------------------
+    dim = property(lambda self: self.grid.dim)
+    spacing = property(lambda self: self.grid.spacing)
+    space_dimensions = property(lambda self: self.grid.dimensions)
+    spacing_map = property(lambda self: self.grid.spacing_map)
+    dtype = property(lambda self: self.grid.dtype)
+
     @property
     def domain_size(self):
-        return tuple((d - 1) * s for d, s in zip(self.shape, self.spacing))
+        return tuple((n - 1) * h for n, h in zip(self.shape, self.spacing))
 
     @property
     def m(self):
-        """Squared slowness 1/vp^2 (model.py:407-411)."""
+        """Squared slowness 1/vp^2 (examples/seismic/model.py:407-411)."""
         return 1 / (self.vp * self.vp)
 
-    # -- time step ----------------------------------------------------------------------------------
-    @property
-    def _max_vp(self):
-        return mmax(self.vp)
-
-    @property
-    def _thomsen_scale(self):
-        if 'epsilon' in self._physical_parameters:
-            return np.sqrt(1 + 2 * mmax(self.epsilon))
-        return 1
-
-    @property
-    def dt_scale(self): return self._dt_scale
-
-    @dt_scale.setter
-    def dt_scale(self, val): self._dt_scale = val
+    # -- time step ------------------------------------------------------------------------------------------
+    dt_scale = property(lambda self: self._dt_scale, lambda self, v: setattr(self, '_dt_scale', v))
 
     @property
     def _cfl_coeff(self):
-        coeffs = finite_diff_weights(2, range(-self.space_order, self.space_order + 1), 0)[-1][-1]
-        return np.sqrt(4.0 / float(self.grid.dim * sum(np.abs(np.array(coeffs, dtype=np.float64)))))
+        """sqrt(4 / (ndim * sum|w|)) with w = second-derivative weights over +-space_order points
+        (examples/seismic/model.py:353-367)."""
+        w = finite_diff_weights(2, range(-self.space_order, self.space_order + 1), 0)[-1][-1]
+        return np.sqrt(4.0 / float(self.grid.dim * np.sum(np.abs(np.array(w, dtype=np.float64)))))
 
     @property
     def critical_dt(self):
-        dt = self._cfl_coeff * np.min(self.spacing) / (self._thomsen_scale * self._max_vp)
-        dt = self.dtype("%.3e" % (self.dt_scale * dt))
-        return self._dt if self._dt else dt
-
-    def update(self, name, value):
-        try:
-            param = getattr(self, name)
-        except AttributeError:
-            setattr(self, name, self._gen_phys_param(value, name, self.space_order))
-            return
-        if isinstance(value, np.ndarray):
-            if value.shape == param.shape:
-                param.data[:] = value[:]
-            elif value.shape == self.shape:
-                initialize_function(param, value, self.nbl)
-            else:
-                raise ValueError(f"Incorrect input size {value.shape}")
-        else:
-            param.data = value
-
-    def smooth(self, physical_parameters, sigma=5.0):
-        params = self.physical_params()
-        for i in physical_parameters:
-            gaussian_smooth(params[i], sigma=sigma)
+        """CFL time step, rounded through "%.3e" to the model dtype (model.py:370-382)."""
+        if self._dt:
+            return self._dt
+        vmax = mmax(self.vp)
+        aniso = np.sqrt(1 + 2 * mmax(self.epsilon)) if 'epsilon' in self._physical_parameters else 1
+        dt = self._cfl_coeff * np.min(self.spacing) / (aniso * vmax)
+        return self.dtype("%.3e" % (self.dt_scale * dt))
 
 
 Model = SeismicModel
