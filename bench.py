@@ -237,7 +237,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dv.configuration['deviceid'] = local
-    dev = torch.device('cuda', local)
+    dev_ = torch.device('cuda', local)
     L = _lib.lib()
 
     so, G, NT, nbl = a.space_order, a.grid, a.nt, 40
@@ -271,6 +271,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # The library enqueues on torch's current stream so that CUDA events recorded on that stream
+    # bracket exactly its work (torch.cuda.Event only sees torch's current stream).
+    bench_stream = torch.cuda.Stream(device=dev_)
+    torch.cuda.set_stream(bench_stream)
+    L.b2_set_stream(ctypes_voidp(bench_stream.cuda_stream))
+
     def timed(fn, reps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -281,13 +287,13 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        dev = e0.elapsed_time(e1) * 1e-3
         barrier()
-        # the library runs on its own stream; its completion is synchronised inside apply(), so
-        # host wall-clock brackets the device work exactly. Report the max over ranks.
-        t = torch.tensor([wall], dtype=torch.float64, device=dev)
+        # device time between the two events (includes host gaps between applies); max over ranks
+        t = torch.tensor([dev, wall], dtype=torch.float64, device=dev_)
         if nranks > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return float(t[0].item())
 
     resident = lambda: solver.forward(src=src, rec=rec, u=u, **fkw)
     for _ in range(a.warmup):
@@ -366,6 +372,11 @@ def main():
 def ctypes_int():
     import ctypes
     return ctypes.c_int(0)
+
+
+def ctypes_voidp(v):
+    import ctypes
+    return ctypes.c_void_p(v)
 
 
 if __name__ == '__main__':
