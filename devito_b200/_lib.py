@@ -75,7 +75,9 @@ SYMBOLS = ['b2_iso_forward', 'b2_tti_forward', 'b2_nccl_unique_id', 'b2_halo_cre
            'b2_halo_destroy', 'b2_halo_update', 'b2_device_count', 'b2_last_error', 'b2_version',
            'b2_launch_count', 'b2_kernel_timing_reset', 'b2_kernel_timing_ms',
            'b2_kernel_timing_enable', 'b2_malloc_device', 'b2_free_device', 'b2_memcpy_h2d',
-           'b2_memcpy_d2h', 'b2_memset_device', 'b2_synchronize', 'b2_set_stream']
+           'b2_memcpy_d2h', 'b2_memset_device', 'b2_synchronize', 'b2_set_stream',
+           'b2_ipc_get_handle', 'b2_ipc_open', 'b2_ipc_close', 'b2_halo_p2p_setup',
+           'b2_halo_p2p_register']
 
 
 def have_lib():
@@ -127,6 +129,16 @@ def load_library():
     L.b2_synchronize.restype = c_int
     L.b2_set_stream.argtypes = [c_void_p]
     L.b2_set_stream.restype = None
+    L.b2_ipc_get_handle.argtypes = [c_void_p, c_char_p]
+    L.b2_ipc_get_handle.restype = c_int
+    L.b2_ipc_open.argtypes = [c_char_p]
+    L.b2_ipc_open.restype = c_void_p
+    L.b2_ipc_close.argtypes = [c_void_p]
+    L.b2_ipc_close.restype = c_int
+    L.b2_halo_p2p_setup.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    L.b2_halo_p2p_setup.restype = c_int
+    L.b2_halo_p2p_register.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int]
+    L.b2_halo_p2p_register.restype = c_int
     _lib = L
     return L
 

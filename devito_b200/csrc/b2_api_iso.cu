@@ -197,6 +197,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     g.so = so;
     g.ndim = nd;
     for (int d = 0; d < nd; ++d) { g.lo[d] = lo_in[d]; g.hi[d] = hi_in[d]; }
+    if (a->halo) { g.nb_lo = a->halo->rank > 0; g.nb_hi = a->halo->rank < a->halo->nranks - 1; }
 
     const float dt2 = a->dt * a->dt;
     const float scalar_scale = dt2 * a->vp * a->vp;
@@ -211,6 +212,8 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     if (timing && !per_step_events) ev_begin = se.next();
 
+    const bool p2p = a->halo && halo_p2p_active(a->halo, p.u);
+    if (a->halo) a->halo->p2p_primed = false;       // first step of a call exchanges through NCCL
     const int dir = a->adjoint ? -1 : 1;
     for (int time = a->adjoint ? a->time_M : a->time_m; a->adjoint ? time >= a->time_m : time <= a->time_M;
          time += dir) {
@@ -227,6 +230,16 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         float *f1 = p.u + (size_t)t1 * p.slot_elems;
         if ((rc = launch_inject(src, g, f1, nullptr, time, p.param_kind, p.param, scalar_scale, dt2)))
             return cleanup(rc);
+        if (p2p) {
+            // boundary planes of u[t1] are final: store them into the neighbours' halos, signal
+            if ((rc = halo_p2p_publish(a->halo, p.u, nullptr, p.slot_elems, t1, (size_t)p.sx, p.o[0], p.n[0],
+                                       p.radius[0])))
+                return cleanup(rc);
+            a->halo->p2p_primed = true;
+            // receivers that sample the just-written time level may touch halo cells: those
+            // arrive with the neighbours' stores of this same step
+            if (a->rec_toff && rec.present && (rc = halo_p2p_wait(a->halo))) return cleanup(rc);
+        }
         if (per_step_events) se.next();
         const float *fr = p.u + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
         if ((rc = launch_interp(rec, g, fr, nullptr, time))) return cleanup(rc);

@@ -104,6 +104,7 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
     g.so = so;
     g.ndim = 3;
     for (int d = 0; d < 3; ++d) { g.lo[d] = lo_in[d]; g.hi[d] = hi_in[d]; }
+    if (a->halo) { g.nb_lo = a->halo->rank > 0; g.nb_hi = a->halo->rank < a->halo->nranks - 1; }
 
     const float dt2 = a->dt * a->dt;
     const float scalar_scale = dt2 * a->vp * a->vp;
@@ -114,6 +115,8 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
         cudaEventCreate(&e1);
         cudaEventRecord(e0, stream());
     }
+    const bool p2p = a->halo && halo_p2p_active(a->halo, p.u) && halo_p2p_active(a->halo, p.v);
+    if (a->halo) a->halo->p2p_primed = false;
     for (int time = a->time_m; time <= a->time_M; ++time) {
         const int t0 = ((time % T) + T) % T;
         const int t1 = (((time + 1) % T) + T) % T;
@@ -128,6 +131,14 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
         if ((rc = launch_inject(src, g, fu, fv, time, p.vp_a ? B2_PARAM_VP : B2_PARAM_SCALAR, p.vp_a,
                                 scalar_scale, dt2)))
             return cleanup(rc);
+        if (p2p) {
+            if ((rc = halo_p2p_publish(a->halo, p.u, p.v, p.slot_elems, t1, (size_t)p.sx, p.o[0], p.n[0], p.R)))
+                return cleanup(rc);
+            a->halo->p2p_primed = true;
+            // receivers that sample the just-written time level may touch halo cells: those
+            // arrive with the neighbours' stores of this same step
+            if (a->rec_toff && rec.present && (rc = halo_p2p_wait(a->halo))) return cleanup(rc);
+        }
         const size_t ro = (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
         if ((rc = launch_interp(rec, g, p.u + ro, p.v + ro, time))) return cleanup(rc);
         if (a->errctl && ((time - a->time_m) % 100 == 99 || time == a->time_M)) {

@@ -90,12 +90,94 @@ int halo_enqueue(b2_halo_ctx *ctx, float *base, size_t plane_elems, int lo, int 
     return B2_OK;
 }
 
+// ---- peer-memory path ----------------------------------------------------------------------------
+__global__ void k_flag_wait(volatile int *flags, int want_left, int want_right) {
+    // one thread; spins until both neighbours have signalled the required step
+    if (want_left >= 0) while (flags[0] < want_left) {}
+    if (want_right >= 0) while (flags[1] < want_right) {}
+    __threadfence_system();
+}
+
+__global__ void k_flag_signal(int *left_remote, int *right_remote, int value) {
+    __threadfence_system();                    // order the preceding peer stores before the flag
+    if (left_remote) *reinterpret_cast<volatile int *>(left_remote) = value;
+    if (right_remote) *reinterpret_cast<volatile int *>(right_remote) = value;
+    __threadfence_system();
+}
+
+// After the boundary planes of time slot `slot1` are final (stencil strips + injection), store them
+// into the neighbours' halos and signal. `base` = local field base (all slots).
+static int p2p_push(b2_halo_ctx *ctx, const b2_halo_ctx::Reg &rg, const float *base, size_t slot_elems,
+                    int slot1, size_t plane, int lo, int n, int width) {
+    cudaStream_t st = stream();
+    const size_t bytes = plane * (size_t)width * sizeof(float);
+    const float *mine = base + (size_t)slot1 * slot_elems;
+    // a neighbour's time slot holds (its owned planes + 2*halo) planes; halo width == lo here
+    const size_t slot_l = (size_t)(rg.n_left + 2 * lo) * plane, slot_r = (size_t)(rg.n_right + 2 * lo) * plane;
+    (void)slot_elems;
+    if (rg.left) {      // my first `width` owned planes -> left neighbour's right halo
+        float *dst = (float *)rg.left + (size_t)slot1 * slot_l + (size_t)(lo + rg.n_left) * plane;
+        B2_CUDA(cudaMemcpyAsync(dst, mine + (size_t)lo * plane, bytes, cudaMemcpyDeviceToDevice, st), B2_ERR_COMM);
+    }
+    if (rg.right) {     // my last `width` owned planes -> right neighbour's left halo
+        float *dst = (float *)rg.right + (size_t)slot1 * slot_r + (size_t)(lo - width) * plane;
+        B2_CUDA(cudaMemcpyAsync(dst, mine + (size_t)(lo + n - width) * plane, bytes, cudaMemcpyDeviceToDevice, st),
+                B2_ERR_COMM);
+    }
+    return B2_OK;
+}
+
+static int p2p_signal(b2_halo_ctx *ctx) {
+    ++ctx->step;
+    k_flag_signal<<<1, 1, 0, stream()>>>(ctx->flag_left_remote, ctx->flag_right_remote, ctx->step);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
+static int p2p_wait(b2_halo_ctx *ctx) {
+    const int want = ctx->step;       // neighbours run the same number of steps
+    k_flag_wait<<<1, 1, 0, stream()>>>(ctx->flags_local, ctx->flag_left_remote ? want : -1,
+                                        ctx->flag_right_remote ? want : -1);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
+int halo_p2p_wait(b2_halo_ctx *ctx) { return p2p_wait(ctx); }
+
+int halo_p2p_active(b2_halo_ctx *ctx, const void *base) { return ctx && ctx->p2p && ctx->find(base) != nullptr; }
+
+// push the just-finished boundary planes of slot `slot1` of one or two fields, then signal once
+int halo_p2p_publish(b2_halo_ctx *ctx, const float *f0, const float *f1, size_t slot_elems, int slot1,
+                     size_t plane, int lo, int n, int width) {
+    int rc;
+    const float *fs[2] = {f0, f1};
+    for (int i = 0; i < 2; ++i) {
+        if (!fs[i]) continue;
+        const b2_halo_ctx::Reg *rg = ctx->find(fs[i]);
+        if (!rg) { set_error("p2p: field not registered"); return B2_ERR_COMM; }
+        if ((rc = p2p_push(ctx, *rg, fs[i], slot_elems, slot1, plane, lo, n, width))) return rc;
+    }
+    return p2p_signal(ctx);
+}
+
 int halo_exchange_and_step_iso(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1) {
     const int R = p.radius[0];
     const int n = p.n[0];
     if (n < 2 * R) {
         set_error("halo: local slab of %d planes is thinner than 2*radius=%d", n, 2 * R);
         return B2_ERR_INVALID;
+    }
+    if (halo_p2p_active(ctx, p.u) && ctx->p2p_primed) {
+        // halos of u[t0] were stored by the neighbours at the end of their previous step: the
+        // interior needs none of them; the boundary strips wait on the flags
+        int rc;
+        if ((rc = iso_step(p, t0, t2, t1, R, n - 2 * R))) return rc;
+        if ((rc = p2p_wait(ctx))) return rc;
+        if ((rc = iso_step(p, t0, t2, t1, 0, R))) return rc;
+        if ((rc = iso_step(p, t0, t2, t1, n - R, R))) return rc;
+        return B2_OK;
     }
     cudaStream_t main = stream();
     B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
@@ -118,6 +200,14 @@ int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t
     if (n < 2 * R) {
         set_error("halo: local slab of %d planes is thinner than 2*radius=%d", n, 2 * R);
         return B2_ERR_INVALID;
+    }
+    if (halo_p2p_active(ctx, p.u) && halo_p2p_active(ctx, p.v) && ctx->p2p_primed) {
+        int rc;
+        if ((rc = tti_step(p, t0, t2, t1, R, n - 2 * R))) return rc;
+        if ((rc = p2p_wait(ctx))) return rc;
+        if ((rc = tti_step(p, t0, t2, t1, 0, R))) return rc;
+        if ((rc = tti_step(p, t0, t2, t1, n - R, R))) return rc;
+        return B2_OK;
     }
     cudaStream_t main = stream();
     B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
@@ -180,6 +270,48 @@ void b2_halo_destroy(b2_halo_ctx *ctx) {
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
+}
+
+int b2_ipc_get_handle(void *devptr, char out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t h;
+    B2_CUDA(cudaIpcGetMemHandle(&h, devptr), B2_ERR_COMM);
+    memcpy(out, &h, 64);
+    return B2_OK;
+}
+
+void *b2_ipc_open(const char handle[64]) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { b2::set_error("cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+int b2_ipc_close(void *mapped) {
+    B2_CUDA(cudaIpcCloseMemHandle(mapped), B2_ERR_COMM);
+    return B2_OK;
+}
+
+int b2_halo_p2p_setup(b2_halo_ctx *ctx, void *flags_local, void *fl, void *fr) {
+    if (!ctx || !flags_local) { b2::set_error("b2_halo_p2p_setup: NULL"); return B2_ERR_INVALID; }
+    ctx->flags_local = (int *)flags_local;
+    ctx->flag_left_remote = (int *)fl;
+    ctx->flag_right_remote = (int *)fr;
+    ctx->p2p = true;
+    ctx->step = 0;
+    ctx->p2p_primed = false;
+    return B2_OK;
+}
+
+int b2_halo_p2p_register(b2_halo_ctx *ctx, void *local_base, void *left_base, void *right_base, int n_left,
+                         int n_right) {
+    if (!ctx || !ctx->p2p) { b2::set_error("b2_halo_p2p_register: p2p not set up"); return B2_ERR_INVALID; }
+    for (auto &r : ctx->regs)
+        if (r.local == local_base) { r = {local_base, left_base, right_base, n_left, n_right}; return B2_OK; }
+    ctx->regs.push_back({local_base, left_base, right_base, n_left, n_right});
+    return B2_OK;
 }
 
 int b2_halo_update(b2_halo_ctx *ctx, struct b2_dataobj *f, int slot, int width) {

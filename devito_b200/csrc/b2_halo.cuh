@@ -3,6 +3,7 @@
 #include "b2_common.cuh"
 #include "b2_iso.cuh"
 #include "b2_tti.cuh"
+#include <vector>
 
 struct b2_halo_ctx {
     int rank = 0, nranks = 1, deviceid = 0;
@@ -11,6 +12,19 @@ struct b2_halo_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_comm = nullptr;
     double seconds = 0.0;                 // accumulated exchange time (when timed)
+    // peer-memory path
+    bool p2p = false;
+    int *flags_local = nullptr;           // [0] written by the left neighbour, [1] by the right one
+    int *flag_left_remote = nullptr;      // slot in the LEFT neighbour's buffer that we signal
+    int *flag_right_remote = nullptr;
+    int step = 0;                         // monotonic count of completed p2p steps
+    bool p2p_primed = false;              // halos of the current u[t0] were stored by the peers
+    struct Reg { void *local, *left, *right; int n_left, n_right; };
+    std::vector<Reg> regs;
+    const Reg *find(const void *local) const {
+        for (const Reg &r : regs) if (r.local == local) return &r;
+        return nullptr;
+    }
 };
 
 namespace b2 {
@@ -24,6 +38,12 @@ int halo_enqueue(b2_halo_ctx *ctx, float *slot_base, size_t plane_elems, int lo,
 //   comm stream : send/recv boundary planes of u[t0]
 //   main stream : interior x in [R, n-R)  ->  wait comm  ->  strips [0,R) and [n-R,n)
 int halo_exchange_and_step_iso(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1);
+
+// peer-memory path helpers (see b2_halo.cu)
+int halo_p2p_active(b2_halo_ctx *ctx, const void *base);
+int halo_p2p_wait(b2_halo_ctx *ctx);     // block the stream until both neighbours signalled the current step
+int halo_p2p_publish(b2_halo_ctx *ctx, const float *f0, const float *f1, size_t slot_elems, int slot1,
+                     size_t plane, int lo, int n, int width);
 
 // Same for the coupled TTI fields: u and v boundary planes travel in one NCCL group.
 int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t2, int t1);

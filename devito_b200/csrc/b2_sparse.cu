@@ -25,6 +25,7 @@ struct SparseK {
     long long sx, sy;
     int so;
     int lo0, lo1, lo2, hi0, hi1, hi2;
+    int ext_lo0, ext_hi0;     // how far beyond [lo0, hi0] the support may reach (r, or 0 next to a neighbour)
 };
 
 __device__ __forceinline__ bool sparse_cell(const SparseK &k, int p, int c, long long &idx, float &wgt,
@@ -41,7 +42,7 @@ __device__ __forceinline__ bool sparse_cell(const SparseK &k, int p, int c, long
         c0 = g[0] + r0 - k.r + 1;
         c1 = g[1] + r1 - k.r + 1;
         c2 = g[2] + r2 - k.r + 1;
-        if (c0 < k.lo0 - k.r || c0 > k.hi0 + k.r) return false;
+        if (c0 < k.lo0 - k.ext_lo0 || c0 > k.hi0 + k.ext_hi0) return false;
         w = k.w0[(long long)p * n + r0] * k.w1[(long long)p * n + r1] * k.w2[(long long)p * n + r2];
     } else {
         c0 = 0;
@@ -110,8 +111,10 @@ k_interp(SparseK k, const float *__restrict__ f0, const float *__restrict__ f1,
     if (lane == 0) out[(long long)time * k.npoint_total + p] = sum;
 }
 
-static SparseK make_k(const SparseDev &s, const FieldGeom &g) {
+static SparseK make_k(const SparseDev &s, const FieldGeom &g, bool injecting) {
     SparseK k;
+    k.ext_lo0 = (injecting && g.nb_lo) ? 0 : s.r;
+    k.ext_hi0 = (injecting && g.nb_hi) ? 0 : s.r;
     k.data = (const float *)s.data.d;
     k.gp = (const int *)s.gp.d;
     if (s.ndim == 3) {
@@ -180,7 +183,7 @@ int launch_inject(const SparseDev &s, const FieldGeom &g, float *f0, float *f1, 
                   int param_kind, const float *param, float scalar_scale, float dt2) {
     if (!s.present) return B2_OK;
     if (time < 0 || time >= s.nt) return B2_OK;
-    SparseK k = make_k(s, g);
+    SparseK k = make_k(s, g, true);
     const int warps = k.p_cnt;
     const int blocks = (warps * 32 + 127) / 128;
     k_inject<<<blocks, 128, 0, stream()>>>(k, f0, f1, time, param_kind, param, scalar_scale, dt2);
@@ -192,7 +195,7 @@ int launch_inject(const SparseDev &s, const FieldGeom &g, float *f0, float *f1, 
 int launch_interp(const SparseDev &s, const FieldGeom &g, const float *f0, const float *f1, int time) {
     if (!s.present) return B2_OK;
     if (time < 0 || time >= s.nt) return B2_OK;
-    SparseK k = make_k(s, g);
+    SparseK k = make_k(s, g, false);
     const int warps = k.p_cnt;
     const int blocks = (warps * 32 + 127) / 128;
     k_interp<<<blocks, 128, 0, stream()>>>(k, f0, f1, (float *)s.data.d, time);

@@ -22,6 +22,9 @@ struct FieldGeom {
     int ndim = 3;
     int lo[3] = {0, 0, 0};      // x_m, y_m, z_m
     int hi[3] = {0, 0, 0};      // x_M, y_M, z_M
+    // x-slab decomposition: a neighbour owns the cells beyond x_m / x_M, so injection must not
+    // touch them (the owner injects and its boundary planes are then exchanged)
+    bool nb_lo = false, nb_hi = false;
 };
 
 int sparse_stage_in(const b2_sparse *s, int ndim, SparseDev &out, bool copy_data_in);

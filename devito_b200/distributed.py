@@ -57,6 +57,9 @@ def finalize_distributed():
     import torch.distributed as dist
     if world.halo_ctx is not None:
         from ._lib import lib
+        for m in _p2p['mapped']:
+            lib().b2_ipc_close(m)
+        _p2p.update(ready=False, disabled=False, flags=None, mapped=[])
         lib().b2_halo_destroy(world.halo_ctx)
         world.halo_ctx = None
     if dist.is_initialized():
@@ -89,6 +92,89 @@ def halo_context(deviceid):
         raise RuntimeError(f"b2_halo_create failed: {L.b2_last_error().decode()}")
     world.halo_ctx = ctx
     return ctx
+
+
+# ---------------------------------------------------------------------------------------------
+# peer-memory halo path: CUDA IPC handle exchange (host plumbing only; the data path is in
+# csrc/b2_halo.cu)
+# ---------------------------------------------------------------------------------------------
+_p2p = {'ready': False, 'disabled': False, 'flags': None, 'mapped': []}
+
+
+def p2p_enabled():
+    return os.environ.get('B2_HALO', 'p2p').lower() != 'nccl' and not _p2p['disabled']
+
+
+def _gather(obj):
+    import torch.distributed as dist
+    out = [None] * world.size
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def _p2p_setup(deviceid):
+    """Collective: every rank allocates its flag buffer and maps its neighbours'."""
+    import ctypes
+    from ._lib import lib
+    if _p2p['ready'] or not p2p_enabled():
+        return _p2p['ready']
+    L = lib()
+    ctx = halo_context(deviceid)
+    flags = L.b2_malloc_device(64, deviceid)
+    L.b2_memset_device(flags, 0, 64, deviceid)
+    L.b2_synchronize(deviceid)
+    buf = ctypes.create_string_buffer(64)
+    ok = L.b2_ipc_get_handle(flags, buf) == 0
+    handles = _gather(bytes(buf.raw) if ok else None)
+    if any(h is None for h in handles):
+        _p2p['disabled'] = True
+        return False
+    left = world.rank - 1 if world.rank > 0 else None
+    right = world.rank + 1 if world.rank < world.size - 1 else None
+    lp = L.b2_ipc_open(handles[left]) if left is not None else None
+    rp = L.b2_ipc_open(handles[right]) if right is not None else None
+    good = (left is None or lp) and (right is None or rp)
+    if not all(_gather(bool(good))):
+        _p2p['disabled'] = True
+        return False
+    # we signal slot [1] ("from right") of the left neighbour and slot [0] of the right neighbour
+    fl = ctypes.c_void_p(lp + 4) if lp else None
+    fr = ctypes.c_void_p(rp) if rp else None
+    if L.b2_halo_p2p_setup(ctx, flags, fl, fr):
+        raise RuntimeError(L.b2_last_error().decode())
+    _p2p.update(ready=True, flags=flags)
+    _p2p['mapped'] += [m for m in (lp, rp) if m]
+    return True
+
+
+def register_field(storage, grid, deviceid):
+    """Collective: export this rank's device allocation of a wavefield to its x-neighbours and map
+    theirs, so that boundary planes can be stored straight into the neighbour's halo."""
+    import ctypes
+    from ._lib import lib
+    if storage.p2p_registered or not _p2p_setup(deviceid):
+        return storage.p2p_registered
+    L = lib()
+    ctx = halo_context(deviceid)
+    buf = ctypes.create_string_buffer(64)
+    ok = L.b2_ipc_get_handle(storage.dev.data_ptr(), buf) == 0
+    info = _gather((bytes(buf.raw) if ok else None, int(grid.shape[0])))
+    if any(h is None for h, _ in info):
+        return False
+    left = world.rank - 1 if world.rank > 0 else None
+    right = world.rank + 1 if world.rank < world.size - 1 else None
+    lp = L.b2_ipc_open(info[left][0]) if left is not None else None
+    rp = L.b2_ipc_open(info[right][0]) if right is not None else None
+    good = (left is None or lp) and (right is None or rp)
+    if not all(_gather(bool(good))):
+        return False
+    nl = info[left][1] if left is not None else 0
+    nr = info[right][1] if right is not None else 0
+    if L.b2_halo_p2p_register(ctx, storage.dev.data_ptr(), lp, rp, nl, nr):
+        raise RuntimeError(L.b2_last_error().decode())
+    _p2p['mapped'] += [m for m in (lp, rp) if m]
+    storage.p2p_registered = True
+    return True
 
 
 class Distributor:

@@ -914,7 +914,14 @@ class Operator:
             return ob
         st = fn.storage
         if resident:
+            dist_ = fn.grid.distributor if fn.grid is not None else None
+            p2p_field = (written and dist_ is not None and dist_.is_parallel and distributed.p2p_enabled()
+                         and getattr(fn, 'is_TimeFunction', False))
+            if p2p_field:
+                st.raw = True        # plain cudaMalloc: exportable through CUDA IPC
             t = st.to_device(torch.device('cuda', dev))
+            if p2p_field and not st.p2p_registered:
+                distributed.register_field(st, fn.grid, dev)
             ob = L_.make_dataobj(dev_ptr=t.data_ptr(), shape=st.shape, halo=fn.halo)
             if written:
                 st.mark_device_written()

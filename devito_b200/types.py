@@ -330,7 +330,39 @@ class Data(np.ndarray):
         return np.asarray(array).view(cls)
 
 
+class RawDeviceBuffer:
+    """Plain cudaMalloc allocation made through the C library (not torch's caching allocator), so
+    that its CUDA IPC handle can be exported to the neighbour ranks (peer-memory halo path)."""
+
+    def __init__(self, nbytes, deviceid):
+        from ._lib import lib
+        self.nbytes, self.deviceid = int(nbytes), int(deviceid)
+        self.ptr = lib().b2_malloc_device(self.nbytes, self.deviceid)
+        if not self.ptr:
+            raise MemoryError(f"b2_malloc_device({self.nbytes}) failed")
+
+    def data_ptr(self):
+        return self.ptr
+
+    @property
+    def device(self):
+        import torch
+        return torch.device('cuda', self.deviceid)
+
+    def __del__(self):
+        try:
+            from ._lib import lib
+            if self.ptr:
+                lib().b2_free_device(self.ptr, self.deviceid)
+                self.ptr = None
+        except Exception:
+            pass
+
+
 class FieldStorage:
+    raw = False          # True: device copy is a RawDeviceBuffer (IPC-exportable)
+    p2p_registered = False
+
     def __init__(self, shape, dtype):
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
@@ -376,6 +408,13 @@ class FieldStorage:
     def sync_to_host(self):
         import torch
         self._alloc_host()
+        if isinstance(self.dev, RawDeviceBuffer):
+            from ._lib import lib
+            rc = lib().b2_memcpy_d2h(self._host.ctypes.data, self.dev.ptr, self._host.nbytes, self.dev.deviceid)
+            if rc:
+                raise RuntimeError("device -> host copy failed")
+            self.host_valid = True
+            return
         src = self.dev
         if self._pinned is not None:
             self._pinned.copy_(src, non_blocking=False)
@@ -387,6 +426,27 @@ class FieldStorage:
         """Device tensor holding current data (upload if the host copy is newer). A function
         whose host array was never touched is all zeros: it is created directly on the device."""
         import torch
+        if self.raw:
+            from ._lib import lib
+            L = lib()
+            nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+            if not isinstance(self.dev, RawDeviceBuffer):
+                if self.dev is not None and not self.host_valid:
+                    self.sync_to_host()
+                self.dev = RawDeviceBuffer(nbytes, device.index)
+                self.p2p_registered = False
+                if self._host is None:
+                    L.b2_memset_device(self.dev.ptr, 0, nbytes, device.index)
+                    L.b2_synchronize(device.index)
+                    self.dev_valid, self.host_valid = True, False
+                    return self.dev
+                self.dev_valid = False
+            if not self.dev_valid:
+                self._alloc_host()
+                if L.b2_memcpy_h2d(self.dev.ptr, self._host.ctypes.data, nbytes, device.index):
+                    raise RuntimeError("host -> device copy failed")
+                self.dev_valid = True
+            return self.dev
         tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
                np.dtype(np.float64): torch.float64}[self.dtype]
         if self.dev is None or self.dev.device != device:

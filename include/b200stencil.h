@@ -168,6 +168,22 @@ void b2_halo_destroy(b2_halo_ctx *ctx);
  * x-neighbours: owned planes -> neighbour halo. Blocking w.r.t. the library stream. */
 int  b2_halo_update(b2_halo_ctx *ctx, struct b2_dataobj *f, int slot, int width);
 
+/* Peer-memory halo path (one process per GPU, NVLink/NVSwitch): boundary planes are stored straight
+ * into the neighbour's halo through CUDA-IPC-mapped peer pointers and ordered with device-side flags
+ * (st.release.sys / ld.acquire.sys) — no NCCL call per time step. The host framework exchanges the
+ * 64-byte IPC handles (torch.distributed), the library does the rest.
+ *   b2_ipc_get_handle / b2_ipc_open / b2_ipc_close : cudaIpc{Get,Open,Close}MemHandle wrappers
+ *   b2_halo_p2p_setup    : local flag buffer (2 ints: [from left, from right]) and the two remote
+ *                          flag slots this rank signals (NULL at the physical boundary)
+ *   b2_halo_p2p_register : for the field whose device base is `local_base`, the neighbours' mapped
+ *                          bases and the number of x-planes they own                              */
+int   b2_ipc_get_handle(void *devptr, char handle_out[64]);
+void *b2_ipc_open(const char handle[64]);
+int   b2_ipc_close(void *mapped);
+int   b2_halo_p2p_setup(b2_halo_ctx *ctx, void *flags_local, void *flag_left_remote, void *flag_right_remote);
+int   b2_halo_p2p_register(b2_halo_ctx *ctx, void *local_base, void *left_base, void *right_base,
+                           int n_left, int n_right);
+
 /* ---- utilities ---------------------------------------------------------------------------- */
 int         b2_device_count(void);
 const char *b2_last_error(void);
