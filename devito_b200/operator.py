@@ -19,6 +19,7 @@ interpreter.  The recognised path NEVER falls back to the CPU.
 """
 import ctypes
 import itertools
+import os
 import time as _time
 from collections import OrderedDict
 
@@ -653,6 +654,24 @@ class Operator:
             raise InvalidOperator("interpreted operators have no C entry point")
         L = L_.load_library()
         return L.b2_iso_forward if self._plan['kind'] == 'iso' else L.b2_tti_forward
+
+    def cinterface(self, force=False):
+        """Write `<name>.c` / `<name>.h` under the JIT directory and return `(ccode, hcode)`
+        (devito/operator/operator.py:871-902). For an operator on the CUDA path the C file is the
+        adapter exporting the reference-style symbol `int <name>(struct dataobj *..., ...)` on top of
+        libb200stencil.so — see devito_b200/cinterface.py."""
+        from . import cinterface as ci
+        if self._plan is None:
+            raise InvalidOperator("interpreted operators have no C interface")
+        dist = self._plan['grid'].distributor.is_parallel
+        ccode, hcode = ci.generate(self._plan, self.name, distributed=dist)
+        dest = ci.jit_dir()
+        for ext, code in (('.c', ccode), ('.h', hcode)):
+            path = os.path.join(dest, self.name + ext)
+            if force or not os.path.isfile(path):
+                with open(path, 'w') as f:
+                    f.write(code)
+        return ccode, hcode
 
     @property
     def parameters(self):
