@@ -771,12 +771,42 @@ class Operator:
         return summary
 
     # -- CUDA path ---------------------------------------------------------------------------------
-    def _resolve(self, kwargs, obj):
-        """User override by name (object of the same kind), else the default object."""
+    def _resolve(self, kwargs, obj, post=None):
+        """User override by name, else the default object. Like the reference
+        (devito/types/dense.py:913-926) an override is either an object of the same kind or a bare
+        ndarray standing in for the function's allocated data (halo included): the array is then
+        used in place — uploaded before the time loop, written back when the call returns."""
         if obj is None:
             return None
         v = kwargs.pop(obj.name, None)
-        return obj if v is None else v
+        if v is None:
+            return obj
+        if isinstance(v, np.ndarray):
+            return self._shadow(obj, v, post)
+        return v
+
+    @staticmethod
+    def _shadow(obj, arr, post):
+        from .types import FieldStorage
+        want = tuple(obj.storage.shape)
+        if tuple(arr.shape) != want:
+            raise InvalidArgument(f"Shape {arr.shape} of runtime value `{obj.name}` does not match "
+                                  f"the allocated shape {want}")
+        if arr.dtype != np.float32 or not arr.flags['C_CONTIGUOUS'] or not arr.flags['WRITEABLE']:
+            raise InvalidArgument(f"runtime value `{obj.name}` must be a writeable C-contiguous float32 array")
+        sh = object.__new__(type(obj))
+        sh.__dict__.update(obj.__dict__)
+        st = FieldStorage(want, np.float32)
+        st._host = arr
+        sh._storage = st
+        if post is not None:
+            def writeback():
+                if not st.host_valid:
+                    st.sync_to_host()
+                st.dev = None
+                st.dev_valid = False
+            post.append(writeback)
+        return sh
 
     def _prepare(self, kwargs):
         p = self._plan
@@ -784,21 +814,22 @@ class Operator:
         nd = grid.dim
         args = OrderedDict()
         hold = []          # keep ctypes/ndarray objects alive during the call
-        u = self._resolve(kwargs, p['u'])
+        post = args['post'] = []     # run after the C call (write-back of ndarray overrides)
+        u = self._resolve(kwargs, p['u'], post)
         fields = [u]
         if p['kind'] == 'tti':
-            v = self._resolve(kwargs, p['v'])
+            v = self._resolve(kwargs, p['v'], post)
             fields.append(v)
         for f in fields:
             if not isinstance(f, TimeFunction) or f.space_order != p['so'] or f.grid.shape != grid.shape:
                 raise InvalidArgument(f"incompatible override for a wavefield")
         args['fields'] = fields
-        damp = self._resolve(kwargs, p['damp']) if p.get('damp') is not None else None
+        damp = self._resolve(kwargs, p['damp'], post) if p.get('damp') is not None else None
         if damp is not None and not isinstance(damp, Function):
             raise InvalidArgument("`damp` override must be a Function")
         args['damp'] = damp
-        args['grad'] = self._resolve(kwargs, p.get('grad'))
-        args['usave'] = self._resolve(kwargs, p.get('usave'))
+        args['grad'] = self._resolve(kwargs, p.get('grad'), post)
+        args['usave'] = self._resolve(kwargs, p.get('usave'), post)
         if args['usave'] is not None:
             us = args['usave']
             if not isinstance(us, TimeFunction) or us.is_buffered or us.space_order != p['so']:
@@ -858,8 +889,8 @@ class Operator:
             hi.append(int(b))
         args['lo'], args['hi'] = lo, hi
         # sparse
-        src = self._resolve(kwargs, p['src'])
-        rec = self._resolve(kwargs, p['rec'])
+        src = self._resolve(kwargs, p['src'], post)
+        rec = self._resolve(kwargs, p['rec'], post)
         args['src'], args['rec'] = src, rec
         # time range (devito/types/dimension.py:279-331)
         sized = [s for s in (src, rec) if s is not None]
@@ -1078,7 +1109,7 @@ class Operator:
         t0 = _time.perf_counter()
         rc = L.b2_iso_forward(ctypes.byref(a))
         t_wall = _time.perf_counter() - t0
-        for fn in post:
+        for fn in post + args['post']:
             fn()
         return self._finish(rc, L, timers, args, 1, t_wall)
 
@@ -1121,7 +1152,7 @@ class Operator:
         t0 = _time.perf_counter()
         rc = L.b2_tti_forward(ctypes.byref(a))
         t_wall = _time.perf_counter() - t0
-        for fn in post:
+        for fn in post + args['post']:
             fn()
         return self._finish(rc, L, timers, args, 2, t_wall)
 

@@ -76,8 +76,12 @@ def _cc(args, cwd):
 def _build_against_stub(jitdir, name):
     # one uniquely named double per test: the dynamic loader shares libraries by soname
     tag = f'stub_{name}_{os.path.basename(jitdir)}'.replace('-', '_')
-    _cc(['-O1', '-shared', '-fPIC', '-Wall', '-Werror', '-I', INCLUDE, STUB_SRC, '-o', f'lib{tag}.so'], jitdir)
-    _cc(['-O1', '-shared', '-fPIC', '-Wall', '-Werror', '-I', INCLUDE, '-I', jitdir, f'{name}.c',
+    # the entry points are renamed on both sides so that the real library, when another test has
+    # already loaded it with RTLD_GLOBAL, cannot interpose them
+    ren = ['-Db2_iso_forward=double_b2_iso_forward', '-Db2_tti_forward=double_b2_tti_forward']
+    _cc(['-O1', '-shared', '-fPIC', '-Wall', '-Werror', '-I', INCLUDE] + ren + [STUB_SRC, '-o', f'lib{tag}.so'],
+        jitdir)
+    _cc(['-O1', '-shared', '-fPIC', '-Wall', '-Werror', '-I', INCLUDE, '-I', jitdir] + ren + [f'{name}.c',
          '-L', jitdir, f'-l{tag}', f'-Wl,-rpath,{jitdir}', '-lm', '-o', f'lib{name}_{tag}.so'], jitdir)
     stub = ctypes.CDLL(os.path.join(jitdir, f'lib{tag}.so'))
     lib = ctypes.CDLL(os.path.join(jitdir, f'lib{name}_{tag}.so'))
@@ -272,3 +276,35 @@ def test_adapter_runs_on_the_gpu(jitdir):
     np.testing.assert_array_equal(vals['u'].host, u_ref)
     np.testing.assert_array_equal(vals['rec'].host, rec_ref)
     assert timers.section0 > 0
+
+
+def test_ndarray_override_is_checked():
+    """`op.apply(u=<ndarray>)`: a bare array stands in for the allocated data (reference
+    devito/types/dense.py:913-926); shape/dtype are validated before anything runs."""
+    from devito_b200.exceptions import InvalidArgument
+    solver = _iso_solver(so=4)
+    op = solver.op_fwd()
+    u = op._plan['u']
+    good = np.zeros(u.shape_allocated, dtype=np.float32)
+    args = op.arguments(u=good, dt=1.0)
+    assert args['fields'][0].storage.host is good and args['fields'][0] is not u
+    with pytest.raises(InvalidArgument):
+        op.arguments(u=np.zeros(u.shape, dtype=np.float32), dt=1.0)          # domain-only shape
+    with pytest.raises(InvalidArgument):
+        op.arguments(u=good.astype(np.float64), dt=1.0)
+
+
+@pytest.mark.gpu
+def test_ndarray_override_runs_in_place():
+    solver = _iso_solver(so=8, n=32, nbl=8)
+    op = solver.op_fwd()
+    p = op._plan
+    u, rec = p['u'], p['rec']
+    dt = solver.model.critical_dt
+    op.apply(dt=dt)
+    u_ref, rec_ref = np.array(u.data_with_halo), np.array(rec.data)
+    ua = np.zeros(u.shape_allocated, dtype=np.float32)
+    ra = np.zeros(rec.data.shape, dtype=np.float32)
+    op.apply(dt=dt, u=ua, rec=ra)
+    np.testing.assert_array_equal(ua, u_ref)
+    np.testing.assert_array_equal(ra, rec_ref)
