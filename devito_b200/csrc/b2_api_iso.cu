@@ -274,6 +274,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
             if (bad) { set_error("NaN/Inf detected in u at time=%d", time); return cleanup(B2_ERR_NAN); }
         }
     }
+    if (a->halo && (rc = halo_p2p_drain(a->halo))) return cleanup(rc);
     if (timing && !per_step_events) ev_end = se.next();
 
     cudaError_t e = cudaStreamSynchronize(stream());

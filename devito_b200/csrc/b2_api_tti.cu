@@ -147,6 +147,7 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
             if (bad) { set_error("NaN/Inf detected in u at time=%d", time); return cleanup(B2_ERR_NAN); }
         }
     }
+    if (a->halo && (rc = halo_p2p_drain(a->halo))) return cleanup(rc);
     if (a->timers) cudaEventRecord(e1, stream());
     cudaError_t e = cudaStreamSynchronize(stream());
     if (e != cudaSuccess) {

@@ -109,7 +109,7 @@ __global__ void k_flag_signal(int *left_remote, int *right_remote, int value) {
 // into the neighbours' halos and signal. `base` = local field base (all slots).
 static int p2p_push(b2_halo_ctx *ctx, const b2_halo_ctx::Reg &rg, const float *base, size_t slot_elems,
                     int slot1, size_t plane, int lo, int n, int width) {
-    cudaStream_t st = stream();
+    cudaStream_t st = ctx->p2p_async ? ctx->push_stream : stream();
     const size_t bytes = plane * (size_t)width * sizeof(float);
     const float *mine = base + (size_t)slot1 * slot_elems;
     // a neighbour's time slot holds (its owned planes + 2*halo) planes; halo width == lo here
@@ -129,7 +129,8 @@ static int p2p_push(b2_halo_ctx *ctx, const b2_halo_ctx::Reg &rg, const float *b
 
 static int p2p_signal(b2_halo_ctx *ctx) {
     ++ctx->step;
-    k_flag_signal<<<1, 1, 0, stream()>>>(ctx->flag_left_remote, ctx->flag_right_remote, ctx->step);
+    cudaStream_t st = ctx->p2p_async ? ctx->push_stream : stream();
+    k_flag_signal<<<1, 1, 0, st>>>(ctx->flag_left_remote, ctx->flag_right_remote, ctx->step);
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
     return B2_OK;
@@ -153,13 +154,32 @@ int halo_p2p_publish(b2_halo_ctx *ctx, const float *f0, const float *f1, size_t 
                      size_t plane, int lo, int n, int width) {
     int rc;
     const float *fs[2] = {f0, f1};
+    if (ctx->p2p_async) {
+        // the planes are final on the main stream: hand them to the side stream
+        B2_CUDA(cudaEventRecord(ctx->ev_final, stream()), B2_ERR_COMM);
+        B2_CUDA(cudaStreamWaitEvent(ctx->push_stream, ctx->ev_final, 0), B2_ERR_COMM);
+    }
     for (int i = 0; i < 2; ++i) {
         if (!fs[i]) continue;
         const b2_halo_ctx::Reg *rg = ctx->find(fs[i]);
         if (!rg) { set_error("p2p: field not registered"); return B2_ERR_COMM; }
         if ((rc = p2p_push(ctx, *rg, fs[i], slot_elems, slot1, plane, lo, n, width))) return rc;
     }
-    return p2p_signal(ctx);
+    if ((rc = p2p_signal(ctx))) return rc;
+    if (ctx->p2p_async) {
+        B2_CUDA(cudaEventRecord(ctx->ev_push, ctx->push_stream), B2_ERR_COMM);
+        ctx->push_pending = true;
+    }
+    return B2_OK;
+}
+
+int halo_p2p_drain(b2_halo_ctx *ctx) {
+    if (!ctx || !ctx->push_pending) return B2_OK;
+    // the pushed planes (time slot t1 of the previous step) are written again three steps later and
+    // the library call must not return before its stores left: order the main stream after them
+    B2_CUDA(cudaStreamWaitEvent(stream(), ctx->ev_push, 0), B2_ERR_COMM);
+    ctx->push_pending = false;
+    return B2_OK;
 }
 
 int halo_exchange_and_step_iso(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1) {
@@ -174,6 +194,7 @@ int halo_exchange_and_step_iso(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t
         // interior needs none of them; the boundary strips wait on the flags
         int rc;
         if ((rc = iso_step(p, t0, t2, t1, R, n - 2 * R))) return rc;
+        if ((rc = halo_p2p_drain(ctx))) return rc;
         if ((rc = p2p_wait(ctx))) return rc;
         if ((rc = iso_step(p, t0, t2, t1, 0, R))) return rc;
         if ((rc = iso_step(p, t0, t2, t1, n - R, R))) return rc;
@@ -204,6 +225,7 @@ int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t
     if (halo_p2p_active(ctx, p.u) && halo_p2p_active(ctx, p.v) && ctx->p2p_primed) {
         int rc;
         if ((rc = tti_step(p, t0, t2, t1, R, n - 2 * R))) return rc;
+        if ((rc = halo_p2p_drain(ctx))) return rc;
         if ((rc = p2p_wait(ctx))) return rc;
         if ((rc = tti_step(p, t0, t2, t1, 0, R))) return rc;
         if ((rc = tti_step(p, t0, t2, t1, n - R, R))) return rc;
@@ -269,6 +291,12 @@ void b2_halo_destroy(b2_halo_ctx *ctx) {
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     if (ctx->ev_comm) cudaEventDestroy(ctx->ev_comm);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->push_stream) {
+        cudaStreamSynchronize(ctx->push_stream);
+        cudaEventDestroy(ctx->ev_final);
+        cudaEventDestroy(ctx->ev_push);
+        cudaStreamDestroy(ctx->push_stream);
+    }
     delete ctx;
 }
 
@@ -302,6 +330,16 @@ int b2_halo_p2p_setup(b2_halo_ctx *ctx, void *flags_local, void *fl, void *fr) {
     ctx->p2p = true;
     ctx->step = 0;
     ctx->p2p_primed = false;
+    const char *as = getenv("B2_P2P_ASYNC");
+    if (as && atoi(as) != 0 && !ctx->push_stream) {
+        B2_CUDA(cudaSetDevice(ctx->deviceid), B2_ERR_DEVICE);
+        int lo_prio = 0, hi_prio = 0;
+        B2_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio), B2_ERR_COMM);
+        B2_CUDA(cudaStreamCreateWithPriority(&ctx->push_stream, cudaStreamNonBlocking, hi_prio), B2_ERR_COMM);
+        B2_CUDA(cudaEventCreateWithFlags(&ctx->ev_final, cudaEventDisableTiming), B2_ERR_COMM);
+        B2_CUDA(cudaEventCreateWithFlags(&ctx->ev_push, cudaEventDisableTiming), B2_ERR_COMM);
+        ctx->p2p_async = true;
+    }
     return B2_OK;
 }
 

@@ -19,6 +19,12 @@ struct b2_halo_ctx {
     int *flag_right_remote = nullptr;
     int step = 0;                         // monotonic count of completed p2p steps
     bool p2p_primed = false;              // halos of the current u[t0] were stored by the peers
+    // opt-in (B2_P2P_ASYNC=1, not yet validated on hardware): peer stores + signal go to a
+    // high-priority side stream so that they overlap the next step's interior update
+    bool p2p_async = false;
+    cudaStream_t push_stream = nullptr;
+    cudaEvent_t ev_final = nullptr, ev_push = nullptr;
+    bool push_pending = false;
     struct Reg { void *local, *left, *right; int n_left, n_right; };
     std::vector<Reg> regs;
     const Reg *find(const void *local) const {
@@ -44,6 +50,9 @@ int halo_p2p_active(b2_halo_ctx *ctx, const void *base);
 int halo_p2p_wait(b2_halo_ctx *ctx);     // block the stream until both neighbours signalled the current step
 int halo_p2p_publish(b2_halo_ctx *ctx, const float *f0, const float *f1, size_t slot_elems, int slot1,
                      size_t plane, int lo, int n, int width);
+// make the main stream wait for an outstanding asynchronous push (no-op otherwise); called before the
+// boundary strips of the next step and once after the time loop
+int halo_p2p_drain(b2_halo_ctx *ctx);
 
 // Same for the coupled TTI fields: u and v boundary planes travel in one NCCL group.
 int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t2, int t1);
