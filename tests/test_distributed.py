@@ -19,12 +19,13 @@ def _free_port():
     return p
 
 
-def _launch(args, timeout=600):
+def _launch(args, timeout=600, extra_env=None):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()),
            os.path.join(HERE, 'dist_worker.py')] + args
     env = dict(os.environ)
     env['OMP_NUM_THREADS'] = '1'
+    env.update(extra_env or {})
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
 
 
@@ -33,13 +34,21 @@ def test_decomposition_host_side():
     assert 'DIST-HOST-OK' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+# halo data paths: default peer-memory stores; complete NCCL path; the asynchronous peer-memory
+# variant is opt-in and only exercised when B2_TEST_EXPERIMENTAL=1 (not yet validated on hardware)
+_PATHS = [('p2p', {}), ('nccl', {'B2_HALO': 'nccl'})]
+if os.environ.get('B2_TEST_EXPERIMENTAL') == '1':
+    _PATHS.append(('p2p-async', {'B2_P2P_ASYNC': '1'}))
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize('path,env', _PATHS, ids=[p for p, _ in _PATHS])
 @pytest.mark.parametrize('kind,tol', [('iso', 1e-5), ('tti', 1e-4)])
-def test_two_gpu_halo_exchange_matches_single_gpu(kind, tol):
+def test_two_gpu_halo_exchange_matches_single_gpu(kind, tol, path, env):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _launch(['gpu', kind])
+    r = _launch(['gpu', kind], extra_env=env)
     assert 'DIST-GPU-DONE' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     sys.path.insert(0, HERE)
     from helpers import rel_linf
