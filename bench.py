@@ -19,8 +19,9 @@ reference's code generator for this operator, compiled here with its flags; else
 port) on a bounded sample of the same workload.
 
 Multi-GPU (torchrun, one rank per GPU): x-slab decomposition, weak scaling — every rank owns a
-1024-plane slab of a (N*1024) x 1024 x 1024 grid; halo exchange by NCCL send/recv overlapped
-with the interior update.
+1024-plane slab of a (N*1024) x 1024 x 1024 grid; boundary planes are stored into the neighbour
+GPU's halo over NVLink (CUDA-IPC peer memory + device flags), or exchanged by NCCL send/recv
+overlapped with the interior update (B2_HALO=nccl, and the first step of every apply).
 """
 import argparse
 import json
@@ -359,6 +360,9 @@ def main():
                                        f"(nbl=40 included), {nt_steps} time steps per apply, 1 Ricker source, "
                                        f"512 receivers, constant vp=1.5",
                            "decomposition": f"x-slabs over {nranks} GPU(s)" if nranks > 1 else "single GPU",
+                           "halo": (None if nranks == 1 else
+                                    "peer-memory stores over NVLink (CUDA IPC + device flags)"
+                                    if getattr(u.storage, 'p2p_registered', False) else "NCCL send/recv"),
                            "l2": "inputs (18 GB/GPU) larger than L2; no flush needed",
                            "time_steps_per_apply": nt_steps, "dt": float(dt)},
                 "clocks": clocks, "gpu_launches": launches,
