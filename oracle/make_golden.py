@@ -73,6 +73,21 @@ def acoustic(name, so, n, nbl, tn, preset='constant-isotropic', interpolation='l
          u=np.array(u.data), norm_rec=np.float32(norm(rec)), norm_u=np.float32(norm(u)), **extra)
 
 
+def kat3d_fs(interpolation, name):
+    """examples/seismic/acoustic/acoustic_example.py:80-87: `run(fs=True, dtype=float32)` -> norm(rec)
+    = 369.955 (linear) / 402.216 (sinc), rtol 1e-3."""
+    from devito import norm
+    from examples.seismic.acoustic.acoustic_example import acoustic_setup
+    solver = acoustic_setup(shape=(50, 50, 50), spacing=(20., 20., 20.), nbl=40, tn=1000., space_order=4,
+                            kernel='OT2', fs=True, preset='layers-isotropic', dtype=np.float32,
+                            interpolation=interpolation)
+    rec, u, _ = solver.forward()
+    g = solver.geometry
+    save(name, norm_rec=np.float32(norm(rec)), rec=np.array(rec.data[::4, ::7]), nt=g.nt,
+         dt=np.float32(solver.model.critical_dt), grid_shape=np.array(solver.model.grid.shape),
+         u_last=np.array(u.data[(g.nt - 1) % 3, ::3, ::3, ::3]))
+
+
 def adjoint(name, so, n, nbl, tn):
     """Forward then adjoint (acoustic/wavesolver.py:118-156): receiver data back-propagated."""
     from devito import norm
@@ -143,9 +158,15 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'fs', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
     if 'kat2d' in which:
         kat2d()
+    if 'fs' in which:
+        acoustic('iso3d_so4_fs', so=4, n=20, nbl=8, tn=150.0, preset='layers-isotropic', nlayers=3, fs=True)
+        acoustic('iso3d_so8_fs_sinc', so=8, n=20, nbl=8, tn=120.0, preset='layers-isotropic', nlayers=2,
+                 interpolation='sinc', fs=True)
+        kat3d_fs('linear', 'kat3d_fs_linear')
+        kat3d_fs('sinc', 'kat3d_fs_sinc')
     if 'iso8' in which:
         acoustic('iso3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'iso12' in which:

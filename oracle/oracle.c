@@ -128,7 +128,12 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                        int param_kind, const float *param, float vp, float dt, const int *lo,
                        const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
                        int rec_toff, int adjoint, float *grad, const int *galloc, int ghalo,
-                       const float *usave) {
+                       const float *usave, int free_surface) {
+    /* free_surface != 0: the reference's `freesurface` (acoustic/operators.py:5-47) on the LAST
+     * dimension: taps of the vertical derivative that fall above the surface, z - k < 0, read
+     * sign(z-k) * u[|z-k|] (antisymmetric mirror; a tap landing exactly on z = 0 contributes 0), and
+     * after the update u[t+1][.., z=0] = 0 (before injection). Halo cells above the surface are never
+     * read by the stencil. Requires the iteration to start at z = 0. */
     /* grad/usave != NULL: imaging condition of the reference's `Gradient` operator
      * (acoustic/operators.py:222): after each step grad -= usave[time] * u.dt2 (3-D only).
      * adjoint != 0: the reference's `Adjoint` operator (acoustic/operators.py:153-187) — the same
@@ -162,10 +167,13 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                     for (int z = lo[2]; z <= hi[2]; ++z) {
                         const size_t i = IDX3(x + so, y + so, z + so);
                         float lap = (wx[0] + wy[0] + wz[0]) * u0[i];
-                        for (int k = 1; k <= R; ++k)
+                        for (int k = 1; k <= R; ++k) {
+                            float zlo = u0[i - k];
+                            if (free_surface && z - k <= 0) zlo = (z - k < 0) ? -u0[i - z + (k - z)] : 0.0f;
                             lap += wx[k] * (u0[i - k * sx] + u0[i + k * sx]) +
                                    wy[k] * (u0[i - k * sy] + u0[i + k * sy]) +
-                                   wz[k] * (u0[i - k] + u0[i + k]);
+                                   wz[k] * (zlo + u0[i + k]);
+                        }
                         float r1 = r1s;
                         if (param_kind == 1) r1 = 1.0f / (param[i] * param[i]);
                         else if (param_kind == 2) r1 = param[i];
@@ -179,8 +187,11 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                 for (int y = lo[1]; y <= hi[1]; ++y) {
                     const size_t i = (size_t)(x + so) * sy + (size_t)(y + so);
                     float lap = (wx[0] + wy[0]) * u0[i];
-                    for (int k = 1; k <= R; ++k)
-                        lap += wx[k] * (u0[i - k * sy] + u0[i + k * sy]) + wy[k] * (u0[i - k] + u0[i + k]);
+                    for (int k = 1; k <= R; ++k) {
+                        float zlo = u0[i - k];
+                        if (free_surface && y - k <= 0) zlo = (y - k < 0) ? -u0[i - y + (k - y)] : 0.0f;
+                        lap += wx[k] * (u0[i - k * sy] + u0[i + k * sy]) + wy[k] * (zlo + u0[i + k]);
+                    }
                     float r1 = r1s;
                     if (param_kind == 1) r1 = 1.0f / (param[i] * param[i]);
                     else if (param_kind == 2) r1 = param[i];
@@ -188,6 +199,15 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                     u1[i] = (-r1 * (-2.0f * r2 * u0[i] + r2 * um[i]) + r3 * d * u0[i] + lap) /
                             (r1 * r2 + r3 * d);
                 }
+        }
+        if (free_surface) {
+            if (lo[ndim - 1] != 0) return 1;
+            if (ndim == 3) {
+                for (int x = lo[0]; x <= hi[0]; ++x)
+                    for (int y = lo[1]; y <= hi[1]; ++y) u1[IDX3(x + so, y + so, so)] = 0.0f;
+            } else {
+                for (int x = lo[0]; x <= hi[0]; ++x) u1[(size_t)(x + so) * sy + (size_t)so] = 0.0f;
+            }
         }
         inject(src, ndim, u1, NULL, sx, sy, so, lo, hi, time, param_kind, param, vp, dt);
         interp(rec, ndim, rec_toff ? u1 : u0, NULL, sx, sy, so, lo, hi, time);

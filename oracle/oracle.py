@@ -39,7 +39,7 @@ def load(fast=False):
     fp, ip = POINTER(c_float), POINTER(c_int)
     L.oracle_iso_forward.argtypes = [c_int, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, c_int, fp,
                                      c_float, c_float, ip, ip, c_int, c_int, POINTER(OSparse),
-                                     POINTER(OSparse), c_int, c_int, fp, ip, c_int, fp]
+                                     POINTER(OSparse), c_int, c_int, fp, ip, c_int, fp, c_int]
     L.oracle_iso_forward.restype = c_int
     L.oracle_tti_forward.argtypes = [fp, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, fp, fp, fp,
                                      c_float, c_float, c_float, c_float, c_float, c_float, ip, ip,
@@ -77,7 +77,7 @@ def _sparse(data, gp, ws, r, keep):
 
 def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, param_kind=0,
                 src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False, adjoint=False,
-                grad=None, ghalo=0, usave=None):
+                grad=None, ghalo=0, usave=None, free_surface=False):
     """grad (3-D, halo `ghalo`) / usave (nt, ...) enable the Gradient operator's imaging condition.
     u: (T, [nx+2so,] ny+2so, nz+2so) float32 C-contiguous, updated in place.
     w: list (per dim) of weights [0..R] incl. 1/h^2. src/rec: dict(data, gp, w, r)."""
@@ -98,7 +98,7 @@ def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, par
                               ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, rec_toff,
                               1 if adjoint else 0, _fp(grad),
                               _ip(galloc) if galloc is not None else None,
-                              ghalo, _fp(usave))
+                              ghalo, _fp(usave), 1 if free_surface else 0)
     assert rc == 0
     return u
 
@@ -159,8 +159,9 @@ def critical_dt(space_order, ndim, h_min, vp_max, eps_max=None, dtype=np.float32
     return dtype("%.3e" % (coeff * h_min / (scale * vp_max)))
 
 
-def damp_field(shape, nbl, spacing, so):
-    """Absorbing profile with halo `so` (zeros in the halo) — examples/seismic/model.py:25-63."""
+def damp_field(shape, nbl, spacing, so, fs=False):
+    """Absorbing profile with halo `so` (zeros in the halo) — examples/seismic/model.py:25-63.
+    fs: free surface, no layer on the low side of the last axis (model.py:45, :166-172)."""
     out = np.zeros(shape, dtype=np.float64)
     coeff = 1.5 * np.log(1.0 / 0.001) / nbl
     for ax, h in enumerate(spacing):
@@ -169,7 +170,8 @@ def damp_field(shape, nbl, spacing, so):
         for i in range(nbl):
             pos = abs((nbl - i + 1) / float(nbl))
             val = coeff * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi))
-            prof[i] += val / float(h)
+            if not (fs and ax == len(shape) - 1):
+                prof[i] += val / float(h)
             prof[n - 1 - i] += val / float(h)
         sh = [1] * len(shape)
         sh[ax] = n
@@ -214,3 +216,13 @@ def tabulate(coords, origin, spacing, r=1, interpolation='linear', dtype=np.floa
                 w[:, ri] = i0(b * np.sqrt(1 - (rpos / r) ** 2)) / i0(b) * np.sinc(rpos)
         ws.append(w)
     return gp, ws
+
+
+def layered_vp(shape, nlayers, vp_top=1.5, vp_bottom=3.5, dtype=np.float32):
+    """Preset `layers-isotropic` (examples/seismic/preset_models.py:120-133)."""
+    v = np.empty(shape, dtype=dtype)
+    v[:] = vp_top
+    vals = np.linspace(vp_top, vp_bottom, nlayers)
+    for i in range(1, nlayers):
+        v[..., i * int(shape[-1] / nlayers):] = vals[i]
+    return v

@@ -53,3 +53,38 @@ def iso_problem(n, nbl, so, tn, f0=0.010, vp=1.5, h=10.0, interpolation='linear'
     return dict(N=N, so=so, dt=dt, nt=nt, damp=damp, w=w, u=u, vp=vp,
                 src=dict(data=src, gp=sgp, w=sw, r=rr), rec=dict(data=rec, gp=rgp, w=rw, r=rr),
                 src_coords=src_c, rec_coords=rec_c, origin=origin, spacing=spacing)
+
+
+def fs_problem(n, nbl, so, tn, h=10.0, nlayers=3, interpolation='linear', f0=0.010):
+    """Inputs of `demo_model('layers-isotropic', fs=True) + setup_geometry` restated with the oracle:
+    free surface on top of z (no absorbing layer there, origin_z unchanged;
+    examples/seismic/model.py:113-131, :166-172), layered velocity edge-padded into the layers."""
+    shape = (n, n, n)
+    N = (n + 2 * nbl, n + 2 * nbl, n + nbl)
+    spacing = (np.float32(h),) * 3
+    origin = (np.float32(-nbl * h), np.float32(-nbl * h), np.float32(0.0))
+    vp_phys = O.layered_vp(shape, nlayers)
+    vp_dom = np.pad(vp_phys, ((nbl, nbl), (nbl, nbl), (0, nbl)), mode='edge')
+    dt = float(O.critical_dt(so, 3, h, float(vp_phys.max())))
+    nt, tvals = O.time_axis(0.0, tn, dt)
+    damp = O.damp_field(N, nbl, spacing, so, fs=True)
+    dom = tuple((n - 1) * h for _ in range(3))
+    src_c = np.array([[dom[0] * .5, dom[1] * .5, h]])
+    rx = np.linspace(0, dom[0], n)
+    ry = np.linspace(0, dom[1], n)
+    rec_c = np.empty((n * n, 3))
+    rec_c[:, 0] = np.repeat(rx, n)
+    rec_c[:, 1] = np.tile(ry, n)
+    rec_c[:, 2] = 2 * h
+    rr = 1 if interpolation == 'linear' else 4
+    sgp, sw = O.tabulate(src_c.astype(np.float32), origin, spacing, rr, interpolation)
+    rgp, rw = O.tabulate(rec_c.astype(np.float32), origin, spacing, rr, interpolation)
+    src = np.zeros((nt, 1), dtype=np.float32)
+    src[:, 0] = O.ricker(f0, tvals)
+    rec = np.zeros((nt, n * n), dtype=np.float32)
+    w = [O.fd2_weights(so, h)] * 3
+    u = np.zeros((3,) + tuple(s + 2 * so for s in N), dtype=np.float32)
+    return dict(N=N, so=so, dt=dt, nt=nt, damp=damp, w=w, u=u, vp_dom=vp_dom,
+                vp=np.pad(vp_dom, so, mode='edge').astype(np.float32),
+                src=dict(data=src, gp=sgp, w=sw, r=rr), rec=dict(data=rec, gp=rgp, w=rw, r=rr),
+                src_coords=src_c, rec_coords=rec_c, origin=origin, spacing=spacing)
