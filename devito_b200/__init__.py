@@ -14,7 +14,7 @@ from .types import (Grid, SubDomain, Dimension, SpaceDimension, TimeDimension,  
                     SteppingDimension, SubDimension, DefaultDimension, ConditionalDimension,
                     Function, TimeFunction, Constant, Buffer, NODE, CELL)
 from .sparse import SparseFunction, SparseTimeFunction, Injection, Interpolation  # noqa: F401
-from .equation import Eq, Inc, solve  # noqa: F401
+from .equation import Eq, Inc, FreeSurface, solve  # noqa: F401
 from .operator import Operator, PerformanceSummary  # noqa: F401
 from .builtins import (norm, sumall, inner, mmin, mmax, assign, smooth, gaussian_smooth,  # noqa: F401
                        initialize_function)

@@ -190,6 +190,10 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         for (int i = 0; i <= a->radius; ++i) p.w[di][i] = a->w[d][i];
     }
     if ((rc = iso_plan_init(p, a->kernel))) return cleanup(rc);
+    if (a->free_surface && p.o[2] != so) {
+        set_error("b2_iso_forward: a free surface needs the vertical iteration to start at 0");
+        return cleanup(B2_ERR_INVALID);
+    }
 
     g.sx = p.sx;
     g.sy = p.sy;
@@ -226,6 +230,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         } else {
             if ((rc = iso_step(p, t0, t2, t1, 0, p.n[0]))) return cleanup(rc);
         }
+        if (a->free_surface && (rc = iso_fs_fix(p, t0, t2, t1, 0, p.n[0]))) return cleanup(rc);
         if (per_step_events) se.next();
         float *f1 = p.u + (size_t)t1 * p.slot_elems;
         if ((rc = launch_inject(src, g, f1, nullptr, time, p.param_kind, p.param, scalar_scale, dt2)))

@@ -70,6 +70,46 @@ __global__ void __launch_bounds__(256) k_iso_generic(IsoGK k) {
     }
 }
 
+// Free surface on the low side of the last dimension (reference `freesurface`,
+// examples/seismic/acoustic/operators.py:5-47; generated form: `r1[z]*u[t0][..][4 + abs(z - 1)]`,
+// `u[t2][x][y][4] = 0`). The sweep kernels compute every row with the plain stencil; this kernel then
+// REDOES the rows z < radius, the only ones whose vertical taps reach above the surface, with the
+// mirrored taps  u[z - k] -> sign(z - k) * u[|z - k|]  (a tap landing on z = 0 contributes 0), and
+// clears the surface row. It touches radius/n2 of the grid (0.4 % at 1024^3, so = 8). The halo above
+// the surface is left alone: sinc sources/receivers deposit into / sample it in the reference too.
+__global__ void __launch_bounds__(256) k_iso_fs_fix(IsoGK k) {
+    const int z = threadIdx.x;                                   // 0 .. r2-1 (blockDim.x == 8)
+    const int y = blockIdx.x * blockDim.y + threadIdx.y;
+    if (z >= k.r2 || y >= k.n1) return;
+    for (int x = blockIdx.y; x < k.n0; x += gridDim.y) {
+        const long long idx = (long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z);
+        if (z == 0) { k.u1[idx] = 0.f; continue; }
+        const float c = k.u0[idx];
+        float acc = (k.w[0][0] + k.w[1][0] + k.w[2][0]) * c;
+        for (int i = 1; i <= k.r0; ++i)
+            acc += k.w[0][i] * (k.u0[idx - i * k.sx] + k.u0[idx + i * k.sx]);
+        for (int i = 1; i <= k.r1; ++i)
+            acc += k.w[1][i] * (k.u0[idx - i * k.sy] + k.u0[idx + i * k.sy]);
+        for (int i = 1; i <= k.r2; ++i) {
+            float lo;
+            if (z - i > 0) lo = k.u0[idx - i];
+            else if (z - i < 0) lo = -k.u0[idx - z + (i - z)];
+            else lo = 0.f;
+            acc += k.w[2][i] * (lo + k.u0[idx + i]);
+        }
+        float m_dt2 = k.m_dt2;
+        if (k.param_kind == B2_PARAM_VP) {
+            const float v = k.param[idx];
+            m_dt2 = k.inv_dt2 / (v * v);
+        } else if (k.param_kind == B2_PARAM_M) {
+            m_dt2 = k.param[idx] * k.inv_dt2;
+        }
+        const float d = k.damp ? k.damp[idx] * k.inv_dt : 0.f;
+        const float num = m_dt2 * (2.f * c - k.um[idx]) + d * c + acc;
+        k.u1[idx] = num / (m_dt2 + d);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA 2.5-D kernel
 // ------------------------------------------------------------------------------------------
@@ -528,17 +568,7 @@ static int launch_tma_pk(const IsoPlan &p, int s0, int sm, int s1, int xlo, int 
     return B2_ERR_INVALID;
 }
 
-int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
-    if (xcount <= 0) return B2_OK;
-    if (p.use_tma) {
-        switch (p.radius[2]) {
-            case 2: return launch_tma_pk<2>(p, slot0, slotm, slot1, xlo, xcount);
-            case 4: return launch_tma_pk<4>(p, slot0, slotm, slot1, xlo, xcount);
-            case 6: return launch_tma_pk<6>(p, slot0, slotm, slot1, xlo, xcount);
-            case 8: return launch_tma_pk<8>(p, slot0, slotm, slot1, xlo, xcount);
-        }
-        return B2_ERR_INVALID;
-    }
+static IsoGK generic_args(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
     IsoGK k;
     k.u0 = p.u + (size_t)slot0 * p.slot_elems;
     k.um = p.u + (size_t)slotm * p.slot_elems;
@@ -561,6 +591,36 @@ int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xco
     k.inv_dt2 = 1.0f / (p.dt * p.dt);
     k.m_dt2 = (1.0f / (p.vp * p.vp)) * k.inv_dt2;
     memcpy(k.w, p.w, sizeof(k.w));
+    return k;
+}
+
+int iso_fs_fix(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
+    if (xcount <= 0) return B2_OK;
+    if (p.n[2] <= 2 * p.radius[2]) {
+        set_error("free surface: the vertical extent %d is too small for radius %d", p.n[2], p.radius[2]);
+        return B2_ERR_INVALID;
+    }
+    IsoGK k = generic_args(p, slot0, slotm, slot1, xlo, xcount);
+    dim3 block(8, 32, 1);
+    dim3 grid((k.n1 + 31) / 32, (unsigned)std::min(xcount, 65535), 1);
+    k_iso_fs_fix<<<grid, block, 0, stream()>>>(k);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
+int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
+    if (xcount <= 0) return B2_OK;
+    if (p.use_tma) {
+        switch (p.radius[2]) {
+            case 2: return launch_tma_pk<2>(p, slot0, slotm, slot1, xlo, xcount);
+            case 4: return launch_tma_pk<4>(p, slot0, slotm, slot1, xlo, xcount);
+            case 6: return launch_tma_pk<6>(p, slot0, slotm, slot1, xlo, xcount);
+            case 8: return launch_tma_pk<8>(p, slot0, slotm, slot1, xlo, xcount);
+        }
+        return B2_ERR_INVALID;
+    }
+    IsoGK k = generic_args(p, slot0, slotm, slot1, xlo, xcount);
     dim3 block(64, 4, 1);
     dim3 grid((k.n2 + 63) / 64, (k.n1 + 3) / 4, (unsigned)std::min(xcount, 65535));
     timing_begin();

@@ -35,4 +35,8 @@ int iso_plan_init(IsoPlan &p, int kernel);
 // u[slot1] = update(u[slot0], u[slotm]).
 int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount);
 
+// Free surface at the low end of the last dimension: after iso_step, recompute the rows z < radius
+// with mirrored vertical taps and clear the surface row (b2_iso_args.free_surface).
+int iso_fs_fix(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount);
+
 }  // namespace b2

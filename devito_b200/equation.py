@@ -4,7 +4,7 @@
 the expression must be linear in the target, and the result is `-rest / coefficient`."""
 from .symbolics import Expr, as_expr, linear_terms, Number, NonLinear
 
-__all__ = ['Eq', 'Inc', 'solve']
+__all__ = ['Eq', 'Inc', 'FreeSurface', 'solve']
 
 
 class Eq:
@@ -46,6 +46,31 @@ class Eq:
 
 class Inc(Eq):
     is_Increment = True
+
+
+class FreeSurface:
+    """Free-surface boundary condition for the explicit update `eq` on the low end of the grid's last
+    dimension — what the reference's `freesurface(model, eq)` builds symbolically
+    (examples/seismic/acoustic/operators.py:5-47): on `subdomain` (the top `space_order` rows) the same
+    update with every vertical tap that falls above the surface replaced by the antisymmetric mirror
+    `sign(z - k) * u[|z - k|]`, followed by `u.forward[z = 0] = 0`.
+
+    It is a first-class object here (the reference rewrites sub-expressions with `sign`/`INT(abs())`
+    indices); the CUDA path implements it natively (`b2_iso_args.free_surface`)."""
+    is_Increment = False
+
+    def __init__(self, eq, subdomain):
+        if not isinstance(eq, Eq):
+            raise TypeError("FreeSurface wraps the time-update Eq it mirrors")
+        self.eq = eq
+        self.subdomain = subdomain
+
+    @property
+    def field(self):
+        return self.eq.lhs.function
+
+    def __repr__(self):
+        return f"FreeSurface({self.eq.lhs!r})"
 
 
 def solve(eq, target, **kwargs):

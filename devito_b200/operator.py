@@ -29,7 +29,7 @@ from .symbolics import (Expr, Number, Symbol, Add, Mul, Pow, Call, Access, as_ex
                         NonLinear, fd_weights, fd_offsets, _py_funcs)
 from .types import Function, TimeFunction, Constant, Dimension
 from .sparse import Injection, Interpolation, SparseTimeFunction
-from .equation import Eq, Inc
+from .equation import Eq, Inc, FreeSurface
 from .interpreter import Interpreter
 from .parameters import configuration
 from .exceptions import InvalidArgument, ExecutionError, BackendUnavailable, InvalidOperator
@@ -163,6 +163,8 @@ class Operator:
         for it in items:
             if isinstance(it, Eq):
                 self._items.append(('eq', it))
+            elif isinstance(it, FreeSurface):
+                self._items.append(('fs', it))
             elif isinstance(it, Injection):
                 self._items.append(('inject', it))
             elif isinstance(it, Interpolation):
@@ -177,6 +179,9 @@ class Operator:
             self._plan = self._recognise()
         except _Unrecognised as e:
             self._why_not = str(e)
+        if self._plan is None and any(k == 'fs' for k, _ in self._items):
+            raise InvalidOperator(f"free-surface operator not recognised by the CUDA path ({self._why_not}); "
+                                  "there is no interpreter (CPU) implementation of it")
         self._interp = None if self._plan is not None else Interpreter(self._items, None, self._subs, name=name)
         self._profiler_last = None
 
@@ -191,6 +196,7 @@ class Operator:
         eqs = [o for k, o in self._items if k == 'eq']
         injs = [o for k, o in self._items if k == 'inject']
         itps = [o for k, o in self._items if k == 'interp']
+        fss = [o for k, o in self._items if k == 'fs']
         incs = [e for e in eqs if e.is_Increment]
         eqs = [e for e in eqs if not e.is_Increment]
         if not eqs:
@@ -208,7 +214,8 @@ class Operator:
             if f.time_order != 2:
                 raise _Unrecognised("time_order != 2")
             if e.subdomain is not None and any(d.is_Sub for d in e.subdomain.dimensions):
-                raise _Unrecognised("restricted subdomain")
+                if not self._covered_by_free_surface(e, fss):
+                    raise _Unrecognised("restricted subdomain")
             updates.append((f, e))
         if len(injs) > 1 or len(itps) > 1:
             raise _Unrecognised("more than one injection/interpolation")
@@ -216,16 +223,43 @@ class Operator:
             raise _Unrecognised("increments are only supported next to a single acoustic update")
         if len(incs) > 1:
             raise _Unrecognised("more than one increment")
+        if fss and (len(updates) != 1 or len(fss) != 1 or fss[0].field is not updates[0][0]):
+            raise _Unrecognised("a free surface is only on the fast path for the single-field acoustic update")
         if len(updates) == 1:
             plan = self._recognise_iso(updates[0], injs, itps)
             if incs:
                 self._attach_imaging(plan, incs[0])
+            plan['free_surface'] = bool(fss)
+            if fss and not self._covered_by_free_surface(updates[0][1], fss):
+                raise _Unrecognised("free-surface rows and the update's subdomain do not tile the grid")
             return plan
         if len(updates) == 2:
             if self._dirn != 1:
                 raise _Unrecognised("adjoint TTI is not on the fast path")
             return self._recognise_tti(updates, injs, itps)
         raise _Unrecognised("unsupported number of update equations")
+
+    @staticmethod
+    def _covered_by_free_surface(eq, fss):
+        """The reference pairs the update on `physdomain` = z in [so, z_M] (examples/seismic/model.py:
+        67-79) with the free-surface rows `fsdomain` = z in [0, so) (model.py:82-98): together they tile
+        the grid. True iff `eq`'s subdomain and the FreeSurface's subdomain are that pair (any equal
+        thickness), restricted on the LAST dimension only, and the FreeSurface mirrors this very update."""
+        if len(fss) != 1:
+            return False
+        fs = fss[0]
+        if fs.eq is not eq and (fs.eq.lhs != eq.lhs or fs.eq.rhs is not eq.rhs):
+            return False
+        if eq.subdomain is None or fs.subdomain is None:
+            return False
+        pd, fd = eq.subdomain.dimensions, fs.subdomain.dimensions
+        if len(pd) != len(fd) or any(d.is_Sub for d in pd[:-1]) or any(d.is_Sub for d in fd[:-1]):
+            return False
+        zp, zf = pd[-1], fd[-1]
+        if not (zp.is_Sub and zf.is_Sub and zp.parent is zf.parent):
+            return False
+        return (zp.kind == 'middle' and zf.kind == 'left' and zp.thickness[1] == 0 and
+                zp.thickness[0] == zf.thickness[0] and zf.thickness[0] >= eq.lhs.function.space_order // 2)
 
     def _coeffs(self, rhs, fields):
         rhs = rhs.evaluate
@@ -643,7 +677,8 @@ class Operator:
         entry = 'b2_iso_forward' if p['kind'] == 'iso' else 'b2_tti_forward'
         return (f"/* Operator `{self.name}` -> libb200stencil.so::{entry} (sm_100a)\n"
                 f"   space_order={p['so']} radius={p['R']} src={p['src'] and p['src'].name} "
-                f"rec={p['rec'] and p['rec'].name} rec_toff={p['rec_toff']} */")
+                f"rec={p['rec'] and p['rec'].name} rec_toff={p['rec_toff']}"
+                f"{' free_surface' if p.get('free_surface') else ''} */")
 
     ccode = property(__str__)
 
@@ -888,6 +923,9 @@ class Operator:
             lo.append(int(a))
             hi.append(int(b))
         args['lo'], args['hi'] = lo, hi
+        if p.get('free_surface') and lo[-1] != 0:
+            raise InvalidArgument("a free-surface operator must iterate from the surface row (lower bound 0 "
+                                  "on the last dimension)")
         # sparse
         src = self._resolve(kwargs, p['src'], post)
         rec = self._resolve(kwargs, p['rec'], post)
@@ -1099,6 +1137,7 @@ class Operator:
         timers = L_.Profiler()
         a.timers = ctypes.pointer(timers)
         a.adjoint = 1 if p.get('adjoint') else 0
+        a.free_surface = 1 if p.get('free_surface') else 0
         if args.get('grad') is not None:
             a.grad = self._field_obj(args['grad'], dev, res, hold, written=True).ptr
             a.usave = self._field_obj(args['usave'], dev, res, hold).ptr

@@ -1,6 +1,6 @@
 """Isotropic acoustic modelling (mirror of examples/seismic/acoustic/operators.py:50-187 and
 wavesolver.py:11-156): forward and adjoint operators (gradient/Born are SURVEY §8f)."""
-from .. import Eq, Inc, Function, Operator, TimeFunction, solve
+from .. import Eq, FreeSurface, Inc, Function, Operator, TimeFunction, solve
 from ..tools import memoized_meth
 
 __all__ = ['iso_stencil', 'ForwardOperator', 'AdjointOperator', 'GradientOperator', 'AcousticWaveSolver']
@@ -14,7 +14,12 @@ def iso_stencil(field, model, kernel='OT2', **kwargs):
     unext = field.forward if forward else field.backward
     udt = field.dt if forward else field.dt.T
     eq_time = solve(model.m * field.dt2 - field.laplace - kwargs.get('q', 0) + model.damp * udt, unext)
-    return [Eq(unext, eq_time, subdomain=model.grid.subdomains['physdomain'])]
+    update = Eq(unext, eq_time, subdomain=model.grid.subdomains['physdomain'])
+    if model.fs:
+        # operators.py:105-106 `freesurface(model, Eq(unext, eq_time))`: the top rows get the same
+        # update with vertical taps mirrored about the surface, and the surface row is cleared
+        return [update, FreeSurface(update, model.grid.subdomains['fsdomain'])]
+    return [update]
 
 
 def ForwardOperator(model, geometry, space_order=4, save=False, kernel='OT2', **kwargs):

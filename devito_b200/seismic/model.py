@@ -40,8 +40,8 @@ def initialize_damp(damp, padsizes, spacing, abc_type="damp", fs=False):
 
 
 class PhysicalDomain(SubDomain):
-    """The whole grid (no free surface on this backend's path) — kept so that equations written
-    with `subdomain=model.grid.subdomains['physdomain']` work unchanged."""
+    """Where the wave equation is solved: the whole grid, or — with a free surface — everything
+    below the top `space_order` rows, which `FSDomain` covers (examples/seismic/model.py:67-98)."""
     name = 'physdomain'
 
     def __init__(self, so, fs=False):
@@ -54,6 +54,20 @@ class PhysicalDomain(SubDomain):
             spec[d] = d
         if self.fs:
             spec[dimensions[-1]] = ('middle', self.so, 0)
+        return spec
+
+
+class FSDomain(SubDomain):
+    """The top `space_order` rows of the last dimension, updated with mirrored vertical taps."""
+    name = 'fsdomain'
+
+    def __init__(self, so):
+        super().__init__()
+        self.size = so
+
+    def define(self, dimensions):
+        spec = {d: d for d in dimensions}
+        spec[dimensions[-1]] = ('left', self.size)
         return spec
 
 
@@ -71,24 +85,30 @@ class SeismicModel:
 
     def __init__(self, origin, spacing, shape, space_order, vp, nbl=20, fs=False, dtype=np.float32,
                  subdomains=(), bcs="mask", grid=None, topology=None, **kwargs):
-        if fs:
-            raise NotImplementedError("free-surface models are outside this backend's scope (SURVEY §8f)")
         if 'vs' in kwargs:
             raise NotImplementedError("elastic models are outside this backend's scope (SURVEY §8f)")
         self.shape = tuple(int(n) for n in shape)
         self.space_order = int(space_order)
         self.nbl = int(nbl)
-        self.fs = False
+        self.fs = bool(fs)
         self.origin = tuple(dtype(o) for o in origin)
-        ext_shape = tuple(n + 2 * self.nbl for n in self.shape)
+        # free surface: no absorbing layer above the last dimension, whose origin stays put
+        # (examples/seismic/model.py:113-131)
+        ext_shape = [n + 2 * self.nbl for n in self.shape]
+        ext_origin = [dtype(o - hh * self.nbl) for o, hh in zip(origin, spacing)]
+        extra = (PhysicalDomain(space_order, fs=self.fs),)
+        if self.fs:
+            ext_shape[-1] -= self.nbl
+            ext_origin[-1] = dtype(origin[-1])
+            extra += (FSDomain(space_order),)
+        ext_shape = tuple(ext_shape)
         if grid is not None:
             self.grid = grid
         else:
             h = np.asarray(spacing, dtype=np.float64)
             self.grid = Grid(shape=ext_shape, extent=tuple(h * (np.asarray(ext_shape) - 1)),
-                             origin=tuple(dtype(o - hh * self.nbl) for o, hh in zip(origin, spacing)),
-                             dtype=dtype, topology=topology,
-                             subdomains=tuple(subdomains) + (PhysicalDomain(space_order),))
+                             origin=tuple(ext_origin), dtype=dtype, topology=topology,
+                             subdomains=tuple(subdomains) + extra)
         self._physical_parameters = set()
         self._dt = kwargs.get('dt')
         self._dt_scale = 1
@@ -127,11 +147,13 @@ class SeismicModel:
             self.damp.data[:] = damp_profile(self.grid.shape_global, self.padsizes, self.grid.spacing, bcs,
                                              x_range=dist.x_range)
         else:
-            initialize_damp(self.damp, self.padsizes, self.spacing, abc_type=bcs, fs=False)
+            initialize_damp(self.damp, self.padsizes, self.spacing, abc_type=bcs, fs=self.fs)
 
     @property
     def padsizes(self):
-        return [(self.nbl, self.nbl)] * self.dim
+        """(left, right) absorbing points per dimension; none above a free surface (model.py:166-172)."""
+        pads = [(self.nbl, self.nbl)] * (self.dim - 1)
+        return pads + [(0 if self.fs else self.nbl, self.nbl)]
 
     # -- parameters ------------------------------------------------------------------------------------
     def _gen_phys_param(self, field, name, space_order, default_value=0, **kwargs):
@@ -226,9 +248,10 @@ def damp_profile(shape, padsizes, spacing, abc_type="damp", x_range=None):
     for ax, ((nbl, nbr), h) in enumerate(zip(padsizes, spacing)):
         n = shape[ax]
         prof = np.zeros(n)
-        i = np.arange(nbl)
-        pos = np.abs((nbl - i + 1) / float(nbl))
-        prof[:nbl] += 1.5 * np.log(1000.0) / nbl * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / float(h)
+        if nbl > 0:
+            i = np.arange(nbl)
+            pos = np.abs((nbl - i + 1) / float(nbl))
+            prof[:nbl] += 1.5 * np.log(1000.0) / nbl * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / float(h)
         j = np.arange(n - nbr, n)
         pos = np.abs((nbr - (n - 1 - j) + 1) / float(nbr))
         prof[n - nbr:] += 1.5 * np.log(1000.0) / nbr * (pos - np.sin(2 * np.pi * pos) / (2 * np.pi)) / float(h)
@@ -252,11 +275,13 @@ def demo_model(preset, **kwargs):
     dtype = kwargs.pop('dtype', np.float32)
     vp = kwargs.pop('vp', 1.5)
     nlayers = kwargs.pop('nlayers', 3)
-    kwargs.pop('fs', None)
+    fs = kwargs.pop('fs', False)
     p = preset.lower()
+    if fs and 'tti' in p:
+        raise NotImplementedError("free-surface TTI models are not on this backend's path yet")
     if p == 'constant-isotropic':
         return SeismicModel(space_order=space_order, vp=vp, origin=origin, shape=shape, dtype=dtype,
-                            spacing=spacing, nbl=nbl, **kwargs)
+                            spacing=spacing, nbl=nbl, fs=fs, **kwargs)
     if p in ('constant-tti', 'constant-tti-noazimuth'):
         phi = .35 if (len(shape) > 2 and p != 'constant-tti-noazimuth') else None
         return SeismicModel(space_order=space_order, vp=vp, origin=origin, shape=shape, dtype=dtype,
@@ -271,7 +296,7 @@ def demo_model(preset, **kwargs):
         for i in range(1, nlayers):
             v[..., i * int(shape[-1] / nlayers):] = vp_i[i]
         return SeismicModel(space_order=space_order, vp=v, origin=origin, shape=shape, dtype=dtype,
-                            spacing=spacing, nbl=nbl, bcs="damp", **kwargs)
+                            spacing=spacing, nbl=nbl, bcs="damp", fs=fs, **kwargs)
     if p in ('layers-tti', 'layers-tti-noazimuth'):
         vp_top = kwargs.pop('vp_top', 1.5)
         vp_bottom = kwargs.pop('vp_bottom', 3.5)

@@ -122,6 +122,11 @@ struct b2_iso_args {
      * `grad` may have its own halo width (hsize). Both NULL -> no imaging condition.          */
     struct b2_dataobj *grad;
     struct b2_dataobj *usave;
+    /* != 0: free surface on the low side of the LAST dimension (reference `freesurface`,
+     * examples/seismic/acoustic/operators.py:5-47, models built with fs=True): vertical taps that fall
+     * above the surface read sign(z-k) * u[|z-k|] (antisymmetric mirror), and u[t+1] is cleared on the
+     * surface row z = 0 before the source is injected. Needs z_m (y_m in 2-D) == 0.               */
+    int free_surface;
 };
 int b2_iso_forward(const struct b2_iso_args *a);
 
