@@ -93,7 +93,8 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         return B2_ERR_INVALID;
     }
     if (a->time_M < a->time_m) return B2_OK;
-    B2_CUDA(cudaSetDevice(a->deviceid), B2_ERR_DEVICE);
+    std::lock_guard<std::mutex> api_lock(api_mutex());
+    if (int rc0 = use_device(a->deviceid)) return rc0;
 
     const int nd = a->ndim;
     const int so = a->space_order;

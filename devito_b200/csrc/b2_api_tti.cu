@@ -15,7 +15,8 @@ int check_finite(const float *f, size_t n, bool &bad);
 extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
     if (!a || !a->u || !a->v) { set_error("b2_tti_forward: NULL args"); return B2_ERR_INVALID; }
     if (a->time_M < a->time_m) return B2_OK;
-    B2_CUDA(cudaSetDevice(a->deviceid), B2_ERR_DEVICE);
+    std::lock_guard<std::mutex> api_lock(api_mutex());
+    if (int rc0 = use_device(a->deviceid)) return rc0;
     const int so = a->space_order;
     int rc = B2_OK;
 

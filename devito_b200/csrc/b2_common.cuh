@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <mutex>
 #include "b200stencil.h"
 
 #define B2_MAX_RADIUS 8
@@ -28,6 +29,14 @@ extern unsigned long long g_launches;
 
 void set_error(const char *fmt, ...);
 cudaStream_t stream();
+// The library keeps device-bound state (stream, staging pool, scratch tables, kernel attributes) and
+// is built for one process per GPU, like the reference's device path (one MPI rank per GPU):
+// use_device() selects `dev` and binds the process to it on first use; a later call naming another
+// device fails with B2_ERR_INVALID instead of touching memory of the wrong GPU.
+int use_device(int dev);
+// serialises the compute entry points (ctypes callers drop the GIL; the global state above is not
+// re-entrant)
+std::mutex &api_mutex();
 
 // kernel timing (CUDA events around every stencil launch when enabled)
 void timing_begin();

@@ -262,7 +262,7 @@ int b2_nccl_unique_id(const char *nccl_lib, char id_out[128]) {
 b2_halo_ctx *b2_halo_create(const char *nccl_lib, const char id_in[128], int rank, int nranks,
                             int deviceid) {
     if (load_nccl(nccl_lib)) return nullptr;
-    if (cudaSetDevice(deviceid) != cudaSuccess) { b2::set_error("cudaSetDevice(%d) failed", deviceid); return nullptr; }
+    if (b2::use_device(deviceid)) return nullptr;
     b2_halo_ctx *ctx = new b2_halo_ctx();
     ctx->rank = rank;
     ctx->nranks = nranks;

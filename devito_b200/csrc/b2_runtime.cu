@@ -26,6 +26,28 @@ void set_error(const char *fmt, ...) {
     g_last_error = buf;
 }
 
+static int g_bound_device = -1;
+
+int use_device(int dev) {
+    if (g_bound_device >= 0 && dev != g_bound_device) {
+        set_error("libb200stencil is bound to device %d in this process (one process per GPU); "
+                  "device %d requested", g_bound_device, dev);
+        return B2_ERR_INVALID;
+    }
+    cudaError_t e = cudaSetDevice(dev);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d) -> %s", dev, cudaGetErrorString(e));
+        return B2_ERR_DEVICE;
+    }
+    g_bound_device = dev;
+    return B2_OK;
+}
+
+std::mutex &api_mutex() {
+    static std::mutex m;
+    return m;
+}
+
 cudaStream_t stream() {
     if (g_user_stream) return g_user_stream;
     if (!g_stream) cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
@@ -81,6 +103,9 @@ static void pool_release(void *p, size_t nbytes) {
 
 int stage_in(const b2_dataobj *obj, int ndim, DevArray &out, bool copy_in) {
     if (!obj) { set_error("stage_in: NULL dataobj"); return B2_ERR_INVALID; }
+    if (!obj->size) { set_error("stage_in: dataobj without `size`"); return B2_ERR_INVALID; }
+    for (int i = 0; i < ndim; ++i)
+        if (obj->size[i] <= 0) { set_error("stage_in: non-positive extent %d on dim %d", obj->size[i], i); return B2_ERR_INVALID; }
     out.ndim = ndim;
     size_t n = 1;
     for (int i = 0; i < ndim; ++i) { out.size[i] = obj->size[i]; n *= (size_t)obj->size[i]; }
@@ -154,38 +179,38 @@ double b2_kernel_timing_ms(int *nlaunches) {
 
 void *b2_malloc_device(unsigned long nbytes, int deviceid) {
     void *p = nullptr;
-    if (cudaSetDevice(deviceid) != cudaSuccess) return nullptr;
-    if (cudaMalloc(&p, nbytes) != cudaSuccess) return nullptr;
+    if (use_device(deviceid)) return nullptr;
+    if (cudaMalloc(&p, nbytes) != cudaSuccess) { set_error("cudaMalloc(%lu bytes) failed", nbytes); return nullptr; }
     return p;
 }
 
 void b2_free_device(void *p, int deviceid) {
-    cudaSetDevice(deviceid);
+    if (use_device(deviceid)) return;
     cudaFree(p);
 }
 
 int b2_memcpy_h2d(void *dst, const void *src, unsigned long nbytes, int deviceid) {
-    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    if (int rc = use_device(deviceid)) return rc;
     B2_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, stream()), B2_ERR_MEMORY);
     B2_CUDA(cudaStreamSynchronize(stream()), B2_ERR_MEMORY);
     return B2_OK;
 }
 
 int b2_memcpy_d2h(void *dst, const void *src, unsigned long nbytes, int deviceid) {
-    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    if (int rc = use_device(deviceid)) return rc;
     B2_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, stream()), B2_ERR_MEMORY);
     B2_CUDA(cudaStreamSynchronize(stream()), B2_ERR_MEMORY);
     return B2_OK;
 }
 
 int b2_memset_device(void *dst, int value, unsigned long nbytes, int deviceid) {
-    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    if (int rc = use_device(deviceid)) return rc;
     B2_CUDA(cudaMemsetAsync(dst, value, nbytes, stream()), B2_ERR_MEMORY);
     return B2_OK;
 }
 
 int b2_synchronize(int deviceid) {
-    B2_CUDA(cudaSetDevice(deviceid), B2_ERR_DEVICE);
+    if (int rc = use_device(deviceid)) return rc;
     B2_CUDA(cudaStreamSynchronize(stream()), B2_ERR_DEVICE);
     return B2_OK;
 }

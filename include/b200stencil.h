@@ -26,6 +26,11 @@
  *     (devito/types/dimension.py:279-331);
  *   - return value: 0 ok; 100 NaN/Inf in the wavefield; 200..203 device/launch failures
  *     (devito/passes/iet/errors.py:192-198).  We add 210 = invalid argument.
+ *
+ * Process model: one process per GPU (like the reference's device path: one MPI rank per GPU).
+ * The library binds to the first `deviceid` it is given; a later call naming another device
+ * returns 210.  b2_iso_forward / b2_tti_forward are blocking and serialised by an internal mutex,
+ * so they may be called from several host threads (ctypes drops the GIL) but do not overlap.
  */
 #ifndef B200STENCIL_H
 #define B200STENCIL_H
