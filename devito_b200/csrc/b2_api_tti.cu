@@ -110,10 +110,13 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
     const float dt2 = a->dt * a->dt;
     const float scalar_scale = dt2 * a->vp * a->vp;
     const int T = p.tsize;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static cudaEvent_t e0 = nullptr, e1 = nullptr;      // created once (the process is bound to one device)
     if (a->timers) {
-        cudaEventCreate(&e0);
-        cudaEventCreate(&e1);
+        if (!e0 && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) {
+            e0 = e1 = nullptr;
+            set_error("b2_tti_forward: cannot create timing events");
+            return cleanup(B2_ERR_DEVICE);
+        }
         cudaEventRecord(e0, stream());
     }
     const bool p2p = a->halo && halo_p2p_active(a->halo, p.u) && halo_p2p_active(a->halo, p.v);
@@ -159,8 +162,6 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         a->timers->section0 += ms * 1e-3;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
     }
     return cleanup(B2_OK);
 }
