@@ -2,7 +2,7 @@
 
 `Eq`/`Inc` mirror devito/types/equation.py; `solve` mirrors devito/operations/solve.py:19-78:
 the expression must be linear in the target, and the result is `-rest / coefficient`."""
-from .symbolics import Expr, as_expr, linear_terms, Number, NonLinear
+from .symbolics import as_expr, linear_terms, NonLinear
 
 __all__ = ['Eq', 'Inc', 'FreeSurface', 'solve']
 

@@ -9,8 +9,7 @@ and fails loudly when it is unavailable).
 """
 import numpy as np
 
-from .symbolics import (Expr, Number, Symbol, Add, Mul, Pow, Call, Access, Derivative, _np_funcs,
-                        as_expr)
+from .symbolics import Number, Add, Mul, Pow, Call, _np_funcs
 from .exceptions import InvalidArgument
 
 __all__ = ['Interpreter']

@@ -18,22 +18,21 @@ over the C ABI in include/b200stencil.h (one FFI crossing per `apply`, like the 
 interpreter.  The recognised path NEVER falls back to the CPU.
 """
 import ctypes
-import itertools
 import os
 import time as _time
 from collections import OrderedDict
 
 import numpy as np
 
-from .symbolics import (Expr, Number, Symbol, Add, Mul, Pow, Call, Access, as_expr, linear_terms,
-                        NonLinear, fd_weights, fd_offsets, _py_funcs)
-from .types import Function, TimeFunction, Constant, Dimension
+from .symbolics import (Number, Add, Mul, Pow, Call, as_expr, linear_terms, NonLinear, fd_weights,
+                        fd_offsets, _py_funcs)
+from .types import Function, TimeFunction, Constant
 from .sparse import Injection, Interpolation, SparseTimeFunction
-from .equation import Eq, Inc, FreeSurface
+from .equation import Eq, FreeSurface
 from .interpreter import Interpreter
 from .parameters import configuration
-from .exceptions import InvalidArgument, ExecutionError, BackendUnavailable, InvalidOperator
-from .logger import perf, warning
+from .exceptions import InvalidArgument, ExecutionError, InvalidOperator
+from .logger import perf
 from .tools import flatten
 from . import _lib as L_
 from . import distributed

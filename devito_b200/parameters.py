@@ -3,7 +3,6 @@
 ``DEVITO_*`` devito/parameters.py:142-159).  Only the keys that influence this backend are
 interpreted; the others are accepted and stored so that user scripts keep working."""
 import os
-from contextlib import contextmanager
 from functools import wraps
 
 __all__ = ['configuration', 'switchconfig']

@@ -11,8 +11,8 @@ one rank for the final gather.
 """
 import numpy as np
 
-from .symbolics import Expr, Access, Index, as_expr
-from .types import DiscreteFunction, DefaultDimension, Data, FieldStorage
+from .symbolics import Index, as_expr
+from .types import DiscreteFunction, DefaultDimension
 
 __all__ = ['SparseFunction', 'SparseTimeFunction', 'Injection', 'Interpolation',
            '_default_radius']

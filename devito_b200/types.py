@@ -12,13 +12,9 @@ device mirror (a torch tensor used purely as an allocation).  `.data` access syn
 device -> host lazily; the next CUDA operator re-uploads only if the host side was exposed.
 (The reference copies every array H2D/D2H on every `apply`, devito/passes/iet/definitions.py:636-671.)
 """
-from fractions import Fraction
-
 import numpy as np
 
-from .symbolics import Expr, Symbol, Access, Index, Number, as_expr, Derivative
-from .parameters import configuration
-from .exceptions import InvalidArgument
+from .symbolics import Symbol, Access, Index
 
 __all__ = ['Dimension', 'SpaceDimension', 'TimeDimension', 'SteppingDimension', 'SubDimension',
            'DefaultDimension', 'ConditionalDimension', 'Grid', 'SubDomain', 'Function',

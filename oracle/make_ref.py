@@ -10,7 +10,6 @@ directory is git-ignored but travels to the GPU box, where oracle/refrun.py comp
 the reference's own flags (-O3 -march=native -ffast-math -fopenmp) and times them as the
 `kind: "reference"` CPU baseline.
 """
-import json
 import os
 import subprocess
 import sys

@@ -7,8 +7,7 @@ the reference itself (oracle/make_golden.py -> tests/golden/).
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, Structure, c_float, c_int, c_void_p
-from fractions import Fraction
+from ctypes import POINTER, Structure, c_float, c_int
 
 import numpy as np
 

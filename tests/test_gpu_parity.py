@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from helpers import load_golden, rel_linf, domain, iso_problem
+from helpers import load_golden, rel_linf, iso_problem
 
 pytestmark = pytest.mark.gpu
 

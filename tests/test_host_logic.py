@@ -1,18 +1,15 @@
 """CPU-side tests (no GPU): the DSL, the finite-difference machinery, the pattern recogniser,
 the NumPy interpreter for set-up operators, the host-side tabulation, and the C-ABI library's
 exported symbols. Golden values come from the reference (tests/golden, oracle/make_golden.py)."""
-import ctypes
 import os
 
 import numpy as np
 import pytest
 
 import devito_b200 as dv
-from devito_b200 import (Grid, Function, TimeFunction, Constant, Eq, Inc, Operator, solve,
-                         SubDimension, norm)
+from devito_b200 import Grid, Function, TimeFunction, Eq, Operator, solve
 from devito_b200.symbolics import fd_weights, fd_offsets
-from devito_b200.seismic import (demo_model, setup_geometry, AcousticWaveSolver,
-                                 AnisotropicWaveSolver, TimeAxis, RickerSource, Receiver)
+from devito_b200.seismic import (demo_model, setup_geometry, AcousticWaveSolver, AnisotropicWaveSolver)
 from helpers import load_golden, rel_linf
 
 

@@ -2,7 +2,6 @@
 oracle port — guards the argument marshalling of the `kind: "reference"` CPU baseline."""
 import os
 
-import numpy as np
 import pytest
 
 from oracle import oracle as O
