@@ -674,10 +674,13 @@ class Operator:
                     f"{' -- not recognised: ' + self._why_not if self._why_not else ''} */")
         p = self._plan
         entry = 'b2_iso_forward' if p['kind'] == 'iso' else 'b2_tti_forward'
-        return (f"/* Operator `{self.name}` -> libb200stencil.so::{entry} (sm_100a)\n"
+        head = (f"/* Operator `{self.name}` -> libb200stencil.so::{entry} (sm_100a)\n"
                 f"   space_order={p['so']} radius={p['R']} src={p['src'] and p['src'].name} "
                 f"rec={p['rec'] and p['rec'].name} rec_toff={p['rec_toff']}"
-                f"{' free_surface' if p.get('free_surface') else ''} */")
+                f"{' free_surface' if p.get('free_surface') else ''} */\n")
+        # like the reference, `str(op)` is C: here the adapter that `cinterface()` writes
+        from . import cinterface as ci
+        return head + ci.generate(p, self.name, distributed=p['grid'].distributor.is_parallel)[0]
 
     ccode = property(__str__)
 
