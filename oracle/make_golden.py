@@ -54,14 +54,14 @@ def kat2d():
          src=np.array(src.data[:, 0]))
 
 
-def acoustic(name, so, n, nbl, tn, preset='constant-isotropic', interpolation='linear', **kw):
+def acoustic(name, so, n, nbl, tn, preset='constant-isotropic', interpolation='linear', kernel='OT2', **kw):
     from devito import norm
     from examples.seismic import demo_model, setup_geometry
     from examples.seismic.acoustic import AcousticWaveSolver
     model = demo_model(preset, spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl, space_order=so,
                        dtype=np.float32, **kw)
     geometry = setup_geometry(model, tn, interpolation=interpolation)
-    solver = AcousticWaveSolver(model, geometry, space_order=so)
+    solver = AcousticWaveSolver(model, geometry, space_order=so, kernel=kernel)
     rec, u, _ = solver.forward()
     extra = {}
     if not model.vp.is_Constant:
@@ -70,7 +70,8 @@ def acoustic(name, so, n, nbl, tn, preset='constant-isotropic', interpolation='l
          damp=np.array(model.damp.data), src=np.array(geometry.src.data),
          src_coords=np.array(geometry.src.coordinates.data),
          rec_coords=np.array(geometry.rec.coordinates.data), rec=np.array(rec.data),
-         u=np.array(u.data), norm_rec=np.float32(norm(rec)), norm_u=np.float32(norm(u)), **extra)
+         u=np.array(u.data), norm_rec=np.float32(norm(rec)), norm_u=np.float32(norm(u)),
+         dt_run=np.float32(solver.dt), **extra)
 
 
 def kat3d_fs(interpolation, name):
@@ -158,7 +159,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'fs', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'fs' in which:
@@ -167,6 +168,10 @@ if __name__ == '__main__':
                  interpolation='sinc', fs=True)
         kat3d_fs('linear', 'kat3d_fs_linear')
         kat3d_fs('sinc', 'kat3d_fs_sinc')
+    if 'ot4' in which:
+        acoustic('iso3d_so8_ot4', so=8, n=20, nbl=8, tn=150.0, kernel='OT4')
+        acoustic('iso3d_so4_ot4_layers', so=4, n=20, nbl=8, tn=150.0, kernel='OT4',
+                 preset='layers-isotropic', nlayers=3)
     if 'iso8' in which:
         acoustic('iso3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'iso12' in which:

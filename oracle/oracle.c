@@ -128,7 +128,10 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                        int param_kind, const float *param, float vp, float dt, const int *lo,
                        const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
                        int rec_toff, int adjoint, float *grad, const int *galloc, int ghalo,
-                       const float *usave, int free_surface) {
+                       const float *usave, int free_surface, int ot4) {
+    /* ot4 != 0: the reference's 4th-order-in-time kernel (acoustic/operators.py:50-68, kernel='OT4'):
+     * H = lap(u) + dt^2/12 * lap( lap(u) / m ), with the inner Laplacian and 1/m sampled at the shifted
+     * point (devito/finite_differences/differentiable.py:442-449 `biharmonic`). 3-D, radius <= so/2. */
     /* free_surface != 0: the reference's `freesurface` (acoustic/operators.py:5-47) on the LAST
      * dimension: taps of the vertical derivative that fall above the surface, z - k < 0, read
      * sign(z-k) * u[|z-k|] (antisymmetric mirror; a tap landing exactly on z = 0 contributes 0), and
@@ -153,6 +156,13 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
     const float r3 = 1.0f / dt;
     const float r1s = 1.0f / (vp * vp);
     const int dir = adjoint ? -1 : 1;
+    float *W = NULL;                      /* OT4: lap(u)/m on the iteration box grown by R */
+    if (ot4) {
+        if (ndim != 3 || free_surface || 2 * R > so) return 2;
+        W = (float *)calloc(slot, sizeof(float));
+        if (!W) return 3;
+    }
+    const float ot4c = dt * dt / 12.0f;
     for (int time = adjoint ? time_M : time_m; adjoint ? time >= time_m : time <= time_M; time += dir) {
         const int t0 = ((time % tsize) + tsize) % tsize;
         const int t1 = (((time + dir) % tsize) + tsize) % tsize;
@@ -160,6 +170,22 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
         const float *u0 = u + (size_t)t0 * slot;
         const float *um = u + (size_t)t2 * slot;
         float *u1 = u + (size_t)t1 * slot;
+        if (ot4) {
+#pragma omp parallel for collapse(2) schedule(static)
+            for (int x = lo[0] - R; x <= hi[0] + R; ++x)
+                for (int y = lo[1] - R; y <= hi[1] + R; ++y)
+                    for (int z = lo[2] - R; z <= hi[2] + R; ++z) {
+                        const size_t i = IDX3(x + so, y + so, z + so);
+                        float l = (wx[0] + wy[0] + wz[0]) * u0[i];
+                        for (int k = 1; k <= R; ++k)
+                            l += wx[k] * (u0[i - k * sx] + u0[i + k * sx]) +
+                                 wy[k] * (u0[i - k * sy] + u0[i + k * sy]) + wz[k] * (u0[i - k] + u0[i + k]);
+                        float minv = vp * vp;
+                        if (param_kind == 1) minv = param[i] * param[i];
+                        else if (param_kind == 2) minv = 1.0f / param[i];
+                        W[i] = l * minv;
+                    }
+        }
         if (ndim == 3) {
 #pragma omp parallel for collapse(2) schedule(static)
             for (int x = lo[0]; x <= hi[0]; ++x)
@@ -167,6 +193,13 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                     for (int z = lo[2]; z <= hi[2]; ++z) {
                         const size_t i = IDX3(x + so, y + so, z + so);
                         float lap = (wx[0] + wy[0] + wz[0]) * u0[i];
+                        if (ot4) {
+                            float bl = (wx[0] + wy[0] + wz[0]) * W[i];
+                            for (int k = 1; k <= R; ++k)
+                                bl += wx[k] * (W[i - k * sx] + W[i + k * sx]) +
+                                      wy[k] * (W[i - k * sy] + W[i + k * sy]) + wz[k] * (W[i - k] + W[i + k]);
+                            lap += ot4c * bl;
+                        }
                         for (int k = 1; k <= R; ++k) {
                             float zlo = u0[i - k];
                             if (free_surface && z - k <= 0) zlo = (z - k < 0) ? -u0[i - z + (k - z)] : 0.0f;
@@ -224,6 +257,7 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
                     }
         }
     }
+    free(W);
     return 0;
 }
 

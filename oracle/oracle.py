@@ -38,7 +38,7 @@ def load(fast=False):
     fp, ip = POINTER(c_float), POINTER(c_int)
     L.oracle_iso_forward.argtypes = [c_int, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, c_int, fp,
                                      c_float, c_float, ip, ip, c_int, c_int, POINTER(OSparse),
-                                     POINTER(OSparse), c_int, c_int, fp, ip, c_int, fp, c_int]
+                                     POINTER(OSparse), c_int, c_int, fp, ip, c_int, fp, c_int, c_int]
     L.oracle_iso_forward.restype = c_int
     L.oracle_tti_forward.argtypes = [fp, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, fp, fp, fp,
                                      c_float, c_float, c_float, c_float, c_float, c_float, ip, ip,
@@ -76,7 +76,7 @@ def _sparse(data, gp, ws, r, keep):
 
 def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, param_kind=0,
                 src=None, rec=None, rec_toff=0, lo=None, hi=None, fast=False, adjoint=False,
-                grad=None, ghalo=0, usave=None, free_surface=False):
+                grad=None, ghalo=0, usave=None, free_surface=False, ot4=False):
     """grad (3-D, halo `ghalo`) / usave (nt, ...) enable the Gradient operator's imaging condition.
     u: (T, [nx+2so,] ny+2so, nz+2so) float32 C-contiguous, updated in place.
     w: list (per dim) of weights [0..R] incl. 1/h^2. src/rec: dict(data, gp, w, r)."""
@@ -97,7 +97,7 @@ def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, par
                               ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, rec_toff,
                               1 if adjoint else 0, _fp(grad),
                               _ip(galloc) if galloc is not None else None,
-                              ghalo, _fp(usave), 1 if free_surface else 0)
+                              ghalo, _fp(usave), 1 if free_surface else 0, 1 if ot4 else 0)
     assert rc == 0
     return u
 
