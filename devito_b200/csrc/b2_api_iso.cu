@@ -190,6 +190,12 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         if (!a->w[d]) { set_error("b2_iso_forward: weights for dim %d missing", d); return cleanup(B2_ERR_INVALID); }
         for (int i = 0; i <= a->radius; ++i) p.w[di][i] = a->w[d][i];
     }
+    p.ot4 = a->ot4 != 0;
+    if (p.ot4 && (a->halo || a->free_surface || a->grad)) {
+        set_error("b2_iso_forward: OT4 is not combined with halo exchange, a free surface or the imaging "
+                  "condition in this version");
+        return cleanup(B2_ERR_INVALID);
+    }
     if ((rc = iso_plan_init(p, a->kernel))) return cleanup(rc);
     if (a->free_surface && p.o[2] != so) {
         set_error("b2_iso_forward: a free surface needs the vertical iteration to start at 0");

@@ -19,6 +19,7 @@
 //                   u[t+1] with 16-byte coalesced stores. No tensor cores: the update is
 //                   HBM-bandwidth bound (16 B/point).
 #include "b2_iso.cuh"
+#include "b2_iso_point.cuh"
 #include "b2_ptx.cuh"
 #include <cstdlib>
 #include <algorithm>
@@ -28,86 +29,33 @@ namespace b2 {
 // ------------------------------------------------------------------------------------------
 // generic kernel
 // ------------------------------------------------------------------------------------------
-struct IsoGK {
-    const float *__restrict__ u0;
-    const float *__restrict__ um;
-    float *__restrict__ u1;
-    const float *__restrict__ damp;
-    const float *__restrict__ param;
-    long long sx, sy;
-    int n0, n1, n2;          // extents of this launch (dim0 count is xcount)
-    int o0, o1, o2;          // array index of first point (o0 already includes xlo)
-    int r0, r1, r2;          // radius per dim
-    int param_kind;
-    float m_dt2, inv_dt, inv_dt2;
-    float w[3][B2_MAX_RADIUS + 1];
-};
-
+// point forms (shared with the CPU emulation test): b2_iso_point.cuh
 __global__ void __launch_bounds__(256) k_iso_generic(IsoGK k) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (z >= k.n2 || y >= k.n1) return;
-    for (int x = blockIdx.z; x < k.n0; x += gridDim.z) {
-        const long long idx = (long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z);
-        const float c = k.u0[idx];
-        float acc = (k.w[0][0] + k.w[1][0] + k.w[2][0]) * c;
-        for (int i = 1; i <= k.r0; ++i)
-            acc += k.w[0][i] * (k.u0[idx - i * k.sx] + k.u0[idx + i * k.sx]);
-        for (int i = 1; i <= k.r1; ++i)
-            acc += k.w[1][i] * (k.u0[idx - i * k.sy] + k.u0[idx + i * k.sy]);
-        for (int i = 1; i <= k.r2; ++i)
-            acc += k.w[2][i] * (k.u0[idx - i] + k.u0[idx + i]);
-        float m_dt2 = k.m_dt2;
-        if (k.param_kind == B2_PARAM_VP) {
-            const float v = k.param[idx];
-            m_dt2 = k.inv_dt2 / (v * v);
-        } else if (k.param_kind == B2_PARAM_M) {
-            m_dt2 = k.param[idx] * k.inv_dt2;
-        }
-        const float d = k.damp ? k.damp[idx] * k.inv_dt : 0.f;
-        const float num = m_dt2 * (2.f * c - k.um[idx]) + d * c + acc;
-        k.u1[idx] = num / (m_dt2 + d);
-    }
+    for (int x = blockIdx.z; x < k.n0; x += gridDim.z) iso_point(k, x, y, z);
 }
 
-// Free surface on the low side of the last dimension (reference `freesurface`,
-// examples/seismic/acoustic/operators.py:5-47; generated form: `r1[z]*u[t0][..][4 + abs(z - 1)]`,
-// `u[t2][x][y][4] = 0`). The sweep kernels compute every row with the plain stencil; this kernel then
-// REDOES the rows z < radius, the only ones whose vertical taps reach above the surface, with the
-// mirrored taps  u[z - k] -> sign(z - k) * u[|z - k|]  (a tap landing on z = 0 contributes 0), and
-// clears the surface row. It touches radius/n2 of the grid (0.4 % at 1024^3, so = 8). The halo above
-// the surface is left alone: sinc sources/receivers deposit into / sample it in the reference too.
+// OT4 first pass over the box grown by the radius (n*/o* already describe the grown box)
+__global__ void __launch_bounds__(256) k_ot4_w(IsoGK k) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (z >= k.n2 || y >= k.n1) return;
+    for (int x = blockIdx.z; x < k.n0; x += gridDim.z) ot4_w_point(k, x, y, z);
+}
+
+// Free surface: the sweep kernels compute every row with the plain stencil; this kernel then REDOES
+// the rows z <= radius — the only ones with a vertical tap that reaches the surface (z - k == 0, which
+// contributes 0 in the reference, not u[0]: u[0] is non-zero right after a source deposited into the
+// surface row) or goes above it — and clears the surface row. It touches (radius+1)/n2 of the grid
+// (0.5 % at 1024^3, so = 8). The halo above the surface is left alone: sinc sources/receivers deposit
+// into / sample it in the reference too.
 __global__ void __launch_bounds__(256) k_iso_fs_fix(IsoGK k) {
-    const int z = threadIdx.x;                                   // 0 .. r2-1 (blockDim.x == 8)
+    const int z = threadIdx.x;                                   // 0 .. r2 (blockDim.x == 16 > B2_MAX_RADIUS)
     const int y = blockIdx.x * blockDim.y + threadIdx.y;
-    if (z >= k.r2 || y >= k.n1) return;
-    for (int x = blockIdx.y; x < k.n0; x += gridDim.y) {
-        const long long idx = (long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z);
-        if (z == 0) { k.u1[idx] = 0.f; continue; }
-        const float c = k.u0[idx];
-        float acc = (k.w[0][0] + k.w[1][0] + k.w[2][0]) * c;
-        for (int i = 1; i <= k.r0; ++i)
-            acc += k.w[0][i] * (k.u0[idx - i * k.sx] + k.u0[idx + i * k.sx]);
-        for (int i = 1; i <= k.r1; ++i)
-            acc += k.w[1][i] * (k.u0[idx - i * k.sy] + k.u0[idx + i * k.sy]);
-        for (int i = 1; i <= k.r2; ++i) {
-            float lo;
-            if (z - i > 0) lo = k.u0[idx - i];
-            else if (z - i < 0) lo = -k.u0[idx - z + (i - z)];
-            else lo = 0.f;
-            acc += k.w[2][i] * (lo + k.u0[idx + i]);
-        }
-        float m_dt2 = k.m_dt2;
-        if (k.param_kind == B2_PARAM_VP) {
-            const float v = k.param[idx];
-            m_dt2 = k.inv_dt2 / (v * v);
-        } else if (k.param_kind == B2_PARAM_M) {
-            m_dt2 = k.param[idx] * k.inv_dt2;
-        }
-        const float d = k.damp ? k.damp[idx] * k.inv_dt : 0.f;
-        const float num = m_dt2 * (2.f * c - k.um[idx]) + d * c + acc;
-        k.u1[idx] = num / (m_dt2 + d);
-    }
+    if (z > k.r2 || y >= k.n1) return;
+    for (int x = blockIdx.y; x < k.n0; x += gridDim.y) iso_fs_point(k, x, y, z);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -434,8 +382,8 @@ static int env_int(const char *name, int dflt) {
 }
 
 // scratch for the coefficient arrays, cached across calls (re-allocated when the size changes)
-static float *g_coef[2] = {nullptr, nullptr};
-static size_t g_coef_elems[2] = {0, 0};
+static float *g_coef[3] = {nullptr, nullptr, nullptr};     // A, B (TMA path), W (OT4)
+static size_t g_coef_elems[3] = {0, 0, 0};
 
 static int coef_buffer(int which, size_t elems, float **out) {
     if (g_coef_elems[which] != elems) {
@@ -493,6 +441,19 @@ int iso_plan_init(IsoPlan &p, int kernel) {
     // tiny grids gain nothing from the pipelined kernel
     ok = ok && (p.n[1] >= 8 && p.n[2] >= 16);
     if (kernel == 1) ok = false;
+    if (p.ot4) {
+        // two-pass generic path: W = lap(u)/m over the box grown by R, then the update with lap(W)
+        if (kernel == 2) { set_error("iso: the OT4 kernel has no TMA variant yet"); return B2_ERR_INVALID; }
+        for (int d = 0; d < 3; ++d) {
+            const int rd = p.radius[d];
+            if (p.o[d] - 2 * rd < 0 || p.o[d] + p.n[d] - 1 + 2 * rd >= p.a[d]) {
+                set_error("iso: OT4 needs a halo of 2*radius = %d points on dim %d", 2 * rd, d);
+                return B2_ERR_INVALID;
+            }
+        }
+        p.use_tma = false;
+        return coef_buffer(2, p.slot_elems, &p.ot4W);
+    }
     if (kernel == 2 && !ok) {
         set_error("iso: TMA kernel forced but layout does not qualify (radius=%d a2=%d o2=%d)", R,
                   p.a[2], p.o[2]);
@@ -591,6 +552,9 @@ static IsoGK generic_args(const IsoPlan &p, int slot0, int slotm, int slot1, int
     k.inv_dt2 = 1.0f / (p.dt * p.dt);
     k.m_dt2 = (1.0f / (p.vp * p.vp)) * k.inv_dt2;
     memcpy(k.w, p.w, sizeof(k.w));
+    k.W = nullptr;
+    k.ot4c = p.dt * p.dt / 12.0f;
+    k.vp2 = p.vp * p.vp;
     return k;
 }
 
@@ -601,8 +565,8 @@ int iso_fs_fix(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int x
         return B2_ERR_INVALID;
     }
     IsoGK k = generic_args(p, slot0, slotm, slot1, xlo, xcount);
-    dim3 block(8, 32, 1);
-    dim3 grid((k.n1 + 31) / 32, (unsigned)std::min(xcount, 65535), 1);
+    dim3 block(16, 16, 1);
+    dim3 grid((k.n1 + 15) / 16, (unsigned)std::min(xcount, 65535), 1);
     k_iso_fs_fix<<<grid, block, 0, stream()>>>(k);
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
@@ -621,6 +585,18 @@ int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xco
         return B2_ERR_INVALID;
     }
     IsoGK k = generic_args(p, slot0, slotm, slot1, xlo, xcount);
+    if (p.ot4) {
+        IsoGK g = k;                       // first pass on the box grown by the radius
+        g.W = p.ot4W;
+        g.o0 -= g.r0; g.o1 -= g.r1; g.o2 -= g.r2;
+        g.n0 += 2 * g.r0; g.n1 += 2 * g.r1; g.n2 += 2 * g.r2;
+        dim3 blk(64, 4, 1);
+        dim3 grd((g.n2 + 63) / 64, (g.n1 + 3) / 4, (unsigned)std::min(g.n0, 65535));
+        k_ot4_w<<<grd, blk, 0, stream()>>>(g);
+        count_launch();
+        B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+        k.W = p.ot4W;
+    }
     dim3 block(64, 4, 1);
     dim3 grid((k.n2 + 63) / 64, (k.n1 + 3) / 4, (unsigned)std::min(xcount, 65535));
     timing_begin();

@@ -25,6 +25,9 @@ struct IsoPlan {
     CUtensorMap tm_uh, tm_uc, tm_damp, tm_par;   // tm_damp/tm_par map coefA/coefB
     float *coefA = nullptr, *coefB = nullptr;    // tabulated update coefficients (library scratch)
     int lx = 0;
+    // OT4 (b2_iso_args.ot4): generic two-pass path, W = lap(u)/m in library scratch
+    bool ot4 = false;
+    float *ot4W = nullptr;
 };
 
 // Prepare the plan (decides generic vs TMA kernel, encodes tensor maps). `kernel`: 0 auto,

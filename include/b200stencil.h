@@ -132,6 +132,11 @@ struct b2_iso_args {
      * above the surface read sign(z-k) * u[|z-k|] (antisymmetric mirror), and u[t+1] is cleared on the
      * surface row z = 0 before the source is injected. Needs z_m (y_m in 2-D) == 0.               */
     int free_surface;
+    /* != 0: the reference's 4th-order-in-time kernel (kernel='OT4', acoustic/operators.py:50-68):
+     * the Laplacian is replaced by  lap(u) + dt^2/12 * lap( lap(u) / m ).  3-D/2-D, needs
+     * space_order >= 2*radius; not combined with halo exchange, free surface or the imaging condition
+     * in this version (-> 210).                                                                   */
+    int ot4;
 };
 int b2_iso_forward(const struct b2_iso_args *a);
 

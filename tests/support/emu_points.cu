@@ -1,0 +1,62 @@
+// CPU emulation of the one-thread-per-point isotropic kernels — TEST INFRASTRUCTURE ONLY.
+//
+// devito_b200/csrc/b2_iso_point.cuh holds the bodies of k_iso_generic / k_ot4_w / k_iso_fs_fix as
+// __host__ __device__ functions. This file loops them over the grid on the CPU (compiled by nvcc as
+// host code, no GPU needed) so that tests/test_zz_emulation.py can compare exactly the code the GPU
+// runs — index arithmetic, mirrored free-surface taps, the OT4 composition — with the oracle.
+// It mirrors the launch sequence of b2::iso_step / b2::iso_fs_fix (b2_iso.cu).
+#include "b2_iso_point.cuh"
+
+using namespace b2;
+
+extern "C" int emu_iso_step(float *u, const int *alloc /* 3 */, int so, int R, int ndim, const float *w0,
+                            const float *w1, const float *w2, const float *damp, int param_kind,
+                            const float *param, float vp, float dt, const int *lo, const int *hi, int t0,
+                            int t2, int t1, int free_surface, int ot4, float *W) {
+    IsoGK k;
+    const size_t slot = (size_t)alloc[0] * alloc[1] * alloc[2];
+    k.u0 = u + (size_t)t0 * slot;
+    k.um = u + (size_t)t2 * slot;
+    k.u1 = u + (size_t)t1 * slot;
+    k.damp = damp;
+    k.param = param;
+    k.sy = alloc[2];
+    k.sx = (long long)alloc[1] * alloc[2];
+    for (int d = 0; d < 3; ++d) {
+        const int n = hi[d] - lo[d] + 1;
+        const int o = (ndim == 2 && d == 0) ? 0 : lo[d] + so;
+        const int r = (ndim == 2 && d == 0) ? 0 : R;
+        if (d == 0) { k.n0 = n; k.o0 = o; k.r0 = r; }
+        if (d == 1) { k.n1 = n; k.o1 = o; k.r1 = r; }
+        if (d == 2) { k.n2 = n; k.o2 = o; k.r2 = r; }
+    }
+    k.param_kind = param_kind;
+    k.inv_dt = 1.0f / dt;
+    k.inv_dt2 = 1.0f / (dt * dt);
+    k.m_dt2 = (1.0f / (vp * vp)) * k.inv_dt2;
+    memset(k.w, 0, sizeof(k.w));
+    const float *ws[3] = {w0, w1, w2};
+    for (int d = 0; d < 3; ++d)
+        if (ws[d]) for (int i = 0; i <= R; ++i) k.w[d][i] = ws[d][i];
+    k.W = nullptr;
+    k.ot4c = dt * dt / 12.0f;
+    k.vp2 = vp * vp;
+    if (ot4) {
+        IsoGK g = k;
+        g.W = W;
+        g.o0 -= g.r0; g.o1 -= g.r1; g.o2 -= g.r2;
+        g.n0 += 2 * g.r0; g.n1 += 2 * g.r1; g.n2 += 2 * g.r2;
+        for (int x = 0; x < g.n0; ++x)
+            for (int y = 0; y < g.n1; ++y)
+                for (int z = 0; z < g.n2; ++z) ot4_w_point(g, x, y, z);
+        k.W = W;
+    }
+    for (int x = 0; x < k.n0; ++x)
+        for (int y = 0; y < k.n1; ++y)
+            for (int z = 0; z < k.n2; ++z) iso_point(k, x, y, z);
+    if (free_surface)
+        for (int x = 0; x < k.n0; ++x)
+            for (int y = 0; y < k.n1; ++y)
+                for (int z = 0; z <= k.r2; ++z) iso_fs_point(k, x, y, z);
+    return 0;
+}

@@ -1,0 +1,106 @@
+"""The one-thread-per-point CUDA kernels, executed on the CPU.
+
+`devito_b200/csrc/b2_iso_point.cuh` holds the bodies of `k_iso_generic`, `k_ot4_w` and `k_iso_fs_fix`
+as `__host__ __device__` functions; tests/support/emu_points.cu loops them over the grid as host code
+(nvcc, no GPU). Comparing that with the oracle checks the very code the GPU runs — index arithmetic,
+mirrored free-surface taps, the OT4 two-pass composition — before any GPU time is spent. It does not
+cover launch geometry or the tiled TMA kernels; those are GPU tests."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from helpers import rel_linf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(shutil.which('nvcc') is None, reason="nvcc not available")
+
+
+@pytest.fixture(scope='module')
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp('emu') / 'libemu_points.so'
+    cmd = ['nvcc', '-O1', '-shared', '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'),
+           '-I', os.path.join(ROOT, 'devito_b200', 'csrc'), os.path.join(ROOT, 'tests', 'support', 'emu_points.cu'),
+           '-o', str(out)]
+    env = dict(os.environ)
+    env.pop('CC', None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    lib = ctypes.CDLL(str(out))
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+    lib.emu_iso_step.argtypes = [fp, ip, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, fp, fp, fp, ctypes.c_int,
+                                 fp, ctypes.c_float, ctypes.c_float, ip, ip, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
+    lib.emu_iso_step.restype = ctypes.c_int
+    return lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def _initial(shape, so, seed):
+    """Two smooth, non-trivial time levels (domain only; halo zero)."""
+    rng = np.random.default_rng(seed)
+    u = np.zeros((3,) + tuple(s + 2 * so for s in shape), dtype=np.float32)
+    dom = (slice(so, -so),) * len(shape)
+    grids = np.meshgrid(*[np.linspace(0, 1, s) for s in shape], indexing='ij')
+    base = sum(np.sin((3 + i) * g * np.pi + rng.uniform(0, 1)) for i, g in enumerate(grids))
+    u[(0,) + dom] = base
+    u[(1,) + dom] = 0.9 * base + 0.05 * rng.standard_normal(shape)
+    return u
+
+
+def _run_emu(emu, u, so, w, dt, nsteps, damp, vp, param, param_kind, fs, ot4):
+    nd = u.ndim - 1
+    alloc3 = np.array(((1,) if nd == 2 else ()) + u.shape[1:], dtype=np.int32)
+    lo = np.array(((0,) if nd == 2 else ()) + (0,) * nd, dtype=np.int32)
+    hi = np.array(((0,) if nd == 2 else ()) + tuple(s - 2 * so - 1 for s in u.shape[1:]), dtype=np.int32)
+    R = len(w[0]) - 1
+    ws = [np.ascontiguousarray(x, dtype=np.float32) for x in w]
+    if nd == 2:
+        ws = [None] + ws
+    W = np.zeros(int(np.prod(alloc3)), dtype=np.float32) if ot4 else None
+    for time in range(1, nsteps + 1):
+        rc = emu.emu_iso_step(_fp(u), _ip(alloc3), so, R, nd, _fp(ws[0]), _fp(ws[1]), _fp(ws[2]), _fp(damp),
+                              param_kind, _fp(param), vp, dt, _ip(lo), _ip(hi), time % 3, (time - 1) % 3,
+                              (time + 1) % 3, 1 if fs else 0, 1 if ot4 else 0, _fp(W))
+        assert rc == 0
+    return u
+
+
+@pytest.mark.parametrize('case', ['plain', 'plain_vp_array', 'free_surface', 'free_surface_so4', 'ot4',
+                                  'ot4_vp_array', 'plain_2d', 'free_surface_2d'])
+def test_point_kernels_match_the_oracle(emu, case):
+    fs = case.startswith('free_surface')
+    ot4 = case.startswith('ot4')
+    nd = 2 if case.endswith('2d') else 3
+    so = 4 if case.endswith('so4') else 8
+    shape = (22, 19, 17) if nd == 3 else (33, 29)
+    h, vp, nsteps = 10.0, 1.5, 7
+    dt = float(O.critical_dt(so, nd, h, 3.0))
+    w = [O.fd2_weights(so, h)] * nd
+    u_ref = _initial(shape, so, seed=3)
+    u_emu = u_ref.copy()
+    rng = np.random.default_rng(11)
+    damp = np.pad((0.02 * rng.uniform(0, 1, shape)).astype(np.float32), so)
+    param, kind = None, 0
+    if case.endswith('vp_array'):
+        param = np.pad(rng.uniform(1.5, 3.0, shape).astype(np.float32), so, mode='edge')
+        kind = 1
+    O.iso_forward(u_ref, so, w, dt, 1, nsteps, damp=damp, vp=vp, param=param, param_kind=kind,
+                  free_surface=fs, ot4=ot4)
+    _run_emu(emu, u_emu, so, w, dt, nsteps, damp, vp, param, kind, fs, ot4)
+    dom = (slice(None),) + (slice(so, -so),) * nd
+    assert np.abs(u_ref[dom]).max() > 0.1
+    assert rel_linf(u_emu[dom], u_ref[dom]) < 1e-5
+    if fs:
+        assert not u_emu[dom][(nsteps + 1) % 3][..., 0].any()
