@@ -219,6 +219,8 @@ def _iso_body(plan, distributed):
     L.append(f"  a.adjoint = {1 if plan.get('adjoint') else 0};")
     if plan.get('free_surface'):
         L.append("  a.free_surface = 1;")
+    if plan.get('ot4'):
+        L.append("  a.ot4 = 1;")
     if plan.get('grad') is not None:
         L.append(f"  a.grad = (struct b2_dataobj *){plan['grad'].name}_vec;")
         L.append(f"  a.usave = (struct b2_dataobj *){plan['usave'].name}_vec;")

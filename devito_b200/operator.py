@@ -342,6 +342,11 @@ class Operator:
                     star.add((0, tuple(o)))
         dirn = self._dirn
         if set(keyed) != star | {(-dirn, zero)}:
+            if set(keyed) > star | {(-dirn, zero)}:
+                plan = self._recognise_ot4(u, keyed, star, R)
+                funcs, consts, syms = self._leaves(keyed.values())
+                self._attach_sparse(plan, injs, itps, [u], funcs, consts, syms, plan['m_role'])
+                return plan
             raise _Unrecognised("stencil support is not the isotropic star")
         funcs, consts, syms = self._leaves(keyed.values())
         for a in funcs:
@@ -391,6 +396,104 @@ class Operator:
                 'dt': dtsym, 'src': None, 'rec': None, 'rec_toff': 0, 'adjoint': dirn == -1}
         self._attach_sparse(plan, injs, itps, [u], funcs, consts, syms, m_role)
         return plan
+
+    def _recognise_ot4(self, u, keyed, star, R):
+        """The reference's 4th-order-in-time acoustic update (examples/seismic/acoustic/operators.py:
+        50-68, kernel='OT4'):  H = lap(u) + dt^2/12 * lap( lap(u)/m ), the inner Laplacian and 1/m
+        sampled at the shifted point. The candidate roles of the parameter leaves are tried in turn;
+        each is checked by comparing EVERY stencil coefficient with the prediction at random parameter
+        values that also carry a random spatial gradient (so the sampling position of 1/m is checked)."""
+        grid = u.grid
+        nd = grid.dim
+        dirn = self._dirn
+        zero = (0,) * nd
+        if 2 * R > u.space_order:
+            raise _Unrecognised("OT4 needs a halo of 2*radius points")
+        funcs, consts, syms = self._leaves(keyed.values())
+        for a in funcs:
+            if getattr(a.function, 'is_TimeFunction', False) or _space_offsets(a, None) is None:
+                raise _Unrecognised("non-affine parameter access")
+        dtsym = grid.stepping_dim.spacing
+        hs = self._spacing_values(grid)
+        w = [second_derivative_weights(u.space_order, h) for h in hs]
+        spv = {sp.name: float(v) for sp, v in grid.spacing_map.items()}
+        fobjs = [a.function for a in funcs]
+        m_cands = [('vp_f', f) for f in fobjs] + [('m_f', f) for f in fobjs] + \
+                  [('vp_c', c) for c in consts] + [('m_c', c) for c in consts] + [('one', None)]
+        d_cands = [None] + [('damp_f', f) for f in fobjs]
+
+        def unit(d, o):
+            v = [0] * nd
+            v[d] = o
+            return tuple(v)
+
+        def mismatch(m_role, d_role, seed):
+            rng = np.random.default_rng(seed)
+            base = {id(f): rng.uniform(0.6, 1.6) for f in fobjs}
+            gradv = {id(f): rng.uniform(-0.02, 0.02, size=nd) for f in fobjs}
+            cval = {id(c): rng.uniform(0.6, 1.6) for c in consts}
+            dt = rng.uniform(0.5, 2.0)
+
+            def fval(f, off):
+                return float(base[id(f)] + np.dot(gradv[id(f)], off))
+
+            def leaf(n):
+                if n.is_Access:
+                    return fval(n.function, _space_offsets(n, None)[1])
+                if n.is_Constant:
+                    return cval[id(n)]
+                if n.name == dtsym.name:
+                    return dt
+                if n.name in spv:
+                    return spv[n.name]
+                raise _Unrecognised(f"unknown symbol {n.name} in the update")
+
+            def m_at(off):
+                kind, obj = m_role
+                if kind == 'vp_f':
+                    return 1.0 / fval(obj, off) ** 2
+                if kind == 'm_f':
+                    return fval(obj, off)
+                if kind == 'vp_c':
+                    return 1.0 / cval[id(obj)] ** 2
+                if kind == 'm_c':
+                    return cval[id(obj)]
+                return 1.0
+            dval = fval(d_role[1], zero) if d_role is not None else 0.0
+            m0 = m_at(zero)
+            den = m0 / dt ** 2 + dval / dt
+            lap = {zero: sum(wd[0] for wd in w)}
+            for d in range(nd):
+                for k in range(1, R + 1):
+                    for sgn in (-k, k):
+                        lap[unit(d, sgn)] = w[d][k]
+            H = dict(lap)
+            for q, wq in lap.items():                       # outer Laplacian tap at q
+                for o, wo in lap.items():                   # inner Laplacian tap about q
+                    key = tuple(a + b for a, b in zip(q, o))
+                    H[key] = H.get(key, 0.0) + dt ** 2 / 12.0 * wq / m_at(q) * wo
+            pred = {(0, k): v / den for k, v in H.items()}
+            pred[(0, zero)] += (2 * m0 / dt ** 2 + dval / dt) / den
+            pred[(-dirn, zero)] = -m0 / dt ** 2 / den
+            for k in set(pred) | set(keyed):
+                got = eval_scalar(keyed[k], leaf) if k in keyed else 0.0
+                want = pred.get(k, 0.0)
+                if abs(got - want) > 1e-8 * max(1.0, abs(want)):
+                    return f"coefficient mismatch at {k}: {got} vs {want}"
+            return None
+
+        why = "no parameter leaves"
+        for m_role in m_cands:
+            for d_role in d_cands:
+                if d_role is not None and m_role[1] is d_role[1]:
+                    continue
+                why = mismatch(m_role, d_role, 2024) or mismatch(m_role, d_role, 4048)
+                if why is None:
+                    return {'kind': 'iso', 'u': u, 'grid': grid, 'so': u.space_order, 'R': R, 'w': w,
+                            'm_role': m_role, 'damp': d_role[1] if d_role is not None else None,
+                            'dt': dtsym, 'src': None, 'rec': None, 'rec_toff': 0, 'adjoint': dirn == -1,
+                            'ot4': True}
+        raise _Unrecognised(f"not the OT4 acoustic update ({why})")
 
     @staticmethod
     def _role_value(role, vals):
@@ -677,7 +780,7 @@ class Operator:
         head = (f"/* Operator `{self.name}` -> libb200stencil.so::{entry} (sm_100a)\n"
                 f"   space_order={p['so']} radius={p['R']} src={p['src'] and p['src'].name} "
                 f"rec={p['rec'] and p['rec'].name} rec_toff={p['rec_toff']}"
-                f"{' free_surface' if p.get('free_surface') else ''} */\n")
+                f"{' free_surface' if p.get('free_surface') else ''}{' OT4' if p.get('ot4') else ''} */\n")
         # like the reference, `str(op)` is C: here the adapter that `cinterface()` writes
         from . import cinterface as ci
         return head + ci.generate(p, self.name, distributed=p['grid'].distributor.is_parallel)[0]
@@ -925,6 +1028,9 @@ class Operator:
             lo.append(int(a))
             hi.append(int(b))
         args['lo'], args['hi'] = lo, hi
+        if p.get('ot4') and (grid.distributor.is_parallel or p.get('free_surface') or p.get('grad') is not None):
+            raise InvalidArgument("the OT4 kernel is not yet combined with domain decomposition, a free "
+                                  "surface or the imaging condition")
         if p.get('free_surface') and lo[-1] != 0:
             raise InvalidArgument("a free-surface operator must iterate from the surface row (lower bound 0 "
                                   "on the last dimension)")
@@ -1140,6 +1246,7 @@ class Operator:
         a.timers = ctypes.pointer(timers)
         a.adjoint = 1 if p.get('adjoint') else 0
         a.free_surface = 1 if p.get('free_surface') else 0
+        a.ot4 = 1 if p.get('ot4') else 0
         if args.get('grad') is not None:
             a.grad = self._field_obj(args['grad'], dev, res, hold, written=True).ptr
             a.usave = self._field_obj(args['usave'], dev, res, hold).ptr

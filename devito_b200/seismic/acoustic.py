@@ -3,17 +3,26 @@ wavesolver.py:11-156): forward and adjoint operators (gradient/Born are SURVEY Â
 from .. import Eq, FreeSurface, Inc, Function, Operator, TimeFunction, solve
 from ..tools import memoized_meth
 
-__all__ = ['iso_stencil', 'ForwardOperator', 'AdjointOperator', 'GradientOperator', 'AcousticWaveSolver']
+__all__ = ['laplacian', 'iso_stencil', 'ForwardOperator', 'AdjointOperator', 'GradientOperator', 'AcousticWaveSolver']
+
+
+def laplacian(field, model, kernel):
+    """Spatial operator (operators.py:50-68): for the 4th-order-in-time scheme the 4th time derivative
+    is traded for a double Laplacian, H = laplace + s**2/12 * laplace(1/m * laplace)."""
+    if kernel not in ('OT2', 'OT4'):
+        raise ValueError("Unrecognized kernel")
+    s = model.grid.time_dim.spacing
+    biharmonic = field.biharmonic(1 / model.m) if kernel == 'OT4' else 0
+    return field.laplace + s ** 2 / 12 * biharmonic
 
 
 def iso_stencil(field, model, kernel='OT2', **kwargs):
-    """u.dt2 * m - laplace(u) + damp * u.dt = 0 solved for u.forward (operators.py:71-107)."""
-    if kernel != 'OT2':
-        raise NotImplementedError("only the OT2 kernel is on this backend's path")
+    """u.dt2 * m - H(u) + damp * u.dt = 0 solved for u.forward (operators.py:71-107)."""
     forward = kwargs.get('forward', True)
     unext = field.forward if forward else field.backward
     udt = field.dt if forward else field.dt.T
-    eq_time = solve(model.m * field.dt2 - field.laplace - kwargs.get('q', 0) + model.damp * udt, unext)
+    lap = laplacian(field, model, kernel)
+    eq_time = solve(model.m * field.dt2 - lap - kwargs.get('q', 0) + model.damp * udt, unext)
     update = Eq(unext, eq_time, subdomain=model.grid.subdomains['physdomain'])
     if model.fs:
         # operators.py:105-106 `freesurface(model, Eq(unext, eq_time))`: the top rows get the same
@@ -79,6 +88,9 @@ class AcousticWaveSolver:
 
     @property
     def dt(self):
+        # the 4th-order scheme is stable with a sqrt(3) = 1.73 larger step (wavesolver.py:39-44)
+        if self.kernel == 'OT4':
+            return self.model.dtype(1.73 * self.model.critical_dt)
         return self.model.critical_dt
 
     @memoized_meth

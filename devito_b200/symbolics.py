@@ -208,6 +208,15 @@ class Expr:
     def laplacian(self, **kwargs):
         return self.laplace
 
+    def biharmonic(self, weight=1):
+        """Weighted biharmonic operator `laplace(weight * laplace(self))`
+        (devito/finite_differences/differentiable.py:442-449)."""
+        inner = self.laplace * weight
+        out = Number(0)
+        for d in self._space_dims:
+            out = out + Derivative(inner, (d, 2))
+        return out
+
 
 def _sub_key(k):
     try:
