@@ -105,6 +105,25 @@ def adjoint(name, so, n, nbl, tn):
          src=np.array(geometry.src.data), norm_v=np.float32(norm(v)))
 
 
+def born(name, so, n, nbl, tn):
+    """Linearised modelling `solver.jacobian(dm)` (acoustic/wavesolver.py:216-254) with a smooth blob
+    as model perturbation."""
+    from examples.seismic import demo_model, setup_geometry
+    from examples.seismic.acoustic import AcousticWaveSolver
+    model = demo_model('layers-isotropic', spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl, space_order=so,
+                       dtype=np.float32, nlayers=2)
+    geometry = setup_geometry(model, tn)
+    solver = AcousticWaveSolver(model, geometry, space_order=so)
+    N = n + 2 * nbl
+    ax = np.arange(N, dtype=np.float64)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing='ij')
+    c = (N - 1) / 2.0
+    dm = (0.05 * np.exp(-((X - c) ** 2 + (Y - c) ** 2 + (Z - c - 2) ** 2) / (2 * 4.0 ** 2))).astype(np.float32)
+    rec, u, U, _ = solver.jacobian(dm)
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(model.critical_dt), nt=geometry.nt,
+         vp=np.array(model.vp.data), dm=dm, rec=np.array(rec.data), u=np.array(u.data), U=np.array(U.data))
+
+
 def gradient(name, so, n, nbl, tn):
     """Forward with the saved wavefield, then the Gradient operator (acoustic/operators.py:190-232,
     wavesolver.py:158-230): adjoint propagation of the data + imaging condition."""
@@ -159,7 +178,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'born', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'fs' in which:
@@ -172,6 +191,8 @@ if __name__ == '__main__':
         acoustic('iso3d_so8_ot4', so=8, n=20, nbl=8, tn=150.0, kernel='OT4')
         acoustic('iso3d_so4_ot4_layers', so=4, n=20, nbl=8, tn=150.0, kernel='OT4',
                  preset='layers-isotropic', nlayers=3)
+    if 'born' in which:
+        born('born3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'iso8' in which:
         acoustic('iso3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'iso12' in which:

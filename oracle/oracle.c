@@ -262,6 +262,68 @@ int oracle_iso_forward(int ndim, float *u, int tsize, const int *alloc, int so, 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Linearised (Born) modelling: the reference's `Born` operator, examples/seismic/acoustic/
+ * operators.py:235-277. Per time step, in the order of its equation list:
+ *     u[t+1]  = update(u)                       (eqn1)
+ *     u[t+1] += inject(src[time])               (source)
+ *     U[t+1]  = update(U) with the extra source q = -dm * u.dt2 in the numerator, where
+ *               u.dt2 = (u[t+1] - 2 u[t] + u[t-1]) / dt^2 uses the u[t+1] just computed (eqn2)
+ *     rec[time] = interpolate(U[t])             (receivers)
+ * 3-D, OT2, no free surface. `dm` has its own halo width (the reference builds it with
+ * space_order 0).
+ * ---------------------------------------------------------------------------------------- */
+int oracle_born_forward(float *u, float *U, int tsize, const int *alloc, int so, int radius,
+                        const float *wx, const float *wy, const float *wz, const float *damp,
+                        int param_kind, const float *param, float vp, float dt, const int *lo,
+                        const int *hi, int time_m, int time_M, osparse *src, osparse *rec,
+                        const float *dm, const int *dmalloc, int dmhalo) {
+    const int R = radius;
+    const size_t sy = (size_t)alloc[2], sx = (size_t)alloc[1] * alloc[2];
+    const size_t slot = (size_t)alloc[0] * sx;
+    const size_t dsy = (size_t)dmalloc[2], dsx = (size_t)dmalloc[1] * dmalloc[2];
+    const float r2 = 1.0f / (dt * dt);
+    const float r3 = 1.0f / dt;
+    const float r1s = 1.0f / (vp * vp);
+    for (int time = time_m; time <= time_M; ++time) {
+        const int t0 = ((time % tsize) + tsize) % tsize;
+        const int t1 = (((time + 1) % tsize) + tsize) % tsize;
+        const int t2 = (((time - 1) % tsize) + tsize) % tsize;
+        for (int pass = 0; pass < 2; ++pass) {
+            float *f = pass == 0 ? u : U;
+            const float *f0 = f + (size_t)t0 * slot, *fm = f + (size_t)t2 * slot;
+            float *f1 = f + (size_t)t1 * slot;
+            const float *u0 = u + (size_t)t0 * slot, *um = u + (size_t)t2 * slot, *u1 = u + (size_t)t1 * slot;
+#pragma omp parallel for collapse(2) schedule(static)
+            for (int x = lo[0]; x <= hi[0]; ++x)
+                for (int y = lo[1]; y <= hi[1]; ++y)
+                    for (int z = lo[2]; z <= hi[2]; ++z) {
+                        const size_t i = IDX3(x + so, y + so, z + so);
+                        float lap = (wx[0] + wy[0] + wz[0]) * f0[i];
+                        for (int k = 1; k <= R; ++k)
+                            lap += wx[k] * (f0[i - k * sx] + f0[i + k * sx]) +
+                                   wy[k] * (f0[i - k * sy] + f0[i + k * sy]) +
+                                   wz[k] * (f0[i - k] + f0[i + k]);
+                        float r1 = r1s;
+                        if (param_kind == 1) r1 = 1.0f / (param[i] * param[i]);
+                        else if (param_kind == 2) r1 = param[i];
+                        const float d = damp ? damp[i] : 0.0f;
+                        float q = 0.0f;
+                        if (pass == 1) {
+                            const size_t j = (size_t)(x + dmhalo) * dsx + (size_t)(y + dmhalo) * dsy + (z + dmhalo);
+                            q = -dm[j] * (r2 * u1[i] - 2.0f * r2 * u0[i] + r2 * um[i]);
+                        }
+                        f1[i] = (-r1 * (-2.0f * r2 * f0[i] + r2 * fm[i]) + r3 * d * f0[i] + lap + q) /
+                                (r1 * r2 + r3 * d);
+                    }
+            if (pass == 0)
+                inject(src, 3, f1, NULL, sx, sy, so, lo, hi, time, param_kind, param, vp, dt);
+        }
+        interp(rec, 3, U + (size_t)t0 * slot, NULL, sx, sy, so, lo, hi, time);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * TTI centred forward, scalar parameters, 3-D.  w2[d][0..R] second-derivative weights,
  * w1[d][0..R-1] half-node first-derivative weights (offsets -R/2+1..R/2 about x+h/2).
  * Follows the generated `ForwardTTI`: first the rotated first derivatives Gz(u), Gz(v) on

@@ -40,6 +40,10 @@ def load(fast=False):
                                      c_float, c_float, ip, ip, c_int, c_int, POINTER(OSparse),
                                      POINTER(OSparse), c_int, c_int, fp, ip, c_int, fp, c_int, c_int]
     L.oracle_iso_forward.restype = c_int
+    L.oracle_born_forward.argtypes = [fp, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, c_int, fp, c_float,
+                                      c_float, ip, ip, c_int, c_int, POINTER(OSparse), POINTER(OSparse),
+                                      fp, ip, c_int]
+    L.oracle_born_forward.restype = c_int
     L.oracle_tti_forward.argtypes = [fp, fp, c_int, ip, c_int, c_int, fp, fp, fp, fp, fp, fp, fp,
                                      c_float, c_float, c_float, c_float, c_float, c_float, ip, ip,
                                      c_int, c_int, POINTER(OSparse), POINTER(OSparse), c_int,
@@ -100,6 +104,29 @@ def iso_forward(u, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, par
                               ghalo, _fp(usave), 1 if free_surface else 0, 1 if ot4 else 0)
     assert rc == 0
     return u
+
+
+def born_forward(u, U, dm, so, w, dt, time_m, time_M, damp=None, vp=1.5, param=None, param_kind=0,
+                 src=None, rec=None, dmhalo=0, fast=False):
+    """The reference's `Born` operator (examples/seismic/acoustic/operators.py:235-277): u driven by
+    `src`, the linearised field U driven by -dm * u.dt2, `rec` sampled from U. 3-D."""
+    L = load(fast)
+    R = len(w[0]) - 1
+    alloc = np.array(u.shape[1:], dtype=np.int32)
+    lo = np.array([0] * 3, dtype=np.int32)
+    hi = np.array([s - 2 * so - 1 for s in u.shape[1:]], dtype=np.int32)
+    wa = [np.ascontiguousarray(x, dtype=np.float32) for x in w]
+    keep = []
+    s = _sparse(src['data'], src['gp'], src['w'], src['r'], keep) if src else None
+    r = _sparse(rec['data'], rec['gp'], rec['w'], rec['r'], keep) if rec else None
+    dm = np.ascontiguousarray(dm, dtype=np.float32)
+    dmalloc = np.array(dm.shape, dtype=np.int32)
+    rc = L.oracle_born_forward(_fp(u), _fp(U), u.shape[0], _ip(alloc), so, R, _fp(wa[0]), _fp(wa[1]), _fp(wa[2]),
+                               _fp(damp), param_kind, _fp(param), vp, dt, _ip(lo), _ip(hi), time_m, time_M,
+                               ctypes.byref(s) if s else None, ctypes.byref(r) if r else None, _fp(dm),
+                               _ip(dmalloc), dmhalo)
+    assert rc == 0
+    return u, U
 
 
 def tti_forward(u, v, so, w2, w1, dt, time_m, time_M, damp, vp, epsilon, delta, theta, phi,
