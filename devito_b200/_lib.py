@@ -49,7 +49,8 @@ class IsoArgs(Structure):
                 ('src', POINTER(Sparse)), ('rec', POINTER(Sparse)), ('rec_toff', c_int),
                 ('errctl', c_int), ('deviceid', c_int), ('kernel', c_int),
                 ('halo', c_void_p), ('timers', POINTER(Profiler)), ('adjoint', c_int),
-                ('grad', POINTER(Dataobj)), ('usave', POINTER(Dataobj)), ('free_surface', c_int), ('ot4', c_int)]
+                ('grad', POINTER(Dataobj)), ('usave', POINTER(Dataobj)), ('free_surface', c_int), ('ot4', c_int),
+                ('born_U', POINTER(Dataobj)), ('born_dm', POINTER(Dataobj))]
 
 
 class TtiArgs(Structure):

@@ -100,8 +100,8 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     const int so = a->space_order;
     int rc = B2_OK;
 
-    DevArray u, damp, param, grad, usave;
-    bool staged_grad = false, staged_usave = false;
+    DevArray u, damp, param, grad, usave, bornU, borndm;
+    bool staged_grad = false, staged_usave = false, staged_bornU = false, staged_borndm = false;
     SparseDev src, rec;
     IsoPlan p;
     FieldGeom g;
@@ -114,6 +114,11 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         if (staged_param) stage_out(param, false);
         if (staged_usave) stage_out(usave, false);
         int r3 = staged_grad ? stage_out(grad, code == B2_OK) : B2_OK;
+        if (staged_borndm) stage_out(borndm, false);
+        if (staged_bornU) {
+            const int r4 = stage_out(bornU, code == B2_OK || code == B2_ERR_NAN);
+            if (!r3) r3 = r4;
+        }
         if (code == B2_OK && r3) return r3;
         sparse_stage_out(src, false);
         int r2 = sparse_stage_out(rec, code == B2_OK || code == B2_ERR_NAN);
@@ -143,6 +148,24 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         staged_grad = true;
         if ((rc = stage_in(a->usave, 4, usave, true))) return cleanup(rc);
         staged_usave = true;
+    }
+
+    const bool born = a->born_U || a->born_dm;
+    if (born) {
+        if (!a->born_U || !a->born_dm || nd != 3 || a->adjoint || a->grad || a->free_surface || a->ot4 || a->halo) {
+            set_error("b2_iso_forward: Born modelling needs born_U and born_dm, 3-D, forward in time, and is "
+                      "not combined with halo exchange, free surface, OT4 or the imaging condition");
+            return cleanup(B2_ERR_INVALID);
+        }
+        if ((rc = stage_in(a->born_U, 4, bornU, true))) return cleanup(rc);
+        staged_bornU = true;
+        if ((rc = stage_in(a->born_dm, 3, borndm, true))) return cleanup(rc);
+        staged_borndm = true;
+        for (int d = 0; d < 4; ++d)
+            if (bornU.size[d] != u.size[d]) {
+                set_error("b2_iso_forward: born_U must have the layout of u");
+                return cleanup(B2_ERR_INVALID);
+            }
     }
 
     // ---- geometry in the internal 3-dim convention ----
@@ -197,6 +220,19 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         return cleanup(B2_ERR_INVALID);
     }
     if ((rc = iso_plan_init(p, a->kernel))) return cleanup(rc);
+    // Born: a second plan for the linearised field (same geometry and coefficient tables, own tensor maps)
+    IsoPlan pU = p;
+    int dmh = 0;
+    if (born) {
+        pU.u = (float *)bornU.d;
+        if ((rc = iso_plan_init(pU, a->kernel))) return cleanup(rc);
+        dmh = a->born_dm->hsize ? a->born_dm->hsize[0] : (borndm.size[0] - (u.size[1] - 2 * so)) / 2;
+        for (int d = 0; d < 3; ++d)
+            if (borndm.size[d] != u.size[d + 1] - 2 * so + 2 * dmh) {
+                set_error("b2_iso_forward: born_dm extent %d on dim %d does not match the grid", borndm.size[d], d);
+                return cleanup(B2_ERR_INVALID);
+            }
+    }
     if (a->free_surface && p.o[2] != so) {
         set_error("b2_iso_forward: a free surface needs the vertical iteration to start at 0");
         return cleanup(B2_ERR_INVALID);
@@ -252,8 +288,16 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
             // arrive with the neighbours' stores of this same step
             if (a->rec_toff && rec.present && (rc = halo_p2p_wait(a->halo))) return cleanup(rc);
         }
+        if (born) {
+            // eqn2 of the reference's Born operator comes after the source injection into u[t+1]
+            if ((rc = iso_step(pU, t0, t2, t1, 0, pU.n[0]))) return cleanup(rc);
+            if ((rc = iso_born_source(p, t0, t2, t1, pU.u + (size_t)t1 * p.slot_elems, (const float *)borndm.d,
+                                      (long long)borndm.size[1] * borndm.size[2], borndm.size[2],
+                                      a->x_m + dmh, a->y_m + dmh, a->z_m + dmh)))
+                return cleanup(rc);
+        }
         if (per_step_events) se.next();
-        const float *fr = p.u + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
+        const float *fr = (born ? pU.u : p.u) + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
         if ((rc = launch_interp(rec, g, fr, nullptr, time))) return cleanup(rc);
         if (staged_grad) {
             if (time < 0 || time >= usave.size[0]) {

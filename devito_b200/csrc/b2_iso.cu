@@ -45,6 +45,14 @@ __global__ void __launch_bounds__(256) k_ot4_w(IsoGK k) {
     for (int x = blockIdx.z; x < k.n0; x += gridDim.z) ot4_w_point(k, x, y, z);
 }
 
+// Born source term added to the freshly updated linearised field (b2_iso_point.cuh::born_src_point)
+__global__ void __launch_bounds__(256) k_born_src(IsoGK k) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (z >= k.n2 || y >= k.n1) return;
+    for (int x = blockIdx.z; x < k.n0; x += gridDim.z) born_src_point(k, x, y, z);
+}
+
 // Free surface: the sweep kernels compute every row with the plain stencil; this kernel then REDOES
 // the rows z <= radius — the only ones with a vertical tap that reaches the surface (z - k == 0, which
 // contributes 0 in the reference, not u[0]: u[0] is non-zero right after a source deposited into the
@@ -555,7 +563,26 @@ static IsoGK generic_args(const IsoPlan &p, int slot0, int slotm, int slot1, int
     k.W = nullptr;
     k.ot4c = p.dt * p.dt / 12.0f;
     k.vp2 = p.vp * p.vp;
+    k.U1 = nullptr;
+    k.dm = nullptr;
+    k.dsx = k.dsy = 0;
+    k.dg0 = k.dg1 = k.dg2 = 0;
     return k;
+}
+
+int iso_born_source(const IsoPlan &p, int slot0, int slotm, int slot1, float *U1, const float *dm,
+                    long long dsx, long long dsy, int dg0, int dg1, int dg2) {
+    IsoGK k = generic_args(p, slot0, slotm, slot1, 0, p.n[0]);
+    k.U1 = U1;
+    k.dm = dm;
+    k.dsx = dsx; k.dsy = dsy;
+    k.dg0 = dg0; k.dg1 = dg1; k.dg2 = dg2;
+    dim3 block(64, 4, 1);
+    dim3 grid((k.n2 + 63) / 64, (k.n1 + 3) / 4, (unsigned)std::min(k.n0, 65535));
+    k_born_src<<<grid, block, 0, stream()>>>(k);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
 }
 
 int iso_fs_fix(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {

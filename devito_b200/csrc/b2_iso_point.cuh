@@ -27,6 +27,12 @@ struct IsoGK {
     float *__restrict__ W;
     float ot4c;              // dt^2 / 12
     float vp2;               // scalar vp^2 (1/m) when param_kind == SCALAR
+    // Born (reference `Born` operator, acoustic/operators.py:235-277): the linearised field's new
+    // time level and the model perturbation dm (own strides / halo width)
+    float *__restrict__ U1;
+    const float *__restrict__ dm;
+    long long dsx, dsy;
+    int dg0, dg1, dg2;       // index in dm of the first iterated point (grid index + dm's halo width)
 };
 
 #define B2_HD __host__ __device__ __forceinline__
@@ -80,6 +86,25 @@ B2_HD void ot4_w_point(const IsoGK &k, int x, int y, int z) {
         minv = 1.0f / k.param[idx];
     }
     k.W[idx] = iso_star(k, k.u0, idx) * minv;
+}
+
+// Born source: eqn2 of the reference's `Born` operator is the plain update of U with
+// q = -dm * u.dt2 added to the numerator, u.dt2 = (u[t+1] - 2 u[t] + u[t-1]) / dt^2 taken AFTER the
+// source was injected into u[t+1]. The plain update of U has already run (same kernels as u), so
+// this adds q / (m/dt^2 + damp/dt). Here u0/um/u1 are the time levels of u.
+B2_HD void born_src_point(const IsoGK &k, int x, int y, int z) {
+    const long long idx = iso_index(k, x, y, z);
+    const long long j = (long long)(k.dg0 + x) * k.dsx + (long long)(k.dg1 + y) * k.dsy + (k.dg2 + z);
+    float m_dt2 = k.m_dt2;
+    if (k.param_kind == B2_PARAM_VP) {
+        const float v = k.param[idx];
+        m_dt2 = k.inv_dt2 / (v * v);
+    } else if (k.param_kind == B2_PARAM_M) {
+        m_dt2 = k.param[idx] * k.inv_dt2;
+    }
+    const float d = k.damp ? k.damp[idx] * k.inv_dt : 0.f;
+    const float q = -k.dm[j] * ((k.u1[idx] - 2.f * k.u0[idx] + k.um[idx]) * k.inv_dt2);
+    k.U1[idx] += q / (m_dt2 + d);
 }
 
 // Free surface on the low side of the last dimension (reference `freesurface`,

@@ -137,6 +137,13 @@ struct b2_iso_args {
      * space_order >= 2*radius; not combined with halo exchange, free surface or the imaging condition
      * in this version (-> 210).                                                                   */
     int ot4;
+    /* Linearised (Born) modelling, the reference's `Born` operator (acoustic/operators.py:235-277):
+     * both non-NULL -> `born_U` (same layout as u) is stepped next to u with the extra source
+     * -born_dm * u.dt2 (u.dt2 taken after `src` was injected into u[t+1]); `rec` then samples born_U
+     * instead of u. `born_dm` is a space array with its own halo width (hsize). Forward only; not
+     * combined with halo exchange, free surface, OT4 or the imaging condition in this version.   */
+    struct b2_dataobj *born_U;
+    struct b2_dataobj *born_dm;
 };
 int b2_iso_forward(const struct b2_iso_args *a);
 

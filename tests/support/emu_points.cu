@@ -9,10 +9,10 @@
 
 using namespace b2;
 
-extern "C" int emu_iso_step(float *u, const int *alloc /* 3 */, int so, int R, int ndim, const float *w0,
-                            const float *w1, const float *w2, const float *damp, int param_kind,
-                            const float *param, float vp, float dt, const int *lo, const int *hi, int t0,
-                            int t2, int t1, int free_surface, int ot4, float *W) {
+static IsoGK make_args(float *u, const int *alloc /* 3 */, int so, int R, int ndim, const float *w0,
+                       const float *w1, const float *w2, const float *damp, int param_kind,
+                       const float *param, float vp, float dt, const int *lo, const int *hi, int t0,
+                       int t2, int t1) {
     IsoGK k;
     const size_t slot = (size_t)alloc[0] * alloc[1] * alloc[2];
     k.u0 = u + (size_t)t0 * slot;
@@ -41,6 +41,18 @@ extern "C" int emu_iso_step(float *u, const int *alloc /* 3 */, int so, int R, i
     k.W = nullptr;
     k.ot4c = dt * dt / 12.0f;
     k.vp2 = vp * vp;
+    k.U1 = nullptr;
+    k.dm = nullptr;
+    k.dsx = k.dsy = 0;
+    k.dg0 = k.dg1 = k.dg2 = 0;
+    return k;
+}
+
+extern "C" int emu_iso_step(float *u, const int *alloc /* 3 */, int so, int R, int ndim, const float *w0,
+                            const float *w1, const float *w2, const float *damp, int param_kind,
+                            const float *param, float vp, float dt, const int *lo, const int *hi, int t0,
+                            int t2, int t1, int free_surface, int ot4, float *W) {
+    IsoGK k = make_args(u, alloc, so, R, ndim, w0, w1, w2, damp, param_kind, param, vp, dt, lo, hi, t0, t2, t1);
     if (ot4) {
         IsoGK g = k;
         g.W = W;
@@ -58,5 +70,30 @@ extern "C" int emu_iso_step(float *u, const int *alloc /* 3 */, int so, int R, i
         for (int x = 0; x < k.n0; ++x)
             for (int y = 0; y < k.n1; ++y)
                 for (int z = 0; z <= k.r2; ++z) iso_fs_point(k, x, y, z);
+    return 0;
+}
+
+// One Born step without sparse terms, in the order of b2_iso_forward: update u, update U with the same
+// kernel, then the Born source (b2::iso_born_source).
+extern "C" int emu_born_step(float *u, float *U, const float *dm, const int *dmalloc, int dmh,
+                             const int *alloc, int so, int R, const float *w0, const float *w1,
+                             const float *w2, const float *damp, int param_kind, const float *param,
+                             float vp, float dt, const int *lo, const int *hi, int t0, int t2, int t1) {
+    IsoGK ku = make_args(u, alloc, so, R, 3, w0, w1, w2, damp, param_kind, param, vp, dt, lo, hi, t0, t2, t1);
+    IsoGK kU = make_args(U, alloc, so, R, 3, w0, w1, w2, damp, param_kind, param, vp, dt, lo, hi, t0, t2, t1);
+    for (int x = 0; x < ku.n0; ++x)
+        for (int y = 0; y < ku.n1; ++y)
+            for (int z = 0; z < ku.n2; ++z) iso_point(ku, x, y, z);
+    for (int x = 0; x < kU.n0; ++x)
+        for (int y = 0; y < kU.n1; ++y)
+            for (int z = 0; z < kU.n2; ++z) iso_point(kU, x, y, z);
+    ku.U1 = kU.u1;
+    ku.dm = dm;
+    ku.dsx = (long long)dmalloc[1] * dmalloc[2];
+    ku.dsy = dmalloc[2];
+    ku.dg0 = lo[0] + dmh; ku.dg1 = lo[1] + dmh; ku.dg2 = lo[2] + dmh;
+    for (int x = 0; x < ku.n0; ++x)
+        for (int y = 0; y < ku.n1; ++y)
+            for (int z = 0; z < ku.n2; ++z) born_src_point(ku, x, y, z);
     return 0;
 }

@@ -36,6 +36,10 @@ def emu(tmp_path_factory):
                                  fp, ctypes.c_float, ctypes.c_float, ip, ip, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
     lib.emu_iso_step.restype = ctypes.c_int
+    lib.emu_born_step.argtypes = [fp, fp, fp, ip, ctypes.c_int, ip, ctypes.c_int, ctypes.c_int, fp, fp, fp, fp,
+                                  ctypes.c_int, fp, ctypes.c_float, ctypes.c_float, ip, ip, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int]
+    lib.emu_born_step.restype = ctypes.c_int
     return lib
 
 
@@ -104,3 +108,35 @@ def test_point_kernels_match_the_oracle(emu, case):
     assert rel_linf(u_emu[dom], u_ref[dom]) < 1e-5
     if fs:
         assert not u_emu[dom][(nsteps + 1) % 3][..., 0].any()
+
+
+@pytest.mark.parametrize('dmh', [0, 3])
+def test_born_point_kernels_match_the_oracle(emu, dmh):
+    so, shape, h, nsteps = 8, (21, 18, 16), 10.0, 6
+    dt = float(O.critical_dt(so, 3, h, 3.0))
+    w = [O.fd2_weights(so, h)] * 3
+    rng = np.random.default_rng(5)
+    u_ref = _initial(shape, so, seed=9)
+    U_ref = 0.1 * _initial(shape, so, seed=10)
+    u_emu, U_emu = u_ref.copy(), U_ref.copy()
+    damp = np.pad((0.02 * rng.uniform(0, 1, shape)).astype(np.float32), so)
+    vpa = np.pad(rng.uniform(1.5, 3.0, shape).astype(np.float32), so, mode='edge')
+    dm = np.pad(rng.uniform(-0.05, 0.05, shape).astype(np.float32), dmh)
+    O.born_forward(u_ref, U_ref, dm, so, w, dt, 1, nsteps, damp=damp, param=vpa, param_kind=1, dmhalo=dmh)
+    alloc = np.array(u_emu.shape[1:], dtype=np.int32)
+    dmalloc = np.array(dm.shape, dtype=np.int32)
+    lo = np.zeros(3, dtype=np.int32)
+    hi = np.array([s - 1 for s in shape], dtype=np.int32)
+    ws = [np.ascontiguousarray(x, dtype=np.float32) for x in w]
+    for time in range(1, nsteps + 1):
+        rc = emu.emu_born_step(_fp(u_emu), _fp(U_emu), _fp(dm), _ip(dmalloc), dmh, _ip(alloc), so, 4, _fp(ws[0]),
+                               _fp(ws[1]), _fp(ws[2]), _fp(damp), 1, _fp(vpa), 1.5, dt, _ip(lo), _ip(hi),
+                               time % 3, (time - 1) % 3, (time + 1) % 3)
+        assert rc == 0
+    dom = (slice(None),) + (slice(so, -so),) * 3
+    assert rel_linf(u_emu[dom], u_ref[dom]) < 1e-5
+    assert rel_linf(U_emu[dom], U_ref[dom]) < 1e-5
+    # the perturbation term matters in this set-up
+    U_plain = 0.1 * _initial(shape, so, seed=10)
+    O.iso_forward(U_plain, so, w, dt, 1, nsteps, damp=damp, param=vpa, param_kind=1)
+    assert rel_linf(U_plain[dom], U_ref[dom]) > 1e-3
