@@ -110,7 +110,7 @@ def signature(plan, name, distributed=False):
             head.append(_Param(obj.name, 'struct dataobj *restrict', f'{obj.name}_vec'))
         elif kind.endswith('_c'):
             head.append(_Param(obj.name, 'const float', obj.name))
-        for key in ('grad', 'usave'):
+        for key in ('grad', 'usave', 'born_U', 'born_dm'):
             f = plan.get(key)
             if f is not None:
                 head.append(_Param(f.name, 'struct dataobj *restrict', f'{f.name}_vec'))
@@ -217,6 +217,9 @@ def _iso_body(plan, distributed):
     L.append("  a.dt = dt;")
     _bounds(plan, L)
     L.append(f"  a.adjoint = {1 if plan.get('adjoint') else 0};")
+    if plan.get('born_U') is not None:
+        L.append(f"  a.born_U = (struct b2_dataobj *){plan['born_U'].name}_vec;")
+        L.append(f"  a.born_dm = (struct b2_dataobj *){plan['born_dm'].name}_vec;")
     if plan.get('free_surface'):
         L.append("  a.free_surface = 1;")
     if plan.get('ot4'):

@@ -235,7 +235,13 @@ class Operator:
         if len(updates) == 2:
             if self._dirn != 1:
                 raise _Unrecognised("adjoint TTI is not on the fast path")
-            return self._recognise_tti(updates, injs, itps)
+            try:
+                return self._recognise_tti(updates, injs, itps)
+            except _Unrecognised as tti_why:
+                try:
+                    return self._recognise_born(updates, injs, itps)
+                except _Unrecognised as born_why:
+                    raise _Unrecognised(f"neither TTI ({tti_why}) nor Born ({born_why})") from None
         raise _Unrecognised("unsupported number of update equations")
 
     @staticmethod
@@ -609,6 +615,75 @@ class Operator:
             plan['rec'] = sf
             plan['rec_toff'] = 1 if toffs.pop() != 0 else 0
 
+    def _recognise_born(self, updates, injs, itps):
+        """The reference's linearised-modelling operator (examples/seismic/acoustic/operators.py:
+        235-277): `eqn1 = iso_stencil(u)`, `eqn2 = iso_stencil(U, q=-dm*u.dt2)`, the source injected
+        into `u.forward`, the receivers sampling `U`. eqn2 must be eqn1's stencil applied to U plus
+        `-dm (u[t+1] - 2u[t] + u[t-1]) / dt^2` divided by the same denominator."""
+        fields = [f for f, _ in updates]
+
+        def depends_on(eq, f):
+            return any(n.is_Access and n.function is f for n in eq.rhs.evaluate.preorder())
+        first = [(f, e) for (f, e) in updates if not any(depends_on(e, g) for g in fields if g is not f)]
+        if len(first) != 1:
+            raise _Unrecognised("no update that is independent of the other field")
+        (u, equ) = first[0]
+        (U, eqU) = [(f, e) for (f, e) in updates if f is not u][0]
+        if U.grid is not u.grid or U.space_order != u.space_order or u.grid.dim != 3:
+            raise _Unrecognised("Born needs two 3-D wavefields of the same space order")
+        # the background update alone is the plain acoustic operator (it also fixes the parameter roles)
+        plan = self._recognise_iso((u, equ), [], [])
+        if plan.get('ot4') or plan.get('adjoint'):
+            raise _Unrecognised("Born is on the fast path for the forward OT2 update only")
+        grid = plan['grid']
+        terms = self._coeffs(eqU.rhs, [u, U])
+        ku = {}
+        for acc, coef in self._coeffs(equ.rhs, [u]).items():
+            ku[_space_offsets(acc, None)] = coef
+        kU, kq = {}, {}
+        for acc, coef in terms.items():
+            k = _space_offsets(acc, None)
+            if k is None:
+                raise _Unrecognised("non-affine wavefield access")
+            (kU if acc.function is U else kq)[k] = coef
+        zero = (0, 0, 0)
+        if set(kU) != set(ku) or set(kq) != {(1, zero), (0, zero), (-1, zero)}:
+            raise _Unrecognised("second update is not the background stencil plus a centred u.dt2 term")
+        funcs, consts, syms = self._leaves(list(kU.values()) + list(kq.values()))
+        known = {id(plan['damp'])} if plan.get('damp') is not None else set()
+        if plan['m_role'][1] is not None:
+            known.add(id(plan['m_role'][1]))
+        extra = [a for a in funcs if id(a.function) not in known]
+        if len(extra) != 1 or getattr(extra[0].function, 'is_TimeFunction', False):
+            raise _Unrecognised("cannot identify the model perturbation dm")
+        dm = extra[0].function
+        kd = _space_offsets(extra[0], None)
+        if kd is None or any(kd[1]):
+            raise _Unrecognised("dm accessed off-centre")
+        dtsym = plan['dt']
+        rng = np.random.default_rng(515)
+        for probe in range(2):
+            vals, leaf = self._probe_env(rng, funcs, consts, syms, grid)
+            dt = vals[('s', dtsym.name)]
+            m_val = self._role_value(plan['m_role'], vals)
+            d_val = vals[('f', id(plan['damp']))] if plan.get('damp') is not None else 0.0
+            den = m_val / dt ** 2 + d_val / dt
+            dmv = vals[('f', id(dm))]
+            for k, coef in kU.items():
+                if abs(eval_scalar(coef, leaf) - eval_scalar(ku[k], leaf)) > 1e-9 * max(1.0, abs(eval_scalar(ku[k], leaf))):
+                    raise _Unrecognised(f"U is not updated with the background stencil (tap {k})")
+            want = {(1, zero): -dmv / dt ** 2 / den, (0, zero): 2 * dmv / dt ** 2 / den, (-1, zero): -dmv / dt ** 2 / den}
+            for k, wv in want.items():
+                if abs(eval_scalar(kq[k], leaf) - wv) > 1e-9 * max(1.0, abs(wv)):
+                    raise _Unrecognised("the source of the second update is not -dm * u.dt2")
+        # sparse terms: the source drives u, the receivers sample U
+        fu, cu, su = self._leaves(ku.values())
+        self._attach_sparse(plan, injs, [], [u], fu, cu, su, plan['m_role'])
+        self._attach_sparse(plan, [], itps, [U], fu, cu, su, plan['m_role'])
+        plan['born_U'] = U
+        plan['born_dm'] = dm
+        return plan
+
     def _attach_imaging(self, plan, inc):
         """`Inc(grad, -u * v.dt2)` next to the adjoint update = the reference's Gradient operator
         (examples/seismic/acoustic/operators.py:190-232)."""
@@ -825,6 +900,7 @@ class Operator:
             out.append(p['m_role'][1])
         else:
             out.extend(p['consts'].values())
+        out += [p.get('born_U'), p.get('born_dm')]
         out += [s for s in (p['src'], p['rec']) if s is not None]
         return tuple(o for o in out if o is not None)
 
@@ -968,6 +1044,16 @@ class Operator:
         if damp is not None and not isinstance(damp, Function):
             raise InvalidArgument("`damp` override must be a Function")
         args['damp'] = damp
+        args['born_U'] = self._resolve(kwargs, p.get('born_U'), post)
+        args['born_dm'] = self._resolve(kwargs, p.get('born_dm'), post)
+        if args['born_U'] is not None:
+            bu = args['born_U']
+            if not isinstance(bu, TimeFunction) or bu.space_order != p['so'] or bu.grid.shape != grid.shape:
+                raise InvalidArgument("incompatible override for the linearised wavefield")
+            if not isinstance(args['born_dm'], Function):
+                raise InvalidArgument("`dm` must be a Function or an array of its allocated shape")
+            if grid.distributor.is_parallel:
+                raise InvalidArgument("Born modelling is not yet combined with domain decomposition")
         args['grad'] = self._resolve(kwargs, p.get('grad'), post)
         args['usave'] = self._resolve(kwargs, p.get('usave'), post)
         if args['usave'] is not None:
@@ -1247,6 +1333,9 @@ class Operator:
         a.adjoint = 1 if p.get('adjoint') else 0
         a.free_surface = 1 if p.get('free_surface') else 0
         a.ot4 = 1 if p.get('ot4') else 0
+        if args.get('born_U') is not None:
+            a.born_U = self._field_obj(args['born_U'], dev, res, hold, written=True).ptr
+            a.born_dm = self._field_obj(args['born_dm'], dev, res, hold).ptr
         if args.get('grad') is not None:
             a.grad = self._field_obj(args['grad'], dev, res, hold, written=True).ptr
             a.usave = self._field_obj(args['usave'], dev, res, hold).ptr

@@ -3,7 +3,8 @@ wavesolver.py:11-156): forward and adjoint operators (gradient/Born are SURVEY Â
 from .. import Eq, FreeSurface, Inc, Function, Operator, TimeFunction, solve
 from ..tools import memoized_meth
 
-__all__ = ['laplacian', 'iso_stencil', 'ForwardOperator', 'AdjointOperator', 'GradientOperator', 'AcousticWaveSolver']
+__all__ = ['laplacian', 'iso_stencil', 'ForwardOperator', 'AdjointOperator', 'GradientOperator',
+           'BornOperator', 'AcousticWaveSolver']
 
 
 def laplacian(field, model, kernel):
@@ -75,6 +76,23 @@ def GradientOperator(model, geometry, space_order=4, save=True, kernel='OT2', **
     return Operator(eqn + receivers + [gradient_update], subs=model.spacing_map, name='Gradient', **kwargs)
 
 
+def BornOperator(model, geometry, space_order=4, kernel='OT2', **kwargs):
+    """operators.py:235-277: background field u driven by the source, linearised field U driven by
+    `-dm * u.dt2`, receivers sampling U."""
+    kwargs.pop('save', None)
+    m = model.m
+    src, rec = geometry.src, geometry.rec
+    u = TimeFunction(name='u', grid=model.grid, save=None, time_order=2, space_order=space_order)
+    U = TimeFunction(name='U', grid=model.grid, save=None, time_order=2, space_order=space_order)
+    dm = Function(name='dm', grid=model.grid, space_order=0)
+    s = model.grid.stepping_dim.spacing
+    eqn1 = iso_stencil(u, model, kernel)
+    eqn2 = iso_stencil(U, model, kernel, q=-dm * u.dt2)
+    source = src.inject(field=u.forward, expr=src * s ** 2 / m)
+    receivers = rec.interpolate(expr=U)
+    return Operator(eqn1 + source + eqn2 + receivers, subs=model.spacing_map, name='Born', **kwargs)
+
+
 class AcousticWaveSolver:
     """wavesolver.py:11-120 (`forward` only)."""
 
@@ -129,6 +147,27 @@ class AcousticWaveSolver:
 
     jacobian_adjoint.__name__ = 'jacobian_adjoint'
     gradient = jacobian_adjoint
+
+    @memoized_meth
+    def op_born(self):
+        return BornOperator(self.model, save=None, geometry=self.geometry, kernel=self.kernel,
+                            space_order=self.space_order, **self._kwargs)
+
+    def jacobian(self, dmin, src=None, rec=None, u=None, U=None, model=None, **kwargs):
+        """wavesolver.py:216-254: linearised (Born) modelling for the model perturbation `dmin`
+        (a Function, or an array of the grid's shape)."""
+        src = src or self.geometry.src
+        rec = rec or self.geometry.rec
+        mk = lambda n: TimeFunction(name=n, grid=self.model.grid, time_order=2, space_order=self.space_order)
+        u = u or mk('u')
+        U = U or mk('U')
+        model = model or self.model
+        kwargs.update(model.physical_params(**kwargs))
+        summary = self.op_born().apply(dm=dmin, u=u, U=U, src=src, rec=rec, dt=kwargs.pop('dt', self.dt),
+                                       **kwargs)
+        return rec, u, U, summary
+
+    born = jacobian
 
     def forward(self, src=None, rec=None, u=None, model=None, save=None, **kwargs):
         src = src or self.geometry.src
