@@ -53,6 +53,7 @@ def test_ot4_lookalikes_are_refused():
 
 
 @pytest.mark.gpu
+@pytest.mark.pending
 @pytest.mark.parametrize('name,preset,so', CASES)
 def test_ot4_vs_reference_golden(name, preset, so):
     g = load_golden(name)
