@@ -32,7 +32,7 @@ from .equation import Eq, FreeSurface
 from .interpreter import Interpreter
 from .parameters import configuration
 from .exceptions import InvalidArgument, ExecutionError, InvalidOperator
-from .logger import perf
+from .logger import perf, warning
 from .tools import flatten
 from . import _lib as L_
 from . import distributed
@@ -181,8 +181,20 @@ class Operator:
         if self._plan is None and any(k == 'fs' for k, _ in self._items):
             raise InvalidOperator(f"free-surface operator not recognised by the CUDA path ({self._why_not}); "
                                   "there is no interpreter (CPU) implementation of it")
+        if self._plan is None and self._looks_like_wave_propagation():
+            # never silent: the CUDA kernels are the product, the interpreter is host plumbing for
+            # set-up operators and the reference's CPU-runnable 2-D diffusion case
+            warning(f"Operator `{name}` updates a second-order-in-time field but is not one of the schemes "
+                    f"the CUDA path implements ({self._why_not}); it will run on the NumPy interpreter")
         self._interp = None if self._plan is not None else Interpreter(self._items, None, self._subs, name=name)
         self._profiler_last = None
+
+    def _looks_like_wave_propagation(self):
+        for k, o in self._items:
+            if k == 'eq' and o.lhs.is_Access and getattr(o.lhs.function, 'is_TimeFunction', False) \
+                    and o.lhs.function.time_order == 2:
+                return True
+        return False
 
     # ------------------------------------------------------------------------------------------
     # recognition
