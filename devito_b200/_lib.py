@@ -50,7 +50,8 @@ class IsoArgs(Structure):
                 ('errctl', c_int), ('deviceid', c_int), ('kernel', c_int),
                 ('halo', c_void_p), ('timers', POINTER(Profiler)), ('adjoint', c_int),
                 ('grad', POINTER(Dataobj)), ('usave', POINTER(Dataobj)), ('free_surface', c_int), ('ot4', c_int),
-                ('born_U', POINTER(Dataobj)), ('born_dm', POINTER(Dataobj))]
+                ('born_U', POINTER(Dataobj)), ('born_dm', POINTER(Dataobj)),
+                ('snap', POINTER(Dataobj)), ('snap_factor', c_int), ('snap_toff', c_int)]
 
 
 class TtiArgs(Structure):

@@ -110,7 +110,7 @@ def signature(plan, name, distributed=False):
             head.append(_Param(obj.name, 'struct dataobj *restrict', f'{obj.name}_vec'))
         elif kind.endswith('_c'):
             head.append(_Param(obj.name, 'const float', obj.name))
-        for key in ('grad', 'usave', 'born_U', 'born_dm'):
+        for key in ('grad', 'usave', 'born_U', 'born_dm', 'snap'):
             f = plan.get(key)
             if f is not None:
                 head.append(_Param(f.name, 'struct dataobj *restrict', f'{f.name}_vec'))
@@ -217,6 +217,10 @@ def _iso_body(plan, distributed):
     L.append("  a.dt = dt;")
     _bounds(plan, L)
     L.append(f"  a.adjoint = {1 if plan.get('adjoint') else 0};")
+    if plan.get('snap') is not None:
+        L.append(f"  a.snap = (struct b2_dataobj *){plan['snap'].name}_vec;")
+        L.append(f"  a.snap_factor = {int(plan['snap_factor'])};")
+        L.append(f"  a.snap_toff = {int(plan['snap_toff'])};")
     if plan.get('born_U') is not None:
         L.append(f"  a.born_U = (struct b2_dataobj *){plan['born_U'].name}_vec;")
         L.append(f"  a.born_dm = (struct b2_dataobj *){plan['born_dm'].name}_vec;")

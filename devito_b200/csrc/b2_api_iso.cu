@@ -100,8 +100,9 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     const int so = a->space_order;
     int rc = B2_OK;
 
-    DevArray u, damp, param, grad, usave, bornU, borndm;
+    DevArray u, damp, param, grad, usave, bornU, borndm, snap;
     bool staged_grad = false, staged_usave = false, staged_bornU = false, staged_borndm = false;
+    bool staged_snap = false;
     SparseDev src, rec;
     IsoPlan p;
     FieldGeom g;
@@ -114,6 +115,10 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         if (staged_param) stage_out(param, false);
         if (staged_usave) stage_out(usave, false);
         int r3 = staged_grad ? stage_out(grad, code == B2_OK) : B2_OK;
+        if (staged_snap) {
+            const int r5 = stage_out(snap, code == B2_OK || code == B2_ERR_NAN);
+            if (!r3) r3 = r5;
+        }
         if (staged_borndm) stage_out(borndm, false);
         if (staged_bornU) {
             const int r4 = stage_out(bornU, code == B2_OK || code == B2_ERR_NAN);
@@ -166,6 +171,27 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
                 set_error("b2_iso_forward: born_U must have the layout of u");
                 return cleanup(B2_ERR_INVALID);
             }
+    }
+
+    int snap_h = 0;
+    if (a->snap) {
+        if (a->snap_factor < 1 || a->adjoint || a->halo) {
+            set_error("b2_iso_forward: snapshots need snap_factor >= 1, forward time stepping, single device");
+            return cleanup(B2_ERR_INVALID);
+        }
+        if ((rc = stage_in(a->snap, nd + 1, snap, true))) return cleanup(rc);
+        staged_snap = true;
+        snap_h = a->snap->hsize ? a->snap->hsize[2] : (snap.size[1] - (u.size[1] - 2 * so)) / 2;
+        for (int d = 0; d < nd; ++d)
+            if (snap.size[d + 1] != u.size[d + 1] - 2 * so + 2 * snap_h) {
+                set_error("b2_iso_forward: snapshot extent %d on dim %d does not match the grid", snap.size[d + 1], d);
+                return cleanup(B2_ERR_INVALID);
+            }
+        if (a->time_m < 0 || a->time_M / a->snap_factor >= snap.size[0]) {
+            set_error("b2_iso_forward: time_M=%d needs %d snapshots, the array holds %d", a->time_M,
+                      a->time_M / a->snap_factor + 1, snap.size[0]);
+            return cleanup(B2_ERR_INVALID);
+        }
     }
 
     // ---- geometry in the internal 3-dim convention ----
@@ -295,6 +321,17 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
                                       (long long)borndm.size[1] * borndm.size[2], borndm.size[2],
                                       a->x_m + dmh, a->y_m + dmh, a->z_m + dmh)))
                 return cleanup(rc);
+        }
+        if (a->snap && time % a->snap_factor == 0) {
+            // internal dims: a 2-D grid is (1, x, y), its snapshots (nsnaps, x, y)
+            const long long ssy = snap.size[nd];
+            const long long ssx = nd == 3 ? (long long)snap.size[2] * snap.size[3] : 0;
+            const size_t one = (size_t)(nd == 3 ? snap.size[1] : 1) * snap.size[nd - 1] * snap.size[nd];
+            float *dst = (float *)snap.d + (size_t)(time / a->snap_factor) * one;
+            const int d0 = nd == 3 ? a->x_m + snap_h : 0;
+            const int d1 = (nd == 3 ? a->y_m : a->x_m) + snap_h;
+            const int d2 = (nd == 3 ? a->z_m : a->y_m) + snap_h;
+            if ((rc = iso_snapshot(p, a->snap_toff ? t1 : t0, dst, ssx, ssy, d0, d1, d2))) return cleanup(rc);
         }
         if (per_step_events) se.next();
         const float *fr = (born ? pU.u : p.u) + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;

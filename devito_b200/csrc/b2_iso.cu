@@ -45,6 +45,31 @@ __global__ void __launch_bounds__(256) k_ot4_w(IsoGK k) {
     for (int x = blockIdx.z; x < k.n0; x += gridDim.z) ot4_w_point(k, x, y, z);
 }
 
+// Time-subsampled snapshot of the iteration box (b2_iso_point.cuh::snapshot_point)
+__global__ void __launch_bounds__(256) k_snapshot(SnapK k) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (z >= k.n2 || y >= k.n1) return;
+    for (int x = blockIdx.z; x < k.n0; x += gridDim.z) snapshot_point(k, x, y, z);
+}
+
+int iso_snapshot(const IsoPlan &p, int slot, float *snap, long long dsx, long long dsy, int d0, int d1, int d2) {
+    SnapK k;
+    k.src = p.u + (size_t)slot * p.slot_elems;
+    k.dst = snap;
+    k.sx = p.sx; k.sy = p.sy;
+    k.dsx = dsx; k.dsy = dsy;
+    k.n0 = p.n[0]; k.n1 = p.n[1]; k.n2 = p.n[2];
+    k.o0 = p.o[0]; k.o1 = p.o[1]; k.o2 = p.o[2];
+    k.d0 = d0; k.d1 = d1; k.d2 = d2;
+    dim3 block(64, 4, 1);
+    dim3 grid((k.n2 + 63) / 64, (k.n1 + 3) / 4, (unsigned)std::min(k.n0, 65535));
+    k_snapshot<<<grid, block, 0, stream()>>>(k);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
 // Born source term added to the freshly updated linearised field (b2_iso_point.cuh::born_src_point)
 __global__ void __launch_bounds__(256) k_born_src(IsoGK k) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;

@@ -42,6 +42,10 @@ int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xco
 // with mirrored vertical taps and clear the surface row (b2_iso_args.free_surface).
 int iso_fs_fix(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount);
 
+// Snapshot: copy the iteration box of time slot `slot` into one snapshot (own strides; (d0,d1,d2) = index
+// of the first iterated point in the snapshot array)
+int iso_snapshot(const IsoPlan &p, int slot, float *snap, long long dsx, long long dsy, int d0, int d1, int d2);
+
 // Born: U1 += -dm * u.dt2 / (m/dt^2 + damp/dt) over the iteration box; `p` is u's plan (slots of u),
 // U1 the new time level of the linearised field (same layout), dm with its own strides and the index
 // (dg0, dg1, dg2) of the first iterated point.

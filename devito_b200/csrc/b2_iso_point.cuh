@@ -107,6 +107,23 @@ B2_HD void born_src_point(const IsoGK &k, int x, int y, int z) {
     k.U1[idx] += q / (m_dt2 + d);
 }
 
+// Snapshot (time-subsampled saving, reference examples/seismic/tutorials/08_snapshotting.ipynb:455-505:
+// `Eq(usave, u)` on a ConditionalDimension -> `if (time % factor == 0) usave[time/factor][..] = u[t0][..]`):
+// copy of the iteration box between two arrays with different halo widths.
+struct SnapK {
+    const float *__restrict__ src;
+    float *__restrict__ dst;
+    long long sx, sy, dsx, dsy;      // strides of the wavefield slot / of one snapshot
+    int n0, n1, n2;
+    int o0, o1, o2;                  // index of the first point in the wavefield slot
+    int d0, d1, d2;                  // index of the first point in the snapshot
+};
+
+B2_HD void snapshot_point(const SnapK &k, int x, int y, int z) {
+    k.dst[(long long)(k.d0 + x) * k.dsx + (long long)(k.d1 + y) * k.dsy + (k.d2 + z)] =
+        k.src[(long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z)];
+}
+
 // Free surface on the low side of the last dimension (reference `freesurface`,
 // examples/seismic/acoustic/operators.py:5-47; generated form `r1[z]*u[t0][..][4 + abs(z - 1)]`,
 // `u[t2][x][y][4] = 0`): rows z <= radius redone with the vertical taps that reach z - k <= 0

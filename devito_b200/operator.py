@@ -212,6 +212,11 @@ class Operator:
         eqs = [e for e in eqs if not e.is_Increment]
         if not eqs:
             raise _Unrecognised("no plain time-update equations")
+        # `Eq(usave, u)` with usave saved on a ConditionalDimension: time-subsampled snapshots
+        snaps = [e for e in eqs if self._is_snapshot_eq(e)]
+        eqs = [e for e in eqs if not self._is_snapshot_eq(e)]
+        if not eqs:
+            raise _Unrecognised("no plain time-update equations")
         updates = []
         for e in eqs:
             lhs = e.lhs
@@ -241,9 +246,13 @@ class Operator:
             if incs:
                 self._attach_imaging(plan, incs[0])
             plan['free_surface'] = bool(fss)
+            if snaps:
+                self._attach_snapshot(plan, snaps)
             if fss and not self._covered_by_free_surface(updates[0][1], fss):
                 raise _Unrecognised("free-surface rows and the update's subdomain do not tile the grid")
             return plan
+        if snaps:
+            raise _Unrecognised("snapshots are on the fast path next to the single-field acoustic update only")
         if len(updates) == 2:
             if self._dirn != 1:
                 raise _Unrecognised("adjoint TTI is not on the fast path")
@@ -255,6 +264,37 @@ class Operator:
                 except _Unrecognised as born_why:
                     raise _Unrecognised(f"neither TTI ({tti_why}) nor Born ({born_why})") from None
         raise _Unrecognised("unsupported number of update equations")
+
+    @staticmethod
+    def _is_snapshot_eq(e):
+        f = e.lhs.function if e.lhs.is_Access else None
+        return (f is not None and getattr(f, 'is_TimeFunction', False) and not f.is_buffered and
+                getattr(f.time_dim, 'is_Conditional', False))
+
+    def _attach_snapshot(self, plan, snaps):
+        """`Eq(usave, u)` / `Eq(usave, u.forward)`, usave = TimeFunction(save=nsnaps, time_dim=
+        ConditionalDimension(parent=time, factor=f)) — examples/seismic/tutorials/08_snapshotting.ipynb:
+        455-505: every f-th step the wavefield is copied into usave[time / f]."""
+        if len(snaps) != 1 or plan.get('adjoint'):
+            raise _Unrecognised("one snapshot equation, forward time stepping only")
+        e = snaps[0]
+        us, u = e.lhs.function, plan['u']
+        tdim = us.time_dim
+        if tdim.condition is not None or not tdim.factor or int(tdim.factor) < 1 or \
+                tdim.parent is not plan['grid'].time_dim:
+            raise _Unrecognised("snapshots need a ConditionalDimension(parent=grid.time_dim, factor=n)")
+        kl = _space_offsets(e.lhs, None)
+        rhs = e.rhs.evaluate if hasattr(e.rhs, 'evaluate') else e.rhs
+        if not (rhs.is_Access and rhs.function is u):
+            raise _Unrecognised("a snapshot must copy the wavefield itself")
+        kr = _space_offsets(rhs, None)
+        if kl is None or kr is None or kl[0] != 0 or any(kl[1]) or any(kr[1]) or kr[0] not in (0, 1):
+            raise _Unrecognised("a snapshot must be `Eq(usave, u)` or `Eq(usave, u.forward)` at the same point")
+        if us.grid is not plan['grid'] or e.subdomain is not None:
+            raise _Unrecognised("snapshots cover the whole grid")
+        plan['snap'] = us
+        plan['snap_factor'] = int(tdim.factor)
+        plan['snap_toff'] = int(kr[0])
 
     @staticmethod
     def _covered_by_free_surface(eq, fss):
@@ -912,7 +952,7 @@ class Operator:
             out.append(p['m_role'][1])
         else:
             out.extend(p['consts'].values())
-        out += [p.get('born_U'), p.get('born_dm')]
+        out += [p.get('born_U'), p.get('born_dm'), p.get('snap')]
         out += [s for s in (p['src'], p['rec']) if s is not None]
         return tuple(o for o in out if o is not None)
 
@@ -1056,6 +1096,13 @@ class Operator:
         if damp is not None and not isinstance(damp, Function):
             raise InvalidArgument("`damp` override must be a Function")
         args['damp'] = damp
+        args['snap'] = self._resolve(kwargs, p.get('snap'), post)
+        if args['snap'] is not None:
+            sn = args['snap']
+            if not isinstance(sn, TimeFunction) or sn.is_buffered or sn.grid.shape != grid.shape:
+                raise InvalidArgument("the snapshot override must be a saved TimeFunction on the same grid")
+            if grid.distributor.is_parallel:
+                raise InvalidArgument("snapshots are not yet combined with domain decomposition")
         args['born_U'] = self._resolve(kwargs, p.get('born_U'), post)
         args['born_dm'] = self._resolve(kwargs, p.get('born_dm'), post)
         if args['born_U'] is not None:
@@ -1146,14 +1193,22 @@ class Operator:
         if time_m is None:
             time_m = 1           # u[t-1] is read: lower offset -1
         if time_M is None:
-            if not sized:
+            cands = [(s.nt if getattr(s, 'is_SparseTimeFunction', False) else s.time_size) - 2 for s in sized]
+            if args.get('snap') is not None:
+                # the sub-sampled dimension bounds its parent: time / factor < nsnaps
+                cands.append(args['snap'].time_size * p['snap_factor'] - 1)
+            if not cands:
                 raise InvalidArgument("No value found for parameter time_M")
-            nt = min(s.nt if getattr(s, 'is_SparseTimeFunction', False) else s.time_size for s in sized)
-            time_M = nt - 2      # u[t+1] is written: upper offset +1
+            time_M = min(cands)      # u[t+1] is written: upper offset +1
         for s in sized:
             n = s.nt if getattr(s, 'is_SparseTimeFunction', False) else s.time_size - 1
             if time_M >= n or time_m < 0:
                 raise InvalidArgument(f"OOB detected due to time_M={time_M}")
+        if args.get('snap') is not None:
+            need = int(time_M) // p['snap_factor'] + 1
+            if need > args['snap'].time_size:
+                raise InvalidArgument(f"OOB detected due to time_M={time_M}: {need} snapshots needed, "
+                                      f"`{args['snap'].name}` holds {args['snap'].time_size}")
         args['time_m'], args['time_M'] = int(time_m), int(time_M)
         args['resident'] = bool(kwargs.pop('resident', True)) and not bool(kwargs.pop('devicerm', 0))
         args['kernel'] = int(kwargs.pop('kernel', 0))
@@ -1345,6 +1400,10 @@ class Operator:
         a.adjoint = 1 if p.get('adjoint') else 0
         a.free_surface = 1 if p.get('free_surface') else 0
         a.ot4 = 1 if p.get('ot4') else 0
+        if args.get('snap') is not None:
+            a.snap = self._field_obj(args['snap'], dev, res, hold, written=True).ptr
+            a.snap_factor = p['snap_factor']
+            a.snap_toff = p['snap_toff']
         if args.get('born_U') is not None:
             a.born_U = self._field_obj(args['born_U'], dev, res, hold, written=True).ptr
             a.born_dm = self._field_obj(args['born_dm'], dev, res, hold).ptr

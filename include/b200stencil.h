@@ -144,6 +144,14 @@ struct b2_iso_args {
      * combined with halo exchange, free surface, OT4 or the imaging condition in this version.   */
     struct b2_dataobj *born_U;
     struct b2_dataobj *born_dm;
+    /* Time-subsampled snapshots (reference: `Eq(usave, u)` with usave on a ConditionalDimension of
+     * `factor`, examples/seismic/tutorials/08_snapshotting.ipynb:455-505): when snap != NULL, at every
+     * time step with time % snap_factor == 0 the iteration box of u[time + snap_toff] is copied into
+     * snap[time / snap_factor]. `snap` is (nsnaps, x, y, z) with its own halo width (hsize); the call
+     * fails with 210 if a snapshot index would fall outside it.                                  */
+    struct b2_dataobj *snap;
+    int snap_factor;
+    int snap_toff;
 };
 int b2_iso_forward(const struct b2_iso_args *a);
 

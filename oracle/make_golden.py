@@ -124,6 +124,30 @@ def born(name, so, n, nbl, tn):
          vp=np.array(model.vp.data), dm=dm, rec=np.array(rec.data), u=np.array(u.data), U=np.array(U.data))
 
 
+def snapshots(name, so, n, nbl, tn, factor):
+    """Time-subsampled saving, examples/seismic/tutorials/08_snapshotting.ipynb:455-505: `Eq(usave, u)`
+    with usave on ConditionalDimension(factor)."""
+    from devito import ConditionalDimension, Eq, Operator, TimeFunction, solve
+    from examples.seismic import demo_model, setup_geometry
+    model = demo_model('constant-isotropic', spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl, space_order=so,
+                       dtype=np.float32, bcs='damp')
+    geometry = setup_geometry(model, tn)
+    nt = geometry.nt
+    nsnaps = (nt + factor - 1) // factor
+    t_sub = ConditionalDimension('t_sub', parent=model.grid.time_dim, factor=factor)
+    usave = TimeFunction(name='usave', grid=model.grid, time_order=2, space_order=2, save=nsnaps, time_dim=t_sub)
+    u = TimeFunction(name='u', grid=model.grid, time_order=2, space_order=so)
+    pde = model.m * u.dt2 - u.laplace + model.damp * u.dt
+    stencil = Eq(u.forward, solve(pde, u.forward))
+    src, rec = geometry.src, geometry.rec
+    dt = model.critical_dt
+    op = Operator([stencil] + src.inject(field=u.forward, expr=src * dt ** 2 / model.m) + [Eq(usave, u)] +
+                  rec.interpolate(expr=u), subs=model.spacing_map)
+    op(time=nt - 2, dt=dt)
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(dt), nt=nt, factor=factor, nsnaps=nsnaps,
+         usave=np.array(usave.data), rec=np.array(rec.data), u=np.array(u.data))
+
+
 def gradient(name, so, n, nbl, tn):
     """Forward with the saved wavefield, then the Gradient operator (acoustic/operators.py:190-232,
     wavesolver.py:158-230): adjoint propagation of the data + imaging condition."""
@@ -178,7 +202,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'born', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'born', 'snap', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'fs' in which:
@@ -191,6 +215,8 @@ if __name__ == '__main__':
         acoustic('iso3d_so8_ot4', so=8, n=20, nbl=8, tn=150.0, kernel='OT4')
         acoustic('iso3d_so4_ot4_layers', so=4, n=20, nbl=8, tn=150.0, kernel='OT4',
                  preset='layers-isotropic', nlayers=3)
+    if 'snap' in which:
+        snapshots('snap3d_so4', so=4, n=20, nbl=8, tn=150.0, factor=4)
     if 'born' in which:
         born('born3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'iso8' in which:

@@ -97,3 +97,22 @@ extern "C" int emu_born_step(float *u, float *U, const float *dm, const int *dma
             for (int z = 0; z < ku.n2; ++z) born_src_point(ku, x, y, z);
     return 0;
 }
+
+// Snapshot copy of the iteration box (b2::iso_snapshot)
+extern "C" int emu_snapshot(const float *slot, const int *alloc, int so, float *snap, const int *salloc, int sh,
+                            const int *lo, const int *hi) {
+    SnapK k;
+    k.src = slot;
+    k.dst = snap;
+    k.sy = alloc[2];
+    k.sx = (long long)alloc[1] * alloc[2];
+    k.dsy = salloc[2];
+    k.dsx = (long long)salloc[1] * salloc[2];
+    k.n0 = hi[0] - lo[0] + 1; k.n1 = hi[1] - lo[1] + 1; k.n2 = hi[2] - lo[2] + 1;
+    k.o0 = lo[0] + so; k.o1 = lo[1] + so; k.o2 = lo[2] + so;
+    k.d0 = lo[0] + sh; k.d1 = lo[1] + sh; k.d2 = lo[2] + sh;
+    for (int x = 0; x < k.n0; ++x)
+        for (int y = 0; y < k.n1; ++y)
+            for (int z = 0; z < k.n2; ++z) snapshot_point(k, x, y, z);
+    return 0;
+}

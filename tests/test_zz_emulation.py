@@ -40,6 +40,8 @@ def emu(tmp_path_factory):
                                   ctypes.c_int, fp, ctypes.c_float, ctypes.c_float, ip, ip, ctypes.c_int,
                                   ctypes.c_int, ctypes.c_int]
     lib.emu_born_step.restype = ctypes.c_int
+    lib.emu_snapshot.argtypes = [fp, ip, ctypes.c_int, fp, ip, ctypes.c_int, ip, ip]
+    lib.emu_snapshot.restype = ctypes.c_int
     return lib
 
 
@@ -140,3 +142,19 @@ def test_born_point_kernels_match_the_oracle(emu, dmh):
     U_plain = 0.1 * _initial(shape, so, seed=10)
     O.iso_forward(U_plain, so, w, dt, 1, nsteps, damp=damp, param=vpa, param_kind=1)
     assert rel_linf(U_plain[dom], U_ref[dom]) > 1e-3
+
+
+def test_snapshot_point_kernel(emu):
+    """Copy of the iteration box between arrays of different halo width (so=8 wavefield -> so=2 snapshot)."""
+    so, sh, shape = 8, 2, (9, 7, 11)
+    rng = np.random.default_rng(2)
+    slot = rng.standard_normal(tuple(s + 2 * so for s in shape)).astype(np.float32)
+    snap = np.full(tuple(s + 2 * sh for s in shape), -7.0, dtype=np.float32)
+    lo = np.array([1, 0, 2], dtype=np.int32)
+    hi = np.array([7, 6, 9], dtype=np.int32)
+    emu.emu_snapshot(_fp(slot), _ip(np.array(slot.shape, dtype=np.int32)), so, _fp(snap),
+                     _ip(np.array(snap.shape, dtype=np.int32)), sh, _ip(lo), _ip(hi))
+    box = tuple(slice(int(l), int(h) + 1) for l, h in zip(lo, hi))
+    want = np.full_like(snap, -7.0)
+    want[tuple(slice(b.start + sh, b.stop + sh) for b in box)] = slot[tuple(slice(b.start + so, b.stop + so) for b in box)]
+    assert np.array_equal(snap, want)
