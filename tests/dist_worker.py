@@ -48,6 +48,16 @@ def host_mode():
     geometry = setup_geometry(model, 30.0)
     op = AcousticWaveSolver(model, geometry, space_order=so).op_fwd()
     assert op.backend == 'cuda-sm100a'
+    # free-surface model under decomposition: no layer above z, slab-local profile, operator recognised
+    fsm = SeismicModel(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=n, space_order=so, vp=vp,
+                       nbl=nbl, bcs="damp", fs=True, topology=('*', 1, 1))
+    assert fsm.grid.shape == (len(parts[w.rank]), n[1] + 2 * nbl, n[2] + nbl)
+    assert tuple(float(o) for o in fsm.grid.origin) == (-10. * nbl, -10. * nbl, 0.)
+    fs_full = damp_profile(fsm.grid.shape_global, fsm.padsizes, fsm.grid.spacing)
+    assert not fs_full[nbl:-nbl, nbl:-nbl, 0].any() and fs_full[nbl:-nbl, nbl:-nbl, -1].all()
+    assert np.array_equal(np.asarray(fsm.damp.data), fs_full[lo:hi])
+    fs_op = AcousticWaveSolver(fsm, setup_geometry(fsm, 30.0), space_order=so).op_fwd()
+    assert fs_op.backend == 'cuda-sm100a' and fs_op._plan['free_surface']
     dist.barrier()
     if w.rank == 0:
         print('DIST-HOST-OK')
