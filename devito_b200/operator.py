@@ -246,6 +246,8 @@ class Operator:
             if incs:
                 self._attach_imaging(plan, incs[0])
             plan['free_surface'] = bool(fss)
+            if fss and plan.get('ot4'):
+                raise _Unrecognised("a free surface under the OT4 kernel is not on the fast path yet")
             if snaps:
                 self._attach_snapshot(plan, snaps)
             if fss and not self._covered_by_free_surface(updates[0][1], fss):
