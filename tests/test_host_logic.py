@@ -211,3 +211,30 @@ def test_reference_examples_run_unchanged_up_to_the_ffi():
     ''') % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ref)
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert 'OK' in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize('so', [2, 4, 8, 12])
+@pytest.mark.parametrize('deriv,attr', [(1, 'dx'), (2, 'dx2'), (1, 'dy'), (2, 'dy2')])
+def test_derivatives_are_exact_on_polynomials(so, deriv, attr):
+    """Like the reference's tests/test_derivatives.py: an FD derivative of space order `so` is exact
+    (to rounding) for polynomials of degree <= so, through Derivative.evaluate and the interpreter."""
+    from devito_b200 import Function
+    n, h = 24, 0.5
+    grid = Grid(shape=(n, n), extent=((n - 1) * h, (n - 1) * h), dtype=np.float64)
+    f = Function(name='f', grid=grid, space_order=so, dtype=np.float64)
+    g = Function(name='g', grid=grid, space_order=so, dtype=np.float64)
+    x = (np.arange(n + 2 * so) - so) * h
+    X, Y = np.meshgrid(x, x, indexing='ij')
+    axis = X if attr.startswith('dx') else Y
+    other = Y if attr.startswith('dx') else X
+    # the reference's first derivative at space_order 2 is the two-point forward difference
+    # (`-f(x)/h + f(x+h)/h`), exact for degree 1 only
+    deg = 1 if (so == 2 and deriv == 1) else min(so, 6)
+    coef = np.linspace(1.0, 2.0, deg + 1)
+    f.data_with_halo[:] = sum(c * axis ** k for k, c in enumerate(coef)) * (1.0 + 0.1 * other)
+    exact = sum(c * np.prod(np.arange(k, k - deriv, -1)) * axis ** (k - deriv)
+                for k, c in enumerate(coef) if k >= deriv) * (1.0 + 0.1 * other)
+    Operator([Eq(g, getattr(f, attr))])()
+    got = np.asarray(g.data)
+    want = exact[so:-so, so:-so]
+    assert np.max(np.abs(got - want)) <= 1e-7 * np.max(np.abs(want))
