@@ -26,8 +26,20 @@ def build(fast=False):
     target = 'liboracle_fast.so' if fast else 'liboracle.so'
     path = os.path.join(HERE, target)
     src = os.path.join(HERE, 'oracle.c')
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
-        subprocess.run(['make', '-C', HERE, target], check=True, capture_output=True)
+    stale = not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src)
+    tag = path + '.cpu'
+    if fast:
+        # -march=native: rebuild when the binary was made on another CPU (see refrun.cpu_signature)
+        from .refrun import cpu_signature
+        sig = cpu_signature()
+        stale = stale or not (os.path.exists(tag) and open(tag).read().strip() == sig)
+    if stale:
+        env = dict(os.environ)
+        env.pop('CC', None)
+        subprocess.run(['make', '-B', '-C', HERE, target], check=True, capture_output=True, env=env)
+        if fast:
+            with open(tag, 'w') as f:
+                f.write(sig)
     return path
 
 

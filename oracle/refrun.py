@@ -26,21 +26,39 @@ class Profiler(Structure):
     _fields_ = [('section0', c_double), ('section1', c_double), ('section2', c_double)]
 
 
+def cpu_signature():
+    """Identifies the instruction set `-march=native` compiled for: the binaries travel from the build
+    container to the GPU box, whose CPU may differ (an unsupported instruction is a SIGILL, not an error
+    code) — a library is rebuilt whenever its recorded signature is not this host's."""
+    import hashlib
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('flags'):
+                    return hashlib.sha1(' '.join(sorted(line.split(':', 1)[1].split())).encode()).hexdigest()
+    except OSError:
+        pass
+    return 'unknown'
+
+
 def _compile(name):
     src = os.path.join(REF, name + '.c')
     so = os.path.join(REF, name + '.so')
+    tag = so + '.cpu'
     if not os.path.exists(src):
         return None
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    sig = cpu_signature()
+    built_here = os.path.exists(tag) and open(tag).read().strip() == sig
+    if not os.path.exists(so) or not built_here or os.path.getmtime(so) < os.path.getmtime(src):
         r = subprocess.run(['gcc'] + CFLAGS + [src, '-lm', '-o', so], capture_output=True, text=True)
         if r.returncode != 0:
             return None
+        with open(tag, 'w') as f:
+            f.write(sig)
     try:
         return ctypes.CDLL(so)
     except OSError:
-        # built on another CPU: rebuild for this one
-        r = subprocess.run(['gcc'] + CFLAGS + [src, '-lm', '-o', so], capture_output=True, text=True)
-        return ctypes.CDLL(so) if r.returncode == 0 else None
+        return None
 
 
 def load_forward(so, kind='iso'):
