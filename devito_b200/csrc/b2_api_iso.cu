@@ -83,6 +83,87 @@ struct StepEvents {
 };
 static StepEvents g_step_events;
 
+// Host-resident snapshots are not staged as a whole (nsnaps wavefields would not fit in HBM for a
+// production run): each snapshot is written into one of two device buffers by k_snapshot and drained
+// to the caller's array on a copy stream while the stencil keeps running — the out-of-core saving the
+// reference does with asynchronous streaming (devito/passes/clusters/buffering.py, passes/iet/
+// asynchrony.py). Only the iteration box travels (cudaMemcpy3DAsync), so the halo of the host
+// snapshots keeps its values, exactly like `Eq(usave, u)` over the domain.
+struct SnapStreamer {
+    bool active = false;
+    bool registered = false;         // we pinned the caller's array for the duration of the call
+    void *host = nullptr;
+    size_t host_bytes = 0;
+    float *buf[2] = {nullptr, nullptr};
+    size_t one = 0;                  // elements of one snapshot (with its halo)
+    int count = 0;
+    static cudaStream_t copy_stream;
+    static cudaEvent_t filled[2], drained[2];
+
+    int begin(void *host_base, size_t nbytes, size_t one_elems) {
+        host = host_base;
+        host_bytes = nbytes;
+        one = one_elems;
+        if (!copy_stream) {
+            B2_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), B2_ERR_DEVICE);
+            for (int i = 0; i < 2; ++i) {
+                B2_CUDA(cudaEventCreateWithFlags(&filled[i], cudaEventDisableTiming), B2_ERR_DEVICE);
+                B2_CUDA(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming), B2_ERR_DEVICE);
+            }
+        }
+        active = true;               // from here on end() has something to release
+        count = 0;
+        for (int i = 0; i < 2; ++i) B2_CUDA(cudaMalloc(&buf[i], one * sizeof(float)), B2_ERR_MEMORY);
+        // pinned memory makes the copies truly asynchronous; pageable memory still works (the driver
+        // stages it), already-pinned memory (e.g. torch pin_memory) is reported as such and left alone
+        cudaError_t e = cudaHostRegister(host, host_bytes, cudaHostRegisterDefault);
+        registered = (e == cudaSuccess);
+        if (!registered) cudaGetLastError();
+        return B2_OK;
+    }
+
+    // device buffer for the next snapshot, safe to overwrite on the compute stream
+    int acquire(float **out) {
+        const int b = count & 1;
+        if (count >= 2) B2_CUDA(cudaStreamWaitEvent(stream(), drained[b], 0), B2_ERR_DEVICE);
+        *out = buf[b];
+        return B2_OK;
+    }
+
+    // the snapshot kernel has been enqueued: drain the box [d, d + n) of the buffer into host slot `index`
+    int release(int index, const int *sz /* x,y,z extents of one snapshot */, const int *d, const int *n) {
+        const int b = count & 1;
+        B2_CUDA(cudaEventRecord(filled[b], stream()), B2_ERR_DEVICE);
+        B2_CUDA(cudaStreamWaitEvent(copy_stream, filled[b], 0), B2_ERR_DEVICE);
+        cudaMemcpy3DParms prm = {};
+        const size_t pitch = (size_t)sz[2] * sizeof(float);
+        prm.srcPtr = make_cudaPitchedPtr(buf[b], pitch, sz[2], sz[1]);
+        prm.dstPtr = make_cudaPitchedPtr((float *)host + (size_t)index * one, pitch, sz[2], sz[1]);
+        prm.srcPos = make_cudaPos((size_t)d[2] * sizeof(float), d[1], d[0]);
+        prm.dstPos = prm.srcPos;
+        prm.extent = make_cudaExtent((size_t)n[2] * sizeof(float), n[1], n[0]);
+        prm.kind = cudaMemcpyDeviceToHost;
+        B2_CUDA(cudaMemcpy3DAsync(&prm, copy_stream), B2_ERR_MEMORY);
+        B2_CUDA(cudaEventRecord(drained[b], copy_stream), B2_ERR_DEVICE);
+        ++count;
+        return B2_OK;
+    }
+
+    int end() {
+        if (!active) return B2_OK;
+        active = false;
+        cudaError_t e = cudaStreamSynchronize(copy_stream);
+        for (int i = 0; i < 2; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; }
+        if (registered) cudaHostUnregister(host);
+        registered = false;
+        if (e != cudaSuccess) { set_error("snapshot streaming: %s", cudaGetErrorString(e)); return B2_ERR_MEMORY; }
+        return B2_OK;
+    }
+};
+cudaStream_t SnapStreamer::copy_stream = nullptr;
+cudaEvent_t SnapStreamer::filled[2] = {nullptr, nullptr};
+cudaEvent_t SnapStreamer::drained[2] = {nullptr, nullptr};
+
 }  // namespace b2
 
 extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
@@ -103,6 +184,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     DevArray u, damp, param, grad, usave, bornU, borndm, snap;
     bool staged_grad = false, staged_usave = false, staged_bornU = false, staged_borndm = false;
     bool staged_snap = false;
+    SnapStreamer streamer;
     SparseDev src, rec;
     IsoPlan p;
     FieldGeom g;
@@ -118,6 +200,10 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         if (staged_snap) {
             const int r5 = stage_out(snap, code == B2_OK || code == B2_ERR_NAN);
             if (!r3) r3 = r5;
+        }
+        {
+            const int r6 = streamer.end();
+            if (!r3) r3 = r6;
         }
         if (staged_borndm) stage_out(borndm, false);
         if (staged_bornU) {
@@ -179,8 +265,19 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
             set_error("b2_iso_forward: snapshots need snap_factor >= 1, forward time stepping, single device");
             return cleanup(B2_ERR_INVALID);
         }
-        if ((rc = stage_in(a->snap, nd + 1, snap, true))) return cleanup(rc);
-        staged_snap = true;
+        const bool stream_out = !a->snap->dmap && a->snap->data && nd == 3 &&
+                                !(getenv("B2_SNAP_STREAM") && atoi(getenv("B2_SNAP_STREAM")) == 0);
+        if (stream_out) {
+            // describe the array without allocating it on the device
+            if (!a->snap->size) { set_error("b2_iso_forward: snapshot dataobj without `size`"); return cleanup(B2_ERR_INVALID); }
+            snap.ndim = nd + 1;
+            for (int d = 0; d <= nd; ++d) snap.size[d] = a->snap->size[d];
+            snap.h = a->snap->data;
+            snap.d = nullptr;
+        } else {
+            if ((rc = stage_in(a->snap, nd + 1, snap, true))) return cleanup(rc);
+            staged_snap = true;
+        }
         snap_h = a->snap->hsize ? a->snap->hsize[2] : (snap.size[1] - (u.size[1] - 2 * so)) / 2;
         for (int d = 0; d < nd; ++d)
             if (snap.size[d + 1] != u.size[d + 1] - 2 * so + 2 * snap_h) {
@@ -191,6 +288,10 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
             set_error("b2_iso_forward: time_M=%d needs %d snapshots, the array holds %d", a->time_M,
                       a->time_M / a->snap_factor + 1, snap.size[0]);
             return cleanup(B2_ERR_INVALID);
+        }
+        if (stream_out) {
+            const size_t one = (size_t)snap.size[1] * snap.size[2] * snap.size[3];
+            if ((rc = streamer.begin(snap.h, one * snap.size[0] * sizeof(float), one))) return cleanup(rc);
         }
     }
 
@@ -327,11 +428,20 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
             const long long ssy = snap.size[nd];
             const long long ssx = nd == 3 ? (long long)snap.size[2] * snap.size[3] : 0;
             const size_t one = (size_t)(nd == 3 ? snap.size[1] : 1) * snap.size[nd - 1] * snap.size[nd];
-            float *dst = (float *)snap.d + (size_t)(time / a->snap_factor) * one;
+            float *dst = nullptr;
+            if (streamer.active) {
+                if ((rc = streamer.acquire(&dst))) return cleanup(rc);
+            } else {
+                dst = (float *)snap.d + (size_t)(time / a->snap_factor) * one;
+            }
             const int d0 = nd == 3 ? a->x_m + snap_h : 0;
             const int d1 = (nd == 3 ? a->y_m : a->x_m) + snap_h;
             const int d2 = (nd == 3 ? a->z_m : a->y_m) + snap_h;
             if ((rc = iso_snapshot(p, a->snap_toff ? t1 : t0, dst, ssx, ssy, d0, d1, d2))) return cleanup(rc);
+            if (streamer.active) {
+                const int dd[3] = {d0, d1, d2};
+                if ((rc = streamer.release(time / a->snap_factor, &snap.size[1], dd, p.n))) return cleanup(rc);
+            }
         }
         if (per_step_events) se.next();
         const float *fr = (born ? pU.u : p.u) + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;

@@ -70,3 +70,19 @@ def test_snapshots_vs_reference_golden():
     assert rel_linf(usave.data, g['usave']) < 1e-5
     assert rel_linf(u.data, g['u']) < 1e-5
     assert rel_linf(rec.data, g['rec']) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.pending
+def test_snapshots_streamed_to_host_match_the_resident_run():
+    """Host-resident snapshots are drained box by box on a copy stream while the stencil runs
+    (SnapStreamer in b2_api_iso.cu); same values as the device-resident run, halo untouched."""
+    g = load_golden('snap3d_so4')
+    op, model, geometry, u, usave, rec, dt = _operator(g)
+    usave.data_with_halo[:] = -3.0                         # marker: the halo and unvisited slots must survive
+    op(time=geometry.nt - 2, dt=dt, resident=False)
+    got = np.array(usave.data_with_halo)
+    assert rel_linf(np.asarray(usave.data)[1:], g['usave'][1:]) < 1e-5
+    h = usave.space_order
+    assert np.all(got[:, :h] == -3.0) and np.all(got[:, :, :, -h:] == -3.0)
+    assert np.all(got[0] == -3.0)                          # time = 0 is never visited
