@@ -1345,14 +1345,38 @@ class Operator:
         pts = float(np.prod([h - l + 1 for l, h in zip(args['lo'], args['hi'])])) * nsteps
         summary = PerformanceSummary()
         tot = timers.section0 + timers.section1 + timers.section2
+        ops, bpp = self._flops_and_bytes_per_point()
         for nm in ('section0', 'section1', 'section2'):
             t = getattr(timers, nm)
-            summary[nm] = PerfEntry(t, gpointss=(pts / t / 1e9 if t > 0 and nm == 'section0' else None))
+            main = t > 0 and nm == 'section0'
+            summary[nm] = PerfEntry(t, gpointss=(pts / t / 1e9 if main else None),
+                                    gflopss=(ops * pts / t / 1e9 if main else None),
+                                    oi=(ops / bpp if main else None), ops=(ops if main else None))
         summary.globals['fdlike'] = PerfEntry(t_wall, gpointss=pts / t_wall / 1e9 if t_wall > 0 else None)
         summary.globals['fdlike-nosetup'] = PerfEntry(tot, gpointss=pts / tot / 1e9 if tot > 0 else None)
         perf(f"Operator `{self.name}` ran in {t_wall:.4f} s [{pts / max(tot, 1e-12) / 1e9:.2f} GPts/s on device]")
         self._profiler_last = summary
         return summary
+
+    def _flops_and_bytes_per_point(self):
+        """Floating-point operations the CUDA kernels execute per grid point and time step (counted on
+        the kernels' own formulas, a multiply-add = 2) and the algorithmic HBM bytes per point (SURVEY
+        §8d) — what the reference reports as `gflopss` / `oi` from its own op count
+        (devito/operator/profiling.py:344-430)."""
+        p = self._plan
+        R, nd = p['R'], p['grid'].dim
+        star = 1 + nd * R * 3                       # centre mul + per tap pair: add, multiply-add
+        if p['kind'] == 'iso':
+            arr = p['m_role'][0].endswith('_f')
+            ops = star + 8
+            bpp = 20.0 if arr else 16.0
+            if p.get('ot4'):
+                ops += 2 * star + 3
+                bpp += 8.0
+            return float(ops), bpp
+        arr = any(hasattr(c, 'space_order') for c in p['consts'].values())
+        ops = star + 2 * (6 * R + 5) + 2 * (6 * R + 3) + 16
+        return float(ops), (48.0 if arr else 28.0)
 
     def _w_arrays(self, wlists, hold):
         arr = (ctypes.POINTER(ctypes.c_float) * 3)()
