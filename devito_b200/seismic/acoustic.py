@@ -62,7 +62,8 @@ def AdjointOperator(model, geometry, space_order=4, kernel='OT2', save=None, **k
 def GradientOperator(model, geometry, space_order=4, save=True, kernel='OT2', **kwargs):
     """operators.py:190-232: adjoint propagation of the data + imaging condition grad -= u * v.dt2."""
     if kernel != 'OT2':
-        raise NotImplementedError("only the OT2 kernel is on this backend's path")
+        raise NotImplementedError("the OT4 imaging condition (extra biharmonic term, operators.py:225-226) "
+                                  "is not on this backend's path yet")
     m = model.m
     grad = Function(name='grad', grid=model.grid)
     u = TimeFunction(name='u', grid=model.grid, save=geometry.nt if save else None, time_order=2,
