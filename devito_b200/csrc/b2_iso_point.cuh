@@ -124,6 +124,25 @@ B2_HD void snapshot_point(const SnapK &k, int x, int y, int z) {
         k.src[(long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z)];
 }
 
+// Generic constant-coefficient explicit update (b2_linear_forward): out[p] = sum_k coef_k * in_k[p + d_k]
+struct LinK {
+    float *__restrict__ out;
+    const float *__restrict__ lvl[4];    // base pointers of the distinct time levels read
+    long long sx, sy;
+    int n0, n1, n2, o0, o1, o2;
+    int ntaps;
+    int sel[B2_MAX_TAPS];                // which level each tap reads
+    long long delta[B2_MAX_TAPS];        // linear index offset of each tap
+    float coef[B2_MAX_TAPS];
+};
+
+B2_HD void linear_point(const LinK &k, int x, int y, int z) {
+    const long long idx = (long long)(k.o0 + x) * k.sx + (long long)(k.o1 + y) * k.sy + (k.o2 + z);
+    float acc = 0.f;
+    for (int i = 0; i < k.ntaps; ++i) acc += k.coef[i] * k.lvl[k.sel[i]][idx + k.delta[i]];
+    k.out[idx] = acc;
+}
+
 // Free surface on the low side of the last dimension (reference `freesurface`,
 // examples/seismic/acoustic/operators.py:5-47; generated form `r1[z]*u[t0][..][4 + abs(z - 1)]`,
 // `u[t2][x][y][4] = 0`): rows z <= radius redone with the vertical taps that reach z - k <= 0

@@ -204,6 +204,63 @@ class Operator:
         return 'cuda-sm100a' if self._plan is not None else 'numpy-interpreter'
 
     def _recognise(self):
+        try:
+            return self._recognise_wave()
+        except _Unrecognised as wave_why:
+            try:
+                return self._recognise_linear()
+            except _Unrecognised as lin_why:
+                raise _Unrecognised(f"{wave_why}; as a generic constant-coefficient update: {lin_why}") from None
+
+    def _recognise_linear(self):
+        """A single explicit update `f.forward|backward = sum_k c_k f[t + s_k][p + o_k]` whose
+        coefficients contain no field (Constants, spacings, dt and numbers only) — e.g. the reference's
+        2-D diffusion example, BASELINE config 1 (examples/cfd/example_diffusion.py:120-133). Runs on
+        `b2_linear_forward`; the coefficients are evaluated when the operator is applied."""
+        if len(self._items) != 1 or self._items[0][0] != 'eq' or self._items[0][1].is_Increment:
+            raise _Unrecognised("not a single plain equation")
+        e = self._items[0][1]
+        lhs = e.lhs
+        if not (lhs.is_Access and getattr(lhs.function, 'is_TimeFunction', False)):
+            raise _Unrecognised("lhs is not a TimeFunction")
+        f = lhs.function
+        grid = f.grid
+        if grid is None or not f.is_buffered or grid.dim not in (1, 2, 3) or grid.distributor.is_parallel:
+            raise _Unrecognised("needs a buffered TimeFunction on a non-decomposed 1-D/2-D/3-D grid")
+        kl = _space_offsets(lhs, None)
+        if kl is None or kl[0] not in (1, -1) or any(kl[1]):
+            raise _Unrecognised("lhs is not `f.forward` / `f.backward`")
+        terms = self._coeffs(e.rhs, [f])
+        taps = []
+        for acc, coef in terms.items():
+            k = _space_offsets(acc, None)
+            if k is None:
+                raise _Unrecognised("non-affine access")
+            if k[0] == kl[0]:
+                raise _Unrecognised("implicit scheme: the written time level is read")
+            if any(abs(o) > f.space_order for o in k[1]):
+                raise _Unrecognised("stencil reaches beyond the halo")
+            for n in coef.preorder():
+                if n.is_Access:
+                    raise _Unrecognised("position-dependent coefficient")
+            taps.append((k[0], k[1], coef))
+        if not taps or len(taps) > L_.MAX_TAPS or len({t for t, _, _ in taps}) > 4:
+            raise _Unrecognised("unsupported number of taps / time levels")
+        if f.time_size < len({t for t, _, _ in taps}) + 1:
+            raise _Unrecognised("not enough time slots")
+        taps.sort(key=lambda t: (t[0], t[1]))
+        # iteration box: the equation's SubDomain (rectangular) or the whole grid
+        box = []
+        sd = e.subdomain.dimensions if e.subdomain is not None else grid.dimensions
+        for d, n in zip(sd, grid.shape):
+            box.append(d.bounds(0, n - 1) if d.is_Sub else (0, n - 1))
+        tmin = min(t for t, _, _ in taps)
+        tmax = max(t for t, _, _ in taps)
+        return {'kind': 'linear', 'u': f, 'grid': grid, 'so': f.space_order, 'R': 0, 'taps': taps,
+                'wshift': kl[0], 'box': box, 'dt': grid.stepping_dim.spacing, 'src': None, 'rec': None,
+                'rec_toff': 0, 'tlo': min(tmin, kl[0], 0), 'thi': max(tmax, kl[0], 0)}
+
+    def _recognise_wave(self):
         eqs = [o for k, o in self._items if k == 'eq']
         injs = [o for k, o in self._items if k == 'inject']
         itps = [o for k, o in self._items if k == 'interp']
@@ -905,6 +962,10 @@ class Operator:
             return (f"/* Operator `{self.name}`: NumPy interpreter ({len(self._items)} expressions)"
                     f"{' -- not recognised: ' + self._why_not if self._why_not else ''} */")
         p = self._plan
+        if p['kind'] == 'linear':
+            taps = ', '.join(f"f[t{t:+d}]{list(o)}" for t, o, _ in p['taps'])
+            return (f"/* Operator `{self.name}` -> libb200stencil.so::b2_linear_forward (sm_100a)\n"
+                    f"   {p['u'].name}[t{p['wshift']:+d}] = sum_k c_k * ({taps}) */")
         entry = 'b2_iso_forward' if p['kind'] == 'iso' else 'b2_tti_forward'
         head = (f"/* Operator `{self.name}` -> libb200stencil.so::{entry} (sm_100a)\n"
                 f"   space_order={p['so']} radius={p['R']} src={p['src'] and p['src'].name} "
@@ -922,7 +983,7 @@ class Operator:
         if self._plan is None:
             raise InvalidOperator("interpreted operators have no C entry point")
         L = L_.load_library()
-        return L.b2_iso_forward if self._plan['kind'] == 'iso' else L.b2_tti_forward
+        return {'iso': L.b2_iso_forward, 'tti': L.b2_tti_forward, 'linear': L.b2_linear_forward}[self._plan['kind']]
 
     def cinterface(self, force=False):
         """Write `<name>.c` / `<name>.h` under the JIT directory and return `(ccode, hcode)`
@@ -930,8 +991,8 @@ class Operator:
         adapter exporting the reference-style symbol `int <name>(struct dataobj *..., ...)` on top of
         libb200stencil.so — see devito_b200/cinterface.py."""
         from . import cinterface as ci
-        if self._plan is None:
-            raise InvalidOperator("interpreted operators have no C interface")
+        if self._plan is None or self._plan['kind'] == 'linear':
+            raise InvalidOperator("no C adapter is generated for interpreted / generic-stencil operators")
         dist = self._plan['grid'].distributor.is_parallel
         ccode, hcode = ci.generate(self._plan, self.name, distributed=dist)
         dest = ci.jit_dir()
@@ -947,6 +1008,9 @@ class Operator:
         p = self._plan
         if p is None:
             return tuple(self._interp.functions.values())
+        if p['kind'] == 'linear':
+            cs = {id(n): n for _, _, c in p['taps'] for n in c.preorder() if n.is_Constant}
+            return (p['u'],) + tuple(cs.values())
         out = [p['u']] + ([p['v']] if p['kind'] == 'tti' else [])
         if p.get('damp') is not None:
             out.append(p['damp'])
@@ -969,11 +1033,15 @@ class Operator:
             return self._apply_interp(**kwargs)
         if self._plan['kind'] == 'iso':
             return self._apply_iso(**kwargs)
+        if self._plan['kind'] == 'linear':
+            return self._apply_linear(**kwargs)
         return self._apply_tti(**kwargs)
 
     def arguments(self, **kwargs):
         if self._plan is None:
             return self._interp_args(dict(kwargs))
+        if self._plan['kind'] == 'linear':
+            return self._prepare_linear(dict(kwargs))
         return self._prepare(dict(kwargs))[0]
 
     _prepare_arguments = arguments
@@ -1012,7 +1080,7 @@ class Operator:
         sized = [f for f in fns.values() if (getattr(f, 'is_SparseTimeFunction', False))
                  or (getattr(f, 'is_TimeFunction', False) and not f.is_buffered)]
         time_m = kwargs.pop('time_m', None)
-        time_M = kwargs.pop('time_M', kwargs.pop('time', None))
+        time_M = kwargs.pop('time_M', kwargs.pop('time', kwargs.pop('t', None)))
         if it.has_time:
             if time_m is None:
                 time_m = -min(tlo, 0)
@@ -1364,6 +1432,8 @@ class Operator:
         §8d) — what the reference reports as `gflopss` / `oi` from its own op count
         (devito/operator/profiling.py:344-430)."""
         p = self._plan
+        if p['kind'] == 'linear':
+            return float(2 * len(p['taps'])), 4.0 * (len({t for t, _, _ in p['taps']}) + 1)
         R, nd = p['R'], p['grid'].dim
         star = 1 + nd * R * 3                       # centre mul + per tap pair: add, multiply-add
         if p['kind'] == 'iso':
@@ -1444,6 +1514,103 @@ class Operator:
         rc = L.b2_iso_forward(ctypes.byref(a))
         t_wall = _time.perf_counter() - t0
         for fn in post + args['post']:
+            fn()
+        return self._finish(rc, L, timers, args, 1, t_wall)
+
+    # -- generic constant-coefficient update ------------------------------------------------------
+    def _prepare_linear(self, kwargs):
+        p = self._plan
+        grid, f0 = p['grid'], p['u']
+        args = OrderedDict()
+        post = args['post'] = []
+        f = self._resolve(kwargs, f0, post)
+        if not isinstance(f, TimeFunction) or f.space_order != f0.space_order or f.grid.shape != grid.shape \
+                or f.time_size != f0.time_size:
+            raise InvalidArgument("incompatible override for the updated field")
+        args['fields'] = [f]
+        # scalar environment of the coefficients: spacings, dt, Constants (overridable by name)
+        env = {sp.name: float(v) for sp, v in grid.spacing_map.items()}
+        for sp in grid.spacing_symbols:
+            if sp.name in kwargs:
+                env[sp.name] = float(kwargs.pop(sp.name))
+        need_dt = any(n.is_Symbol and n.name == p['dt'].name for _, _, c in p['taps'] for n in c.preorder())
+        if 'dt' in kwargs:
+            env[p['dt'].name] = float(np.float32(kwargs.pop('dt')))
+        elif need_dt:
+            raise InvalidArgument("No value found for parameter dt")
+        consts = {}
+        for _, _, c in p['taps']:
+            for n in c.preorder():
+                if n.is_Constant:
+                    v = kwargs.pop(n.name, n)
+                    consts[id(n)] = float(v.data if isinstance(v, Constant) else v)
+
+        def leaf(n):
+            if n.is_Constant:
+                return consts[id(n)]
+            if n.name in env:
+                return env[n.name]
+            raise InvalidArgument(f"No value found for parameter {n.name}")
+        args['taps'] = [(t, o, float(np.float32(eval_scalar(c, leaf)))) for t, o, c in p['taps']]
+        lo, hi = [], []
+        for d, n, (bl, bh) in zip(grid.dimensions, grid.shape, p['box']):
+            a = kwargs.pop(d.min_name, None)
+            b = kwargs.pop(d.max_name, None)
+            a = bl if a is None else a
+            b = bh if b is None else b
+            if a < 0 or b > n - 1:
+                raise InvalidArgument(f"OOB detected due to {d.min_name}={a}, {d.max_name}={b}")
+            lo.append(int(a))
+            hi.append(int(b))
+        args['lo'], args['hi'] = lo, hi
+        time_m = kwargs.pop('time_m', None)
+        time_M = kwargs.pop('time_M', kwargs.pop('time', kwargs.pop(grid.stepping_dim.name, None)))
+        if time_m is None:
+            time_m = -p['tlo']
+        if time_M is None:
+            raise InvalidArgument("No value found for parameter time_M")
+        if time_m < 0:
+            raise InvalidArgument(f"OOB detected due to time_m={time_m}")
+        args['time_m'], args['time_M'] = int(time_m), int(time_M)
+        args['resident'] = bool(kwargs.pop('resident', True)) and not bool(kwargs.pop('devicerm', 0))
+        args['deviceid'] = kwargs.pop('deviceid', None)
+        for k in ('autotune', 'nthreads', 'nthreads_nonaffine', 'kernel', 'errctl'):
+            kwargs.pop(k, None)
+        if kwargs and not configuration['ignore-unknowns']:
+            raise InvalidArgument(f"Unrecognized argument(s) {sorted(kwargs)} in kwargs")
+        return args
+
+    def _apply_linear(self, **kwargs):
+        L = L_.lib()
+        args = self._prepare_linear(dict(kwargs))
+        p = self._plan
+        grid = p['grid']
+        nd = grid.dim
+        dev = self._device(args)
+        hold = []
+        a = L_.LinearArgs()
+        a.ndim = nd
+        a.f = self._field_obj(args['fields'][0], dev, args['resident'], hold, written=True).ptr
+        a.halo = p['so']
+        taps = (L_.Tap * len(args['taps']))()
+        for i, (t, o, c) in enumerate(args['taps']):
+            taps[i].tshift = int(t)
+            for d in range(nd):
+                taps[i].off[d] = int(o[d])
+            taps[i].coef = c
+        a.ntaps = len(args['taps'])
+        a.taps = taps
+        a.wshift = p['wshift']
+        lo, hi = args['lo'] + [0] * (3 - nd), args['hi'] + [0] * (3 - nd)
+        a.x_m, a.x_M, a.y_m, a.y_M, a.z_m, a.z_M = lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]
+        a.time_m, a.time_M = args['time_m'], args['time_M']
+        a.deviceid = dev
+        timers = L_.Profiler()
+        a.timers = ctypes.pointer(timers)
+        t0 = _time.perf_counter()
+        rc = L.b2_linear_forward(ctypes.byref(a))
+        t_wall = _time.perf_counter() - t0
+        for fn in args['post']:
             fn()
         return self._finish(rc, L, timers, args, 1, t_wall)
 

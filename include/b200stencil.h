@@ -186,6 +186,32 @@ struct b2_tti_args {
 };
 int b2_tti_forward(const struct b2_tti_args *a);
 
+/* ---- generic explicit update with constant coefficients --------------------------------------
+ * Any Operator whose single equation is  f[t + wshift][p] = sum_k coef_k * f[t + tshift_k][p + off_k]
+ * with coefficients that do not depend on position (Constants, spacings, dt) — e.g. the reference's
+ * 2-D diffusion example `Eq(u.dt, a*(u.dx2 + u.dy2))` solved for u.forward
+ * (examples/cfd/example_diffusion.py:120-133, BASELINE config 1). Replaces the generated `Kernel`
+ * function of such operators. Cells outside [x_m..x_M] x ... are not written (SubDomain semantics). */
+struct b2_tap {
+    int tshift;                       /* time level read: t + tshift                           */
+    int off[3];                       /* space offsets (unused dims 0)                          */
+    float coef;
+};
+#define B2_MAX_TAPS 64
+struct b2_linear_args {
+    int ndim;                         /* 1, 2 or 3                                              */
+    struct b2_dataobj *f;             /* (tsize, x[, y[, z]]) with halo                         */
+    int halo;                         /* halo width of f on every space dimension               */
+    int ntaps;
+    const struct b2_tap *taps;
+    int wshift;                       /* +1: f.forward is written, -1: f.backward               */
+    int x_m, x_M, y_m, y_M, z_m, z_M;
+    int time_m, time_M;
+    int deviceid;
+    struct b2_profiler *timers;       /* may be NULL; section0 accumulates the loop time        */
+};
+int b2_linear_forward(const struct b2_linear_args *a);
+
 /* ---- halo exchange under x-slab decomposition (replaces `haloupdate0`/`sendrecv0`,
  *      devito/mpi/routines.py:285-552; printed examples/mpi/overview.ipynb:503-560) -------- */
 /* NCCL bootstrap: rank 0 calls b2_nccl_unique_id, the 128 bytes are broadcast by the host

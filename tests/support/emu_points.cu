@@ -116,3 +116,44 @@ extern "C" int emu_snapshot(const float *slot, const int *alloc, int so, float *
             for (int z = 0; z < k.n2; ++z) snapshot_point(k, x, y, z);
     return 0;
 }
+
+// Generic constant-coefficient update, same marshalling as b2_linear_forward (b2_api_linear.cu)
+extern "C" int emu_linear_steps(float *f, int tsize, int ndim, const int *size /* ndim */, int halo, int ntaps,
+                                const int *tshift, const int *off /* ntaps x 3 */, const float *coef,
+                                int wshift, const int *lo_in, const int *hi_in, int time_m, int time_M) {
+    int alloc[3] = {1, 1, 1}, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, hal[3] = {0, 0, 0};
+    for (int d = 0; d < ndim; ++d) {
+        const int di = 3 - ndim + d;
+        alloc[di] = size[d]; lo[di] = lo_in[d]; hi[di] = hi_in[d]; hal[di] = halo;
+    }
+    LinK k;
+    k.sy = alloc[2];
+    k.sx = (long long)alloc[1] * alloc[2];
+    const size_t slot = (size_t)alloc[0] * alloc[1] * alloc[2];
+    k.n0 = hi[0] - lo[0] + 1; k.n1 = hi[1] - lo[1] + 1; k.n2 = hi[2] - lo[2] + 1;
+    k.o0 = lo[0] + hal[0]; k.o1 = lo[1] + hal[1]; k.o2 = lo[2] + hal[2];
+    k.ntaps = ntaps;
+    int shifts[4], nshift = 0;
+    for (int i = 0; i < ntaps; ++i) {
+        int s = -1;
+        for (int j = 0; j < nshift; ++j) if (shifts[j] == tshift[i]) s = j;
+        if (s < 0) { shifts[nshift] = tshift[i]; s = nshift++; }
+        k.sel[i] = s;
+        long long delta = 0;
+        for (int d = 0; d < ndim; ++d) {
+            const int di = 3 - ndim + d;
+            delta += (long long)off[3 * i + d] * (di == 0 ? k.sx : di == 1 ? k.sy : 1);
+        }
+        k.delta[i] = delta;
+        k.coef[i] = coef[i];
+    }
+    for (int time = time_m; time <= time_M; ++time) {
+        k.out = f + (size_t)((((time + wshift) % tsize) + tsize) % tsize) * slot;
+        for (int j = 0; j < 4; ++j)
+            k.lvl[j] = f + (size_t)((((time + shifts[j < nshift ? j : 0]) % tsize) + tsize) % tsize) * slot;
+        for (int x = 0; x < k.n0; ++x)
+            for (int y = 0; y < k.n1; ++y)
+                for (int z = 0; z < k.n2; ++z) linear_point(k, x, y, z);
+    }
+    return 0;
+}

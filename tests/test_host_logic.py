@@ -116,9 +116,10 @@ def test_recogniser_accepts_the_reference_formulations():
 def test_recogniser_rejects_other_equations():
     g = Grid(shape=(16, 16), extent=(1., 1.))
     u = TimeFunction(name='u', grid=g, time_order=1, space_order=2)
+    # a constant-coefficient explicit update is not a wave scheme: it goes to the generic stencil entry
     op = Operator([Eq(u.forward, u + 0.1 * u.laplace)], subs=g.spacing_map)
-    assert op.backend == 'numpy-interpreter'
-    # a wave equation with a wrong coefficient is NOT silently mapped to the kernel
+    assert op.backend == 'cuda-sm100a' and op._plan['kind'] == 'linear'
+    # a wave equation with a wrong coefficient is NOT silently mapped to the wave kernels
     v = TimeFunction(name='v', grid=g, time_order=2, space_order=4)
     m = Function(name='m', grid=g, space_order=4)
     m.data[:] = 1.0
@@ -127,27 +128,39 @@ def test_recogniser_rejects_other_equations():
     assert op2.backend == 'numpy-interpreter'
 
 
-def test_diffusion_config1_matches_numpy_twin():
-    """BASELINE config 1: 2-D diffusion, Laplace so=2 (NumPy twin: examples/cfd/example_diffusion.py:61-83)."""
-    n, nt, a = 64, 20, 0.5
+def test_diffusion_config1_is_on_the_generic_stencil_path():
+    """BASELINE config 1: 2-D diffusion, Laplace so=2 (examples/cfd/example_diffusion.py:120-133). The
+    operator is recognised as a constant-coefficient explicit update and marshalled for
+    `b2_linear_forward`; the kernel's point code against the NumPy twin is tests/test_zz_emulation.py,
+    the run on the GPU tests/test_zz_linear.py."""
+    n, a = 64, 0.5
     g = Grid(shape=(n, n), extent=(2., 2.))
     u = TimeFunction(name='u', grid=g, time_order=1, space_order=2)
-    init = np.zeros((n, n), dtype=np.float32)
-    init[n // 4:n // 2, n // 4:n // 2] = 1.0
-    u.data[0] = init
     hx, hy = g.spacing
     dt = 0.2 * hx * hy / a
     eq = Eq(u.forward, solve(Eq(u.dt, a * u.laplace), u.forward), subdomain=g.interior)
     op = Operator([eq])
-    op(time_M=nt - 1, dt=dt)
-    ref = init.astype(np.float64)
-    for _ in range(nt):
-        new = ref.copy()
-        new[1:-1, 1:-1] = ref[1:-1, 1:-1] + a * dt * (
-            (ref[2:, 1:-1] - 2 * ref[1:-1, 1:-1] + ref[:-2, 1:-1]) / hx ** 2 +
-            (ref[1:-1, 2:] - 2 * ref[1:-1, 1:-1] + ref[1:-1, :-2]) / hy ** 2)
-        ref = new
-    assert rel_linf(u.data[nt % 2], ref) < 1e-5
+    assert op.backend == 'cuda-sm100a' and op._plan['kind'] == 'linear'
+    args = op.arguments(time_M=19, dt=dt)
+    taps = {(t, o): c for t, o, c in args['taps']}
+    dtf = float(np.float32(dt))
+    want = {(0, (0, 0)): 1 - 2 * a * dtf / hx ** 2 - 2 * a * dtf / hy ** 2,
+            (0, (1, 0)): a * dtf / hx ** 2, (0, (-1, 0)): a * dtf / hx ** 2,
+            (0, (0, 1)): a * dtf / hy ** 2, (0, (0, -1)): a * dtf / hy ** 2}
+    assert set(taps) == set(want)
+    for k in want:
+        assert abs(taps[k] - want[k]) < 1e-6 * max(1.0, abs(want[k]))
+    assert (args['lo'], args['hi'], args['time_m'], args['time_M']) == ([1, 1], [n - 2, n - 2], 0, 19)
+    # the reference's own call: `op.apply(u=u, t=timesteps, dt=dt)` on the whole grid
+    op2 = Operator(Eq(u.forward, solve(Eq(u.dt, a * (u.dx2 + u.dy2)), u.forward)))
+    a2 = op2.arguments(u=u, t=500, dt=dt)
+    assert (a2['lo'], a2['hi'], a2['time_M']) == ([0, 0], [n - 1, n - 1], 500)
+    # it fails loudly without a GPU — no interpreter fallback for a recognised operator
+    from devito_b200.exceptions import BackendUnavailable
+    from devito_b200 import _lib
+    if not _lib.have_gpu():
+        with pytest.raises(BackendUnavailable):
+            op(time_M=3, dt=dt)
 
 
 def test_interpolation_and_injection_interpreter():

@@ -42,6 +42,9 @@ def emu(tmp_path_factory):
     lib.emu_born_step.restype = ctypes.c_int
     lib.emu_snapshot.argtypes = [fp, ip, ctypes.c_int, fp, ip, ctypes.c_int, ip, ip]
     lib.emu_snapshot.restype = ctypes.c_int
+    lib.emu_linear_steps.argtypes = [fp, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int, ctypes.c_int, ip, ip, fp,
+                                     ctypes.c_int, ip, ip, ctypes.c_int, ctypes.c_int]
+    lib.emu_linear_steps.restype = ctypes.c_int
     return lib
 
 
@@ -158,3 +161,39 @@ def test_snapshot_point_kernel(emu):
     want = np.full_like(snap, -7.0)
     want[tuple(slice(b.start + sh, b.stop + sh) for b in box)] = slot[tuple(slice(b.start + so, b.stop + so) for b in box)]
     assert np.array_equal(snap, want)
+
+
+def test_linear_point_kernel_runs_the_diffusion_example(emu):
+    """BASELINE config 1 through the generic stencil kernel's point code: the operator's own taps
+    (from the recogniser) applied by `linear_point` reproduce the reference's NumPy twin
+    (examples/cfd/example_diffusion.py:61-83)."""
+    from devito_b200 import Eq, Grid, Operator, TimeFunction, solve
+    n, nt, a = 64, 20, 0.5
+    g = Grid(shape=(n, n), extent=(2., 2.))
+    u = TimeFunction(name='u', grid=g, time_order=1, space_order=2)
+    hx, hy = g.spacing
+    dt = 0.2 * hx * hy / a
+    op = Operator([Eq(u.forward, solve(Eq(u.dt, a * u.laplace), u.forward), subdomain=g.interior)])
+    args = op.arguments(time_M=nt - 1, dt=dt)
+    init = np.zeros((n, n), dtype=np.float32)
+    init[n // 4:n // 2, n // 4:n // 2] = 1.0
+    so = 2
+    f = np.zeros((2, n + 2 * so, n + 2 * so), dtype=np.float32)
+    f[0, so:-so, so:-so] = init
+    f[1, so:-so, so:-so] = init                       # cells outside the interior box are never written
+    tshift = np.array([t for t, _, _ in args['taps']], dtype=np.int32)
+    off = np.zeros((len(tshift), 3), dtype=np.int32)
+    for i, (_, o, _) in enumerate(args['taps']):
+        off[i, :2] = o
+    coef = np.array([c for _, _, c in args['taps']], dtype=np.float32)
+    emu.emu_linear_steps(_fp(f), 2, 2, _ip(np.array(f.shape[1:], dtype=np.int32)), so, len(tshift), _ip(tshift),
+                         _ip(off), _fp(coef), op._plan['wshift'], _ip(np.array(args['lo'], dtype=np.int32)),
+                         _ip(np.array(args['hi'], dtype=np.int32)), args['time_m'], args['time_M'])
+    ref = init.astype(np.float64)
+    for _ in range(nt):
+        new = ref.copy()
+        new[1:-1, 1:-1] = ref[1:-1, 1:-1] + a * dt * (
+            (ref[2:, 1:-1] - 2 * ref[1:-1, 1:-1] + ref[:-2, 1:-1]) / hx ** 2 +
+            (ref[1:-1, 2:] - 2 * ref[1:-1, 1:-1] + ref[1:-1, :-2]) / hy ** 2)
+        ref = new
+    assert rel_linf(f[nt % 2, so:-so, so:-so], ref) < 1e-5
