@@ -89,6 +89,21 @@ def kat3d_fs(interpolation, name):
          u_last=np.array(u.data[(g.nt - 1) % 3, ::3, ::3, ::3]))
 
 
+def adjoint_variant(name, so, n, nbl, tn, kernel='OT2', **kw):
+    """Forward then adjoint for the free-surface / OT4 variants of the acoustic operators."""
+    from examples.seismic import demo_model, setup_geometry
+    from examples.seismic.acoustic import AcousticWaveSolver
+    model = demo_model('layers-isotropic', spacing=(10., 10., 10.), shape=(n, n, n), nbl=nbl, space_order=so,
+                       dtype=np.float32, nlayers=2, **kw)
+    geometry = setup_geometry(model, tn)
+    solver = AcousticWaveSolver(model, geometry, space_order=so, kernel=kernel)
+    rec, u, _ = solver.forward()
+    srca, v, _ = solver.adjoint(rec)
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(model.critical_dt), dt_run=np.float32(solver.dt),
+         nt=geometry.nt, vp=np.array(model.vp.data), rec=np.array(rec.data), srca=np.array(srca.data),
+         v=np.array(v.data))
+
+
 def adjoint(name, so, n, nbl, tn):
     """Forward then adjoint (acoustic/wavesolver.py:118-156): receiver data back-propagated."""
     from devito import norm
@@ -202,7 +217,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'born', 'snap', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'born', 'snap', 'adjvar', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'fs' in which:
@@ -215,6 +230,9 @@ if __name__ == '__main__':
         acoustic('iso3d_so8_ot4', so=8, n=20, nbl=8, tn=150.0, kernel='OT4')
         acoustic('iso3d_so4_ot4_layers', so=4, n=20, nbl=8, tn=150.0, kernel='OT4',
                  preset='layers-isotropic', nlayers=3)
+    if 'adjvar' in which:
+        adjoint_variant('adj3d_so4_fs', so=4, n=20, nbl=8, tn=120.0, fs=True)
+        adjoint_variant('adj3d_so4_ot4', so=4, n=20, nbl=8, tn=120.0, kernel='OT4')
     if 'snap' in which:
         snapshots('snap3d_so4', so=4, n=20, nbl=8, tn=150.0, factor=4)
     if 'born' in which:

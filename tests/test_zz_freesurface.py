@@ -90,3 +90,15 @@ def test_free_surface_known_answer_norms(name, interp, kat):
     assert np.isclose(norm(rec), kat, rtol=1e-3, atol=0)
     assert rel_linf(np.asarray(rec.data)[::4, ::7], g['rec']) < 1e-4
     assert rel_linf(np.asarray(u.data)[(geometry.nt - 1) % 3, ::3, ::3, ::3], g['u_last']) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.pending
+def test_free_surface_adjoint_vs_reference_golden():
+    g = load_golden('adj3d_so4_fs')
+    model, geometry, solver = _solver(so=4, n=int(g['n']), nbl=int(g['nbl']), tn=float(g['tn']), nlayers=2)
+    rec, u, _ = solver.forward()
+    assert rel_linf(rec.data, g['rec']) < 1e-5
+    srca, v, _ = solver.adjoint(rec)
+    assert rel_linf(v.data, g['v']) < 1e-4                 # non-deterministic atomics in the reference
+    assert rel_linf(srca.data, g['srca']) < 1e-4

@@ -61,3 +61,20 @@ def test_ot4_vs_reference_golden(name, preset, so):
     rec, u, _ = solver.forward()
     assert rel_linf(u.data, g['u']) < 1e-5
     assert rel_linf(rec.data, g['rec']) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.pending
+def test_ot4_adjoint_vs_reference_golden():
+    from devito_b200.seismic import AcousticWaveSolver, demo_model, setup_geometry
+    g = load_golden('adj3d_so4_ot4')
+    n, nbl = int(g['n']), int(g['nbl'])
+    model = demo_model('layers-isotropic', shape=(n,) * 3, spacing=(10.,) * 3, nbl=nbl, space_order=4, nlayers=2)
+    geometry = setup_geometry(model, float(g['tn']))
+    solver = AcousticWaveSolver(model, geometry, space_order=4, kernel='OT4')
+    assert np.float32(solver.dt) == g['dt_run']
+    rec, u, _ = solver.forward()
+    assert rel_linf(rec.data, g['rec']) < 1e-5
+    srca, v, _ = solver.adjoint(rec)
+    assert rel_linf(v.data, g['v']) < 1e-4
+    assert rel_linf(srca.data, g['srca']) < 1e-4
