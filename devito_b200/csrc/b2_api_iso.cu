@@ -230,6 +230,13 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     }
     if ((rc = sparse_stage_in(a->src, nd, src, true))) return cleanup(rc);
     if ((rc = sparse_stage_in(a->rec, nd, rec, true))) return cleanup(rc);
+    // the support of a sparse point reaches r cells beyond the iterated box: it must fit in the halo
+    // (devito/operations/interpolators.py:28-37 `check_radius`)
+    if ((src.present && src.r > so) || (rec.present && rec.r > so)) {
+        set_error("b2_iso_forward: sparse radius %d exceeds the halo (space_order %d)",
+                  src.present && src.r > so ? src.r : rec.r, so);
+        return cleanup(B2_ERR_INVALID);
+    }
     if (a->grad || a->usave) {
         if (!a->grad || !a->usave || nd != 3) {
             set_error("b2_iso_forward: the imaging condition needs both grad and usave (3-D)");

@@ -101,7 +101,10 @@ extern "C" int b2_linear_forward(const struct b2_linear_args *a) {
     dim3 grid((k.n2 + 63) / 64, (k.n1 + 3) / 4, (unsigned)std::min(k.n0, 65535));
     float *base = (float *)f.d;
     auto slot_of = [&](int time, int shift) { return (((time + shift) % T) + T) % T; };
-    for (int time = a->time_m; time <= a->time_M; ++time) {
+    // an update of `f.backward` (wshift = -1) runs from time_M down to time_m, like the reference's
+    // backward-in-time loop (devito/ir/support/space.py: Backward direction)
+    const int dirn = a->wshift;
+    for (int time = dirn > 0 ? a->time_m : a->time_M; dirn > 0 ? time <= a->time_M : time >= a->time_m; time += dirn) {
         k.out = base + (size_t)slot_of(time, a->wshift) * slot;
         for (int j = 0; j < nshift; ++j) k.lvl[j] = base + (size_t)slot_of(time, shifts[j]) * slot;
         for (int j = nshift; j < 4; ++j) k.lvl[j] = k.lvl[0];

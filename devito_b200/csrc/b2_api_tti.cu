@@ -58,6 +58,12 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
     }
     if ((rc = sparse_stage_in(a->src, 3, src, true))) return cleanup(rc);
     if ((rc = sparse_stage_in(a->rec, 3, rec, true))) return cleanup(rc);
+    // devito/operations/interpolators.py:28-37 `check_radius`
+    if ((src.present && src.r > so) || (rec.present && rec.r > so)) {
+        set_error("b2_tti_forward: sparse radius %d exceeds the halo (space_order %d)",
+                  src.present && src.r > so ? src.r : rec.r, so);
+        return cleanup(B2_ERR_INVALID);
+    }
 
     const int lo_in[3] = {a->x_m, a->y_m, a->z_m};
     const int hi_in[3] = {a->x_M, a->y_M, a->z_M};

@@ -177,6 +177,21 @@ class Interpreter:
                             hi = max(hi, int(idx.shift))
         return lo, hi
 
+    def direction(self):
+        """+1 / -1: the reference iterates time backward when the updates write an earlier level than they
+        read (`f.backward = ...`, devito/ir/support/space.py Backward); a mix is refused."""
+        shifts = set()
+        for kind, _, obj, lhs, rhs in self.items:
+            if kind == 'eq' and lhs.is_Access and getattr(lhs.function, 'is_TimeFunction', False):
+                idx = lhs.index_objs[0]
+                if idx.absolute is None:
+                    shifts.add(int(idx.shift))
+        if any(s < 0 for s in shifts):
+            if any(s > 0 for s in shifts):
+                raise InvalidArgument("forward and backward time updates in one operator")
+            return -1
+        return 1
+
     # -- iteration space of one equation ---------------------------------------------------------
     def _ranges(self, eq, lhs, bounds):
         f = lhs.function
@@ -330,6 +345,8 @@ class Interpreter:
     # -- driver ------------------------------------------------------------------------------------
     def run(self, time_m, time_M, scalars, bounds):
         steps = range(time_m, time_M + 1) if self.has_time else [0]
+        if self.has_time and self.direction() < 0:
+            steps = reversed(steps)
         for time in steps:
             for kind, _, obj, lhs, rhs in self.items:
                 if kind == 'eq':

@@ -660,6 +660,14 @@ class Operator:
                 raise _Unrecognised("cannot identify the damping field")
         return m_role, d_role
 
+    @staticmethod
+    def _check_radius(sf, fields):
+        """devito/operations/interpolators.py:28-37 `check_radius`: the support of a sparse point reaches
+        `r` cells beyond the domain, so it must fit in the halo of every field it touches."""
+        so = min(f.space_order for f in fields)
+        if so < sf.r:
+            raise ValueError(f"Space order {so} too small for interpolation r {sf.r}")
+
     def _attach_sparse(self, plan, injs, itps, fields, funcs, consts, syms, m_role):
         grid = plan['grid']
         dtsym = plan['dt']
@@ -669,6 +677,7 @@ class Operator:
             sf = inj.sfunction
             if not isinstance(sf, SparseTimeFunction) or sf.interpolation not in ('linear', 'sinc'):
                 raise _Unrecognised("unsupported sparse function for injection")
+            self._check_radius(sf, fields)
             tgt = {id(f) for f in fields}
             if {id(a.function) for a in inj.fields} != tgt:
                 raise _Unrecognised("injection targets differ from the updated fields")
@@ -704,6 +713,7 @@ class Operator:
             sf = itp.sfunction
             if not isinstance(sf, SparseTimeFunction) or sf.interpolation not in ('linear', 'sinc'):
                 raise _Unrecognised("unsupported sparse function for interpolation")
+            self._check_radius(sf, fields)
             if itp.increment:
                 raise _Unrecognised("incremental interpolation")
             ex = itp.expr.evaluate
@@ -1350,7 +1360,7 @@ class Operator:
         hold.append(ob)
         return ob
 
-    def _sparse_obj(self, sf, grid, hold, written=False, post=None):
+    def _sparse_obj(self, sf, grid, hold, written=False, post=None, trange=None):
         """b2_sparse for a SparseTimeFunction. Under x-slab decomposition every rank holds all
         points (positions are made relative to the local slab; the kernels' bound guards drop
         what lies outside). A *written* function (receivers) is evaluated only for the points
@@ -1370,21 +1380,26 @@ class Operator:
                 idx = np.nonzero(mask)[0]
                 gp = np.ascontiguousarray(gp[idx])
                 ws = [np.ascontiguousarray(w[idx]) for w in ws]
-                local = np.zeros((host.shape[0], len(idx)), dtype=host.dtype)
+                # start from the caller's traces: rows outside [time_m, time_M] are not this call's to touch
+                # (restart over time sub-ranges keeps what earlier calls recorded, like the reference)
+                local = np.ascontiguousarray(host[:, idx])
                 full = host
+                t_lo, t_hi = trange if trange is not None else (0, host.shape[0] - 1)
+                t_lo, t_hi = max(0, t_lo), min(host.shape[0] - 1, t_hi)
 
                 def merge():
-                    full[...] = 0
-                    full[:, idx] = local
                     import torch
                     import torch.distributed as tdist
-                    t = torch.from_numpy(full)
+                    blk = np.zeros((t_hi - t_lo + 1, full.shape[1]), dtype=full.dtype)
+                    blk[:, idx] = local[t_lo:t_hi + 1]
+                    t = torch.from_numpy(blk)
                     if tdist.get_backend() == 'nccl':
                         tg = t.cuda()
                         tdist.all_reduce(tg)
                         t.copy_(tg.cpu())
                     else:
                         tdist.all_reduce(t)
+                    full[t_lo:t_hi + 1] = blk
                 if post is not None:
                     post.append(merge)
                 host = local
@@ -1483,7 +1498,8 @@ class Operator:
         a.time_m, a.time_M = args['time_m'], args['time_M']
         s = self._sparse_obj(args['src'], grid, hold)
         post = []
-        r = self._sparse_obj(args['rec'], grid, hold, written=True, post=post)
+        r = self._sparse_obj(args['rec'], grid, hold, written=True, post=post,
+                             trange=(args['time_m'], args['time_M']))
         a.src = ctypes.pointer(s) if s is not None else None
         a.rec = ctypes.pointer(r) if r is not None else None
         a.rec_toff = p['rec_toff']
@@ -1640,7 +1656,8 @@ class Operator:
         a.time_m, a.time_M = args['time_m'], args['time_M']
         s = self._sparse_obj(args['src'], grid, hold)
         post = []
-        r = self._sparse_obj(args['rec'], grid, hold, written=True, post=post)
+        r = self._sparse_obj(args['rec'], grid, hold, written=True, post=post,
+                             trange=(args['time_m'], args['time_M']))
         a.src = ctypes.pointer(s) if s is not None else None
         a.rec = ctypes.pointer(r) if r is not None else None
         a.rec_toff = p['rec_toff']

@@ -59,6 +59,17 @@ class _SparseOp:
         return list(other) + [self]
 
 
+def _check_radius(sfunction, *exprs):
+    """devito/operations/interpolators.py:28-37 `check_radius`: the support of a point reaches `r` cells
+    beyond the domain, so every dense function involved needs at least `r` halo points."""
+    r = sfunction.r
+    orders = {n.function.space_order for e in exprs for n in as_expr(e).preorder()
+              if getattr(n, 'is_Access', False) and not getattr(n.function, 'is_SparseFunction', False)}
+    so = min(orders or {r})
+    if so < r:
+        raise ValueError(f"Space order {so} too small for interpolation r {r}")
+
+
 class Injection(_SparseOp):
     """`field[cells] += weights * expr` for every sparse point (interpolators.py:127-189)."""
 
@@ -67,6 +78,7 @@ class Injection(_SparseOp):
         self.fields = tuple(field) if isinstance(field, (tuple, list)) else (field,)
         self.exprs = tuple(expr) if isinstance(expr, (tuple, list)) else (expr,) * len(self.fields)
         self.exprs = tuple(as_expr(e) for e in self.exprs)
+        _check_radius(sfunction, *self.fields, *self.exprs)
         self.implicit_dims = implicit_dims
 
     def __repr__(self):
@@ -79,6 +91,7 @@ class Interpolation(_SparseOp):
     def __init__(self, sfunction, expr, increment=False, implicit_dims=None):
         self.sfunction = sfunction
         self.expr = as_expr(expr)
+        _check_radius(sfunction, self.expr)
         self.increment = increment
         self.implicit_dims = implicit_dims
 

@@ -448,6 +448,9 @@ class FieldStorage:
         if self.dev is None or self.dev.device != device:
             if self._host is None:
                 self.dev = torch.zeros(self.shape, dtype=tdt, device=device)
+                # the fill runs on torch's current stream, the library launches on its own non-blocking
+                # stream: finish the fill before anyone else touches the array
+                torch.cuda.current_stream(device).synchronize()
                 self.dev_valid = True
                 self.host_valid = False
                 return self.dev

@@ -251,3 +251,31 @@ def test_derivatives_are_exact_on_polynomials(so, deriv, attr):
     got = np.asarray(g.data)
     want = exact[so:-so, so:-so]
     assert np.max(np.abs(got - want)) <= 1e-7 * np.max(np.abs(want))
+
+
+def test_interpreter_runs_backward_updates_backward_in_time():
+    """`f.backward = ...` is stepped from time_M down to time_m like the reference's backward loop
+    (the interpreter iterated forward and read levels nobody had produced)."""
+    g = Grid(shape=(8, 8))
+    nt = 6
+    f = TimeFunction(name='f', grid=g, time_order=1, space_order=2, save=nt)
+    c = Function(name='c', grid=g, space_order=2)           # position-dependent factor: not the linear path
+    c.data[:] = 2.0
+    f.data[nt - 1] = 1.0
+    op = Operator([Eq(f.backward, c * f)])
+    assert op.backend == 'numpy-interpreter'
+    op(time_m=1, time_M=nt - 1)
+    for k in range(nt):
+        assert np.allclose(f.data[k], 2.0 ** (nt - 1 - k))
+
+
+def test_sparse_radius_must_fit_the_halo():
+    """devito/operations/interpolators.py:28-37 `check_radius`."""
+    from devito_b200 import SparseTimeFunction
+    g = Grid(shape=(12, 12, 12))
+    u2 = TimeFunction(name='u2', grid=g, time_order=2, space_order=2)
+    s = SparseTimeFunction(name='s', grid=g, npoint=1, nt=4, interpolation='sinc', r=4)
+    with pytest.raises(ValueError):
+        s.inject(field=u2.forward, expr=s)
+    with pytest.raises(ValueError):
+        s.interpolate(expr=u2)
