@@ -394,6 +394,15 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     if (timing && !per_step_events) ev_begin = se.next();
 
     const bool p2p = a->halo && halo_p2p_active(a->halo, p.u);
+    // halo step fused into the sweep kernel (peer stores + flag acquire inside k_iso_tma)
+    const bool fused = p2p && halo_fused_ok(a->halo, p) && !a->free_surface;
+    IsoFuse fz;
+    if (fused && (rc = halo_fuse_desc(a->halo, p, fz))) return cleanup(rc);
+    if (a->halo && nd == 3 && (a->x_m != 0 || a->x_M != p.a[0] - 2 * so - 1)) {
+        set_error("b2_iso_forward: the decomposed dimension must be iterated over the whole slab "
+                  "(x_m=%d, x_M=%d, %d owned planes)", a->x_m, a->x_M, p.a[0] - 2 * so);
+        return cleanup(B2_ERR_INVALID);
+    }
     if (a->halo) a->halo->p2p_primed = false;       // first step of a call exchanges through NCCL
     const int dir = a->adjoint ? -1 : 1;
     for (int time = a->adjoint ? a->time_M : a->time_m; a->adjoint ? time >= a->time_m : time <= a->time_M;
@@ -402,7 +411,14 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         const int t1 = (((time + dir) % T) + T) % T;     // written
         const int t2 = (((time - dir) % T) + T) % T;     // the other time level read
         if (per_step_events) se.next();
-        if (a->halo) {
+        if (fused) {
+            if ((rc = halo_step_iso_fused(a->halo, p, t0, t2, t1))) return cleanup(rc);
+            // the injection below must reach the copies of my boundary planes in the neighbours' halos
+            g.peer_lo = fz.peer_lo; g.peer_hi = fz.peer_hi;
+            g.off_lo = (long long)t1 * fz.slot_lo + (long long)(p.o[0] + fz.n_lo) * p.sx;
+            g.off_hi = (long long)t1 * fz.slot_hi + (long long)(p.o[0] - p.n[0]) * p.sx;
+            g.nown = p.n[0]; g.pw = p.radius[0];
+        } else if (a->halo) {
             if ((rc = halo_exchange_and_step_iso(a->halo, p, t0, t2, t1))) return cleanup(rc);
         } else {
             if ((rc = iso_step(p, t0, t2, t1, 0, p.n[0]))) return cleanup(rc);
@@ -412,7 +428,11 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         float *f1 = p.u + (size_t)t1 * p.slot_elems;
         if ((rc = launch_inject(src, g, f1, nullptr, time, p.param_kind, p.param, scalar_scale, dt2)))
             return cleanup(rc);
-        if (p2p) {
+        if (fused) {
+            // the sweep stored the boundary planes, the injection patched them: release the flags
+            if ((rc = halo_fused_signal(a->halo))) return cleanup(rc);
+            if (a->rec_toff && rec.present && (rc = halo_p2p_wait(a->halo))) return cleanup(rc);
+        } else if (p2p) {
             // boundary planes of u[t1] are final: store them into the neighbours' halos, signal
             if ((rc = halo_p2p_publish(a->halo, p.u, nullptr, p.slot_elems, t1, (size_t)p.sx, p.o[0], p.n[0],
                                        p.radius[0])))

@@ -9,6 +9,7 @@
 // devito/types/dense.py:1256-1259). Neighbours at the physical boundary are skipped
 // (MPI_PROC_NULL in the reference, routines.py:429-433).
 #include "b2_halo.cuh"
+#include "b2_ptx.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -91,18 +92,21 @@ int halo_enqueue(b2_halo_ctx *ctx, float *base, size_t plane_elems, int lo, int 
 }
 
 // ---- peer-memory path ----------------------------------------------------------------------------
-__global__ void k_flag_wait(volatile int *flags, int want_left, int want_right) {
+// Flags live in plain device memory that the neighbours map through CUDA IPC. The writer orders its
+// peer stores (earlier kernels / copies of the same stream, or its own stores) before the flag with
+// a system-scope release; the reader acquires at system scope before touching the halo planes.
+__global__ void k_flag_wait(const int *flags, int want_left, int want_right) {
     // one thread; spins until both neighbours have signalled the required step
-    if (want_left >= 0) while (flags[0] < want_left) {}
-    if (want_right >= 0) while (flags[1] < want_right) {}
-    __threadfence_system();
+    if (want_left >= 0) while (b2ptx::ld_acquire_sys(flags + 0) < want_left) __nanosleep(40);
+    if (want_right >= 0) while (b2ptx::ld_acquire_sys(flags + 1) < want_right) __nanosleep(40);
 }
 
 __global__ void k_flag_signal(int *left_remote, int *right_remote, int value) {
-    __threadfence_system();                    // order the preceding peer stores before the flag
-    if (left_remote) *reinterpret_cast<volatile int *>(left_remote) = value;
-    if (right_remote) *reinterpret_cast<volatile int *>(right_remote) = value;
-    __threadfence_system();
+    // everything this stream did before (sweep kernel with its peer stores, injection, copies) is
+    // ordered before the flag stores
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    if (left_remote) b2ptx::st_release_sys(left_remote, value);
+    if (right_remote) b2ptx::st_release_sys(right_remote, value);
 }
 
 // After the boundary planes of time slot `slot1` are final (stencil strips + injection), store them
@@ -211,6 +215,58 @@ int halo_exchange_and_step_iso(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t
     B2_CUDA(cudaStreamWaitEvent(main, ctx->ev_comm, 0), B2_ERR_COMM);
     if ((rc = iso_step(p, t0, t2, t1, 0, R))) return rc;
     if ((rc = iso_step(p, t0, t2, t1, n - R, R))) return rc;
+    return B2_OK;
+}
+
+// ---- fused path (isotropic TMA sweep): ONE launch per step ----------------------------------------
+// The sweep kernel itself stores its boundary planes into the neighbours' halos and acquires the
+// neighbours' flags right before it reads their planes (b2_iso.cu, IsoTK). What is left on the host
+// side is the flag release after the step's injection (halo_fused_signal). The first step of a call
+// has no flags to rely on: it exchanges u[t0] through NCCL like the fallback path.
+bool halo_fused_ok(b2_halo_ctx *ctx, const IsoPlan &p) {
+    const char *e = getenv("B2_HALO_FUSED");          // read per call: tests and bench.py toggle the data path
+    const bool off = e && atoi(e) == 0;
+    return !off && halo_p2p_active(ctx, p.u) && p.use_tma && p.n[0] >= 2 * p.radius[0];
+}
+
+int halo_fuse_desc(b2_halo_ctx *ctx, const IsoPlan &p, IsoFuse &f) {
+    const b2_halo_ctx::Reg *rg = ctx->find(p.u);
+    if (!rg) { set_error("fused halo: field not registered"); return B2_ERR_COMM; }
+    const long long plane = p.sx;
+    f.peer_lo = (float *)rg->left;
+    f.peer_hi = (float *)rg->right;
+    f.n_lo = rg->n_left;
+    f.n_hi = rg->n_right;
+    f.slot_lo = (long long)(rg->n_left + 2 * p.o[0]) * plane;     // halo width == p.o[0] (x_m == 0 is enforced)
+    f.slot_hi = (long long)(rg->n_right + 2 * p.o[0]) * plane;
+    f.flag_lo = ctx->flag_left_remote ? ctx->flags_local + 0 : nullptr;
+    f.flag_hi = ctx->flag_right_remote ? ctx->flags_local + 1 : nullptr;
+    f.want = -1;
+    return B2_OK;
+}
+
+int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1) {
+    IsoFuse f;
+    int rc = halo_fuse_desc(ctx, p, f);
+    if (rc) return rc;
+    if (ctx->p2p_primed) {
+        f.want = ctx->step;               // the neighbours released `step` after publishing u[t0]
+    } else {
+        cudaStream_t main = stream();
+        B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
+        B2_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0), B2_ERR_COMM);
+        if ((rc = halo_enqueue(ctx, p.u + (size_t)t0 * p.slot_elems, (size_t)p.sx, p.o[0], p.n[0], p.radius[0])))
+            return rc;
+        B2_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream), B2_ERR_COMM);
+        B2_CUDA(cudaStreamWaitEvent(main, ctx->ev_comm, 0), B2_ERR_COMM);
+    }
+    return iso_step_fused(p, t0, t2, t1, f);
+}
+
+int halo_fused_signal(b2_halo_ctx *ctx) {
+    int rc = p2p_signal(ctx);
+    if (rc) return rc;
+    ctx->p2p_primed = true;
     return B2_OK;
 }
 

@@ -54,6 +54,13 @@ int halo_p2p_publish(b2_halo_ctx *ctx, const float *f0, const float *f1, size_t 
 // boundary strips of the next step and once after the time loop
 int halo_p2p_drain(b2_halo_ctx *ctx);
 
+// Fused path (isotropic TMA sweep): the kernel stores its boundary planes into the neighbours' halos and
+// acquires their flags itself; halo_fused_signal releases this rank's flags after the step's injection.
+bool halo_fused_ok(b2_halo_ctx *ctx, const IsoPlan &p);
+int halo_fuse_desc(b2_halo_ctx *ctx, const IsoPlan &p, IsoFuse &f);
+int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1);
+int halo_fused_signal(b2_halo_ctx *ctx);
+
 // Same for the coupled TTI fields: u and v boundary planes travel in one NCCL group.
 int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t2, int t1);
 

@@ -112,6 +112,19 @@ struct IsoTK {
     int slot0, slotm;
     float m_dt2;
     float wx[R + 1], wy[R + 1], wz[R + 1];
+    // ---- x-slab decomposition, halo step fused into the sweep (all zero / null on a single device) ----
+    // The CTAs that produce a boundary plane also store it into the neighbour GPU's halo through the
+    // CUDA-IPC mapped peer pointer (16-byte stores over NVLink), and the producer lane of a CTA that
+    // needs a halo plane of u[t] first acquires the flag the neighbour released after its previous
+    // step. Chunk 0 marches from its high end DOWN to x = 0 when a low neighbour exists, so every CTA
+    // touches the neighbour's planes at the very END of its march: by then the flag has long been set.
+    int back0;                    // chunk 0 marches backwards
+    int nown;                     // planes owned by this rank: peer planes are [0, pw) and [nown - pw, nown)
+    int pw;                       // planes published per side (= R)
+    float *peer_lo, *peer_hi;     // neighbour field bases (NULL: physical boundary)
+    long long off_lo, off_hi;     // element offset of "my plane 0" inside the neighbour's array (output slot)
+    const int *flag_lo, *flag_hi; // local flags the neighbours release (NULL: nothing to wait for)
+    int want;                     // flag value that says "halos of u[t] are in place" (< 0: already ensured)
 };
 
 constexpr int ceil4(int v) { return (v + 3) / 4 * 4; }
@@ -179,6 +192,11 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
     const int xs = k.xlo + ix * k.lx;
     const int xe = min(xs + k.lx, k.xlo + k.xcount);
     const int NP = (xe - xs) + 2 * R;
+    // plane j of the march sits at x = xb + dx * j (relative to the iteration origin); the output of
+    // iteration j is the plane x = xb + dx * (j - R)
+    const bool back = (ix == 0) && k.back0;
+    const int dx = back ? -1 : 1;
+    const int xb = back ? xe - 1 + R : xs - R;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -200,22 +218,37 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
             b2ptx::tma_prefetch_desc(&tm_a);
             if (PK != B2_PARAM_SCALAR) b2ptx::tma_prefetch_desc(&tm_b);
             int slot = 0, round = 0, ss = 0;
+            bool need_lo = k.want >= 0 && k.flag_lo != nullptr, need_hi = k.want >= 0 && k.flag_hi != nullptr;
             for (int j = 0; j < NP; ++j) {
                 if (round > 0) b2ptx::mbar_wait(&empty[slot], (round - 1) & 1);
                 const int s = j - 2 * R;
+                const int xj = xb + dx * j;
+                // a plane the neighbour GPU owns: it stored it into our halo at the end of its previous
+                // step and then released the flag; acquire it once, then let the TMA engine read
+                if (need_lo && xj < 0) {
+                    while (b2ptx::ld_acquire_sys(k.flag_lo) < k.want) __nanosleep(40);
+                    b2ptx::fence_proxy_async_global();
+                    need_lo = false;
+                }
+                if (need_hi && xj >= k.nown) {
+                    while (b2ptx::ld_acquire_sys(k.flag_hi) < k.want) __nanosleep(40);
+                    b2ptx::fence_proxy_async_global();
+                    need_hi = false;
+                }
                 uint32_t bytes = C::BY * BZ * 4;
                 if (s >= 0) bytes += TILE * 4 * C::NTILES;
                 b2ptx::mbar_arrive_expect_tx(&full[slot], bytes);
                 b2ptx::tma_load_4d(s_u + slot * PLANE, &tm_uh, &full[slot], k.oz + z0 - RZ,
-                                   k.oy + y0 - R, k.ox + xs - R + j, k.slot0);
+                                   k.oy + y0 - R, k.ox + xj, k.slot0);
                 if (s >= 0) {
+                    const int xo = xj - dx * R;
                     b2ptx::tma_load_4d(s_prev + ss * TILE, &tm_uc, &full[slot], k.oz + z0,
-                                       k.oy + y0, k.ox + xs + s, k.slotm);
+                                       k.oy + y0, k.ox + xo, k.slotm);
                     b2ptx::tma_load_3d(s_a + ss * TILE, &tm_a, &full[slot], k.oz + z0, k.oy + y0,
-                                       k.ox + xs + s);
+                                       k.ox + xo);
                     if (PK != B2_PARAM_SCALAR)
                         b2ptx::tma_load_3d(s_b + ss * TILE, &tm_b, &full[slot], k.oz + z0,
-                                           k.oy + y0, k.ox + xs + s);
+                                           k.oy + y0, k.ox + xo);
                     if (++ss == NS) ss = 0;
                 }
                 if (++slot == NU) { slot = 0; ++round; }
@@ -231,8 +264,10 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
     const int zcnt = yok ? min(max(k.nz - gz, 0), 4) : 0;
     const float *my_col = s_u + (ty + R) * BZ + RZ + 4 * tz4;
     const float *my_prev = s_prev + ty * TZ + 4 * tz4;
-    float *outp = k.u1 + (long long)(k.ox + xs - 2 * R) * k.sx + (long long)(k.oy + gy) * k.sy + (k.oz + gz);
-    const long long osx = k.sx;
+    const long long rowoff = (long long)(k.oy + gy) * k.sy + (k.oz + gz);
+    float *outp = k.u1 + (long long)(k.ox + xb - dx * R) * k.sx + rowoff;
+    const long long osx = dx * k.sx;
+    const bool fuse = (k.peer_lo != nullptr) | (k.peer_hi != nullptr);
 
     float4 q[Q];
 #pragma unroll
@@ -321,6 +356,22 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
                     dst[0] = o.x;
                     if (zcnt > 1) dst[1] = o.y;
                     if (zcnt > 2) dst[2] = o.z;
+                }
+                if (fuse) {
+                    // a boundary plane: the same 16 bytes also go into the neighbour's halo (NVLink)
+                    const int xo = xb + dx * (j - R);
+                    float *pd = nullptr;
+                    if (k.peer_lo && xo < k.pw) pd = k.peer_lo + (k.off_lo + (long long)xo * k.sx + rowoff);
+                    if (k.peer_hi && xo >= k.nown - k.pw) pd = k.peer_hi + (k.off_hi + (long long)xo * k.sx + rowoff);
+                    if (pd) {
+                        if (zcnt == 4) {
+                            *reinterpret_cast<float4 *>(pd) = o;
+                        } else if (zcnt > 0) {
+                            pd[0] = o.x;
+                            if (zcnt > 1) pd[1] = o.y;
+                            if (zcnt > 2) pd[2] = o.z;
+                        }
+                    }
                 }
                 ssoff += TILE;
                 if (ssoff == NS * TILE) ssoff = 0;
@@ -506,7 +557,8 @@ int iso_plan_init(IsoPlan &p, int kernel) {
 }
 
 template <int R, int PK>
-static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
+static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount,
+                      const IsoFuse *fz = nullptr) {
     using T = TileOf<R>;
     using C = IsoTmaCfg<R, T::TY, T::TZ4, PK>;
     auto kern = k_iso_tma<R, T::TY, T::TZ4, PK>;
@@ -533,8 +585,29 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     int lx = env_int("B2_ISO_LX", 0);
     if (lx <= 0) lx = choose_chunk_len(k.ntz * k.nty, xcount, 2 * R, 32);
     lx = std::min(lx, xcount);
+    // fused halo step with neighbours on both sides: at least two chunks, so that the one marching down
+    // to x = 0 and the one marching up to x = n-1 each meet the neighbour's planes at their end
+    if (fz && (fz->peer_lo || fz->flag_lo) && (fz->peer_hi || fz->flag_hi) && lx >= xcount && xcount >= 4 * R)
+        lx = (xcount + 1) / 2;
     k.lx = lx;
     const int ntx = (xcount + lx - 1) / lx;
+    k.back0 = 0; k.nown = p.n[0]; k.pw = R;
+    k.peer_lo = k.peer_hi = nullptr;
+    k.off_lo = k.off_hi = 0;
+    k.flag_lo = k.flag_hi = nullptr;
+    k.want = -1;
+    if (fz) {
+        const long long plane = p.sx;
+        k.back0 = (fz->peer_lo || fz->flag_lo) ? 1 : 0;
+        k.peer_lo = fz->peer_lo;
+        k.peer_hi = fz->peer_hi;
+        // my owned plane x mirrors plane (halo + n_lo + x) of the low neighbour / (halo - nown + x) of the high one
+        k.off_lo = (long long)slot1 * fz->slot_lo + (long long)(p.o[0] + fz->n_lo) * plane;
+        k.off_hi = (long long)slot1 * fz->slot_hi + (long long)(p.o[0] - p.n[0]) * plane;
+        k.flag_lo = fz->flag_lo;
+        k.flag_hi = fz->flag_hi;
+        k.want = fz->want;
+    }
     k.slot0 = slot0;
     k.slotm = slotm;
     k.m_dt2 = (1.0f / (p.vp * p.vp)) * (1.0f / (p.dt * p.dt));
@@ -553,11 +626,11 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
 }
 
 template <int R>
-static int launch_tma_pk(const IsoPlan &p, int s0, int sm, int s1, int xlo, int xcount) {
+static int launch_tma_pk(const IsoPlan &p, int s0, int sm, int s1, int xlo, int xcount, const IsoFuse *fz = nullptr) {
     switch (p.param_kind) {
-        case B2_PARAM_SCALAR: return launch_tma<R, B2_PARAM_SCALAR>(p, s0, sm, s1, xlo, xcount);
-        case B2_PARAM_VP: return launch_tma<R, B2_PARAM_VP>(p, s0, sm, s1, xlo, xcount);
-        case B2_PARAM_M: return launch_tma<R, B2_PARAM_M>(p, s0, sm, s1, xlo, xcount);
+        case B2_PARAM_SCALAR: return launch_tma<R, B2_PARAM_SCALAR>(p, s0, sm, s1, xlo, xcount, fz);
+        case B2_PARAM_VP: return launch_tma<R, B2_PARAM_VP>(p, s0, sm, s1, xlo, xcount, fz);
+        case B2_PARAM_M: return launch_tma<R, B2_PARAM_M>(p, s0, sm, s1, xlo, xcount, fz);
     }
     return B2_ERR_INVALID;
 }
@@ -623,6 +696,17 @@ int iso_fs_fix(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int x
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
     return B2_OK;
+}
+
+int iso_step_fused(const IsoPlan &p, int slot0, int slotm, int slot1, const IsoFuse &f) {
+    if (!p.use_tma) { set_error("iso: the fused halo step needs the TMA sweep kernel"); return B2_ERR_INVALID; }
+    switch (p.radius[2]) {
+        case 2: return launch_tma_pk<2>(p, slot0, slotm, slot1, 0, p.n[0], &f);
+        case 4: return launch_tma_pk<4>(p, slot0, slotm, slot1, 0, p.n[0], &f);
+        case 6: return launch_tma_pk<6>(p, slot0, slotm, slot1, 0, p.n[0], &f);
+        case 8: return launch_tma_pk<8>(p, slot0, slotm, slot1, 0, p.n[0], &f);
+    }
+    return B2_ERR_INVALID;
 }
 
 int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {

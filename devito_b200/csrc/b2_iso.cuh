@@ -30,6 +30,17 @@ struct IsoPlan {
     float *ot4W = nullptr;
 };
 
+// x-slab decomposition: the halo step fused into the TMA sweep (b2_halo.cu fills it per step). The CTAs that
+// produce the first / last `radius` owned planes also store them into the neighbour's halo through the
+// CUDA-IPC mapped pointers; CTAs that read halo planes of u[t] acquire the neighbour's flag first.
+struct IsoFuse {
+    float *peer_lo = nullptr, *peer_hi = nullptr;     // neighbour field bases (all time slots); NULL = boundary
+    long long slot_lo = 0, slot_hi = 0;               // elements of one time slot in the neighbour's array
+    int n_lo = 0, n_hi = 0;                           // x-planes the neighbours own
+    const int *flag_lo = nullptr, *flag_hi = nullptr; // local flags released by the neighbours
+    int want = -1;                                    // flag value to acquire (< 0: halos already in place)
+};
+
 // Prepare the plan (decides generic vs TMA kernel, encodes tensor maps). `kernel`: 0 auto,
 // 1 force generic, 2 force TMA (error if the layout does not qualify).
 int iso_plan_init(IsoPlan &p, int kernel);
@@ -37,6 +48,9 @@ int iso_plan_init(IsoPlan &p, int kernel);
 // One time step over x in [xlo, xlo + xcount) (relative to the iteration origin):
 // u[slot1] = update(u[slot0], u[slotm]).
 int iso_step(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount);
+
+// Same over the whole owned x-range with the fused halo step (TMA kernel only: p.use_tma).
+int iso_step_fused(const IsoPlan &p, int slot0, int slotm, int slot1, const IsoFuse &f);
 
 // Free surface at the low end of the last dimension: after iso_step, recompute the rows z < radius
 // with mirrored vertical taps and clear the surface row (b2_iso_args.free_surface).

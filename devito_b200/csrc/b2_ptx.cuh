@@ -76,6 +76,22 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// generic-proxy writes (ours or a peer GPU's, observed through an acquire) -> async-proxy (TMA) reads of global memory
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+// system-scope flag handshake between GPUs (peer-mapped memory)
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ float4 lds128(const float *p) {
     return *reinterpret_cast<const float4 *>(p);
 }

@@ -26,6 +26,10 @@ struct SparseK {
     int so;
     int lo0, lo1, lo2, hi0, hi1, hi2;
     int ext_lo0, ext_hi0;     // how far beyond [lo0, hi0] the support may reach (r, or 0 next to a neighbour)
+    // fused halo step (FieldGeom): mirror injected boundary cells into the neighbours' halos
+    float *peer_lo, *peer_hi;
+    long long off_lo, off_hi;
+    int nown, pw;
 };
 
 __device__ __forceinline__ bool sparse_cell(const SparseK &k, int p, int c, long long &idx, float &wgt,
@@ -84,6 +88,12 @@ k_inject(SparseK k, float *__restrict__ f0, float *__restrict__ f1, int time, in
         const float val = w * sv * scale;
         atomicAdd(f0 + idx, val);
         if (f1) atomicAdd(f1 + idx, val);
+        if (k.pw > 0) {
+            // idx = (c0 + so) * sx + row; the neighbour's copy of my plane c0 sits at off + c0 * sx + row
+            const long long row = idx - (long long)(c0 + k.so) * k.sx;
+            if (k.peer_lo && c0 < k.pw) atomicAdd_system(k.peer_lo + (k.off_lo + (long long)c0 * k.sx + row), val);
+            if (k.peer_hi && c0 >= k.nown - k.pw) atomicAdd_system(k.peer_hi + (k.off_hi + (long long)c0 * k.sx + row), val);
+        }
     }
 }
 
@@ -115,6 +125,11 @@ static SparseK make_k(const SparseDev &s, const FieldGeom &g, bool injecting) {
     SparseK k;
     k.ext_lo0 = (injecting && g.nb_lo) ? 0 : s.r;
     k.ext_hi0 = (injecting && g.nb_hi) ? 0 : s.r;
+    k.peer_lo = injecting ? g.peer_lo : nullptr;
+    k.peer_hi = injecting ? g.peer_hi : nullptr;
+    k.off_lo = g.off_lo; k.off_hi = g.off_hi;
+    k.nown = g.nown;
+    k.pw = injecting && s.ndim == 3 && (g.peer_lo || g.peer_hi) ? g.pw : 0;
     k.data = (const float *)s.data.d;
     k.gp = (const int *)s.gp.d;
     if (s.ndim == 3) {

@@ -25,6 +25,11 @@ struct FieldGeom {
     // x-slab decomposition: a neighbour owns the cells beyond x_m / x_M, so injection must not
     // touch them (the owner injects and its boundary planes are then exchanged)
     bool nb_lo = false, nb_hi = false;
+    // fused halo step: cells injected into the first / last `pw` owned planes are mirrored into the
+    // neighbour's halo copy (the sweep kernel stored those planes there before the injection)
+    float *peer_lo = nullptr, *peer_hi = nullptr;
+    long long off_lo = 0, off_hi = 0;        // element offset of "my plane 0" in the neighbour's array (slot included)
+    int nown = 0, pw = 0;
 };
 
 int sparse_stage_in(const b2_sparse *s, int ndim, SparseDev &out, bool copy_data_in);

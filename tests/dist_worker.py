@@ -69,7 +69,7 @@ def gpu_mode(kind):
     w = dv.init_distributed()
     local = int(os.environ.get('LOCAL_RANK', '0'))
     dv.configuration['deviceid'] = local
-    so, nbl, n, tn = 8, 10, (44, 28, 28), 150.0
+    so, nbl, n, tn = 8, 10, (24 * w.size - 4, 28, 28), 150.0        # 24 owned planes per rank
     preset = 'constant-isotropic' if kind == 'iso' else 'constant-tti'
     cls = AcousticWaveSolver if kind == 'iso' else AnisotropicWaveSolver
     model = demo_model(preset, spacing=(10., 10., 10.), shape=n, nbl=nbl, space_order=so, topology=('*', 1, 1))

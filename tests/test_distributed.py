@@ -19,8 +19,8 @@ def _free_port():
     return p
 
 
-def _launch(args, timeout=600, extra_env=None):
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+def _launch(args, timeout=600, extra_env=None, nproc=2):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(nproc),
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()),
            os.path.join(HERE, 'dist_worker.py')] + args
     env = dict(os.environ)
@@ -34,11 +34,29 @@ def test_decomposition_host_side():
     assert 'DIST-HOST-OK' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
-# halo data paths: default peer-memory stores; complete NCCL path; the asynchronous peer-memory
-# variant is opt-in and only exercised when B2_TEST_EXPERIMENTAL=1 (not yet validated on hardware)
-_PATHS = [('p2p', {}), ('nccl', {'B2_HALO': 'nccl'})]
+# halo data paths: the halo step fused into the sweep kernel (default for the isotropic TMA kernel), the
+# copy-based peer-memory path (TTI, generic kernels, B2_HALO_FUSED=0) and the complete NCCL path
+_PATHS = [('p2p-fused', {}), ('p2p-copy', {'B2_HALO_FUSED': '0'}), ('nccl', {'B2_HALO': 'nccl'})]
 if os.environ.get('B2_TEST_EXPERIMENTAL') == '1':
-    _PATHS.append(('p2p-async', {'B2_P2P_ASYNC': '1'}))
+    _PATHS.append(('p2p-copy-async', {'B2_HALO_FUSED': '0', 'B2_P2P_ASYNC': '1'}))
+
+
+def _decomposed_vs_single(kind, tol, env, nproc):
+    r = _launch(['gpu', kind], extra_env=env, nproc=nproc)
+    assert 'DIST-GPU-DONE' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    sys.path.insert(0, HERE)
+    from helpers import rel_linf
+    from devito_b200.seismic import demo_model, setup_geometry, AcousticWaveSolver, AnisotropicWaveSolver
+    so, nbl, n, tn = 8, 10, (24 * nproc - 4, 28, 28), 150.0
+    preset = 'constant-isotropic' if kind == 'iso' else 'constant-tti'
+    cls = AcousticWaveSolver if kind == 'iso' else AnisotropicWaveSolver
+    model = demo_model(preset, spacing=(10., 10., 10.), shape=n, nbl=nbl, space_order=so)
+    out = cls(model, setup_geometry(model, tn), space_order=so).forward()
+    rec, u = out[0], out[1]
+    ud = np.concatenate([np.load(f'/tmp/b2_dist_{kind}_u_{r}.npy') for r in range(nproc)], axis=1)
+    assert ud.shape == u.data.shape
+    assert rel_linf(ud, u.data) < tol
+    assert rel_linf(np.load(f'/tmp/b2_dist_{kind}_rec.npy'), rec.data) < tol
 
 
 @pytest.mark.gpu
@@ -48,20 +66,16 @@ def test_two_gpu_halo_exchange_matches_single_gpu(kind, tol, path, env):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _launch(['gpu', kind], extra_env=env)
-    assert 'DIST-GPU-DONE' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
-    sys.path.insert(0, HERE)
-    from helpers import rel_linf
-    from devito_b200.seismic import demo_model, setup_geometry, AcousticWaveSolver, AnisotropicWaveSolver
-    so, nbl, n, tn = 8, 10, (44, 28, 28), 150.0
-    preset = 'constant-isotropic' if kind == 'iso' else 'constant-tti'
-    cls = AcousticWaveSolver if kind == 'iso' else AnisotropicWaveSolver
-    model = demo_model(preset, spacing=(10., 10., 10.), shape=n, nbl=nbl, space_order=so)
-    out = cls(model, setup_geometry(model, tn), space_order=so).forward()
-    rec, u = out[0], out[1]
-    u0 = np.load(f'/tmp/b2_dist_{kind}_u_0.npy')
-    u1 = np.load(f'/tmp/b2_dist_{kind}_u_1.npy')
-    ud = np.concatenate([u0, u1], axis=1)
-    assert ud.shape == u.data.shape
-    assert rel_linf(ud, u.data) < tol
-    assert rel_linf(np.load(f'/tmp/b2_dist_{kind}_rec.npy'), rec.data) < tol
+    _decomposed_vs_single(kind, tol, env, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('path,env', _PATHS, ids=[p for p, _ in _PATHS])
+@pytest.mark.parametrize('kind,tol', [('iso', 1e-5), ('tti', 1e-4)])
+def test_four_gpu_halo_exchange_matches_single_gpu(kind, tol, path, env):
+    """Ranks 1 and 2 have neighbours on both sides (tests/test_mpi.py of the reference runs its halo tests at
+    4 ranks for the same reason)."""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    _decomposed_vs_single(kind, tol, env, 4)
