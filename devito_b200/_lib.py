@@ -15,7 +15,7 @@ import numpy as np
 from .exceptions import BackendUnavailable
 
 __all__ = ['lib', 'have_lib', 'have_gpu', 'Dataobj', 'Profiler', 'Sparse', 'IsoArgs', 'TtiArgs', 'Tap', 'LinearArgs',
-           'make_dataobj', 'nccl_library_path', 'LIB_PATH']
+           'make_dataobj', 'ForeignDataobj', 'ForeignSparse', 'nccl_library_path', 'LIB_PATH']
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libb200stencil.so')
 
@@ -228,3 +228,35 @@ class DataobjHolder:
 
 def make_dataobj(host=None, dev_ptr=None, shape=None, halo=None):
     return DataobjHolder(host=host, dev_ptr=dev_ptr, shape=shape, halo=halo)
+
+
+class ForeignDataobj:
+    """A `struct dataobj` somebody else built — the reference's own `_C_make_dataobj`
+    (devito/types/dense.py:749-777) when its Operator hands its arguments to this backend
+    (devito_b200/refplugin.py). The struct is used as it is: same field layout, `data` = host array,
+    `size` = allocated extents (halo included), `dmap` = NULL (host-staged by the library)."""
+
+    def __init__(self, address, keep=None):
+        self.obj = Dataobj.from_address(int(address))
+        self._keep = keep                      # whatever owns the struct's memory
+
+    @property
+    def ptr(self):
+        return ctypes.pointer(self.obj)
+
+    def shape(self, ndim):
+        return tuple(int(self.obj.size[i]) for i in range(ndim))
+
+
+class ForeignSparse:
+    """A sparse time function described by foreign structs: traces `data` (nt, npoint), base cells `gp`
+    (npoint, ndim, int32) and per-dimension weight tables (npoint, 2r) — the arguments `src, src_gp,
+    src_wx, ...` the reference computes for its own generated kernel
+    (devito/operations/interpolators.py:674-718)."""
+    is_SparseTimeFunction = True
+    is_foreign = True
+
+    def __init__(self, name, data, gp, ws, p_m, p_M, r):
+        self.name, self.data, self.gp, self.ws = name, data, gp, list(ws)
+        self.p_m, self.p_M, self.r = int(p_m), int(p_M), int(r)
+        self.nt, self.npoint = data.shape(2)

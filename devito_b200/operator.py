@@ -1131,7 +1131,25 @@ class Operator:
             return obj
         if isinstance(v, np.ndarray):
             return self._shadow(obj, v, post)
+        if isinstance(v, L_.ForeignDataobj):
+            return self._foreign(obj, v)
         return v
+
+    @staticmethod
+    def _foreign(obj, fo):
+        """A `struct dataobj` built by the caller (devito_b200/refplugin.py passes the reference's own)
+        stands in for `obj`'s data; the library stages it in and out inside the call."""
+        want = tuple(obj.storage.shape)
+        got = fo.shape(len(want))
+        if got != want:
+            raise InvalidArgument(f"Shape {got} of runtime value `{obj.name}` does not match the allocated "
+                                  f"shape {want}")
+        if fo.obj.dmap or not fo.obj.data:
+            raise InvalidArgument(f"runtime struct for `{obj.name}` must describe a host array")
+        sh = object.__new__(type(obj))
+        sh.__dict__.update(obj.__dict__)
+        sh._foreign_obj = fo
+        return sh
 
     @staticmethod
     def _shadow(obj, arr, post):
@@ -1209,6 +1227,10 @@ class Operator:
                 pass
             else:
                 val = kwargs.pop(obj.name, obj)
+                if isinstance(val, L_.ForeignDataobj) and isinstance(obj, Function):
+                    val = self._foreign(obj, val)
+                elif isinstance(val, np.ndarray) and val.ndim and isinstance(obj, Function):
+                    val = self._shadow(obj, val, None)
                 if isinstance(val, Function):
                     args['param'] = val
                     args['param_kind'] = B2_PARAM_VP if kind.startswith('vp') else B2_PARAM_M
@@ -1220,6 +1242,10 @@ class Operator:
             for n, c in p['consts'].items():
                 val = kwargs.pop(n, c)
                 if isinstance(c, Function):
+                    if isinstance(val, L_.ForeignDataobj):
+                        val = self._foreign(c, val)
+                    elif isinstance(val, np.ndarray) and val.ndim:
+                        val = self._shadow(c, val, None)
                     if not isinstance(val, Function) or val.space_order != p['so']:
                         raise InvalidArgument(f"`{n}` must be overridden by a Function of the same space_order")
                     args['tti_arrays'][n] = val
@@ -1329,6 +1355,14 @@ class Operator:
     def _field_obj(self, fn, dev, resident, hold, so=None, written=False):
         """b2_dataobj for a dense function: resident (dmap set) or host-staged."""
         import torch
+        fo = getattr(fn, '_foreign_obj', None)
+        if fo is not None:
+            if so is not None and fn.space_order != so:
+                raise InvalidArgument(f"`{fn.name}`: a caller-built struct needs the wavefield's space order {so}")
+            if resident:
+                raise InvalidArgument("caller-built structs are host arrays: apply with resident=False")
+            hold.append(fo)
+            return fo
         if so is not None and fn.space_order != so:
             host = self._as_layout(fn, so, None)
             hold.append(host)
@@ -1368,6 +1402,16 @@ class Operator:
         scatters points to their owner ranks instead (devito/types/sparse.py:608-730)."""
         if sf is None:
             return None
+        if getattr(sf, 'is_foreign', False):
+            if grid.distributor.is_parallel:
+                raise InvalidArgument("caller-built sparse tables are not combined with domain decomposition")
+            s = L_.Sparse()
+            s.data, s.gp = sf.data.ptr, sf.gp.ptr
+            for i, wo in enumerate(sf.ws):
+                s.w[i] = wo.ptr
+            s.p_m, s.p_M, s.r = sf.p_m, sf.p_M, sf.r
+            hold.extend([sf, s])
+            return s
         gp, ws = sf.tabulate()
         dist = grid.distributor
         host = sf.storage.host if written else sf.storage.host_ro

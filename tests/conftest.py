@@ -15,8 +15,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "pending: GPU test written after the round's GPU budget was spent; "
-                                       "never executed on hardware yet. Skipped unless B2_RUN_PENDING=1")
+    config.addinivalue_line("markers", "pending: GPU test that has not run on hardware yet (none at the moment: every "
+                                       "test written in round 1 ran green on a B200 in round 2); skipped unless "
+                                       "B2_RUN_PENDING=1")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -1,0 +1,147 @@
+"""Worker for tests/test_zy_refplugin.py — runs in its own interpreter because here `import devito` is the
+REAL reference (installed unmodified under baseline/_ref, or /root/reference in the build container), made
+importable next to devito_b200 by the launcher's PYTHONPATH.
+
+  ffi : no GPU. `(Blackwell, 'advanced', 'cuda')` is selected, the reference's examples build their
+        operators, and `b2_iso_forward` / `b2_tti_forward` are replaced by recording doubles that check
+        the structs the plugin passes: they must be the reference's own `struct dataobj` (same data
+        pointers as the reference's arrays, allocated extents, coordinate tables).
+  gpu : the reference's examples/seismic/{acoustic,tti} example functions run unchanged on the GPU;
+        norms against the reference's own known-answer values and its CPU run (tests/golden).
+"""
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+import devito                                             # noqa: E402  (the reference)
+import devito_b200.refplugin as rp                        # noqa: E402
+from devito_b200 import _lib as L_                        # noqa: E402
+
+assert 'devito_b200' not in devito.__file__
+rp.activate()
+
+from devito import configuration, norm                    # noqa: E402
+from examples.seismic import demo_model, setup_geometry   # noqa: E402
+from examples.seismic.acoustic import AcousticWaveSolver  # noqa: E402
+from examples.seismic.tti import AnisotropicWaveSolver    # noqa: E402
+
+
+def ffi():
+    calls = []
+
+    class Double:
+        """Stands in for libb200stencil.so: records what crosses the C ABI."""
+        def b2_iso_forward(self, ref):
+            a = ref._obj
+            u = a.u.contents
+            calls.append(dict(kind='iso', ndim=a.ndim, so=a.space_order, R=a.radius, u_data=u.data,
+                              u_size=[u.size[i] for i in range(4)], u_dmap=u.dmap, dt=a.dt, vp=a.vp,
+                              param_kind=a.param_kind, param_data=a.param.contents.data if a.param else None,
+                              damp_data=a.damp.contents.data, time=(a.time_m, a.time_M),
+                              box=(a.x_m, a.x_M, a.y_m, a.y_M, a.z_m, a.z_M), fs=a.free_surface, adjoint=a.adjoint,
+                              src=dict(data=a.src.contents.data.contents.data, gp=a.src.contents.gp.contents.data,
+                                       w0=a.src.contents.w[0].contents.data, r=a.src.contents.r,
+                                       p=(a.src.contents.p_m, a.src.contents.p_M)),
+                              rec=dict(data=a.rec.contents.data.contents.data, gp=a.rec.contents.gp.contents.data,
+                                       nrec=a.rec.contents.data.contents.size[1], r=a.rec.contents.r)))
+            return 0
+
+        def b2_tti_forward(self, ref):
+            a = ref._obj
+            calls.append(dict(kind='tti', so=a.space_order, R=a.radius, u_data=a.u.contents.data,
+                              v_data=a.v.contents.data, scal=(a.vp, a.epsilon, a.delta, a.theta, a.phi),
+                              arrays=[bool(x) for x in (a.vp_arr, a.epsilon_arr, a.delta_arr, a.theta_arr, a.phi_arr)]))
+            return 0
+
+        def b2_last_error(self):
+            return b''
+
+    L_.lib = lambda: Double()
+    kw = dict(shape=(20, 20, 20), nbl=6, spacing=(20., 20., 20.), dtype=np.float32)
+    # layered velocity (array parameter), free surface
+    model = demo_model('layers-isotropic', space_order=4, fs=True, **kw)
+    geometry = setup_geometry(model, 100.0)
+    solver = AcousticWaveSolver(model, geometry, space_order=4)
+    op = solver.op_fwd()
+    assert type(op).__name__ == 'B200CudaOperator' and op.backend == 'cuda-sm100a', op._b200_why
+    u = devito.TimeFunction(name='u', grid=model.grid, time_order=2, space_order=4)
+    rec = geometry.rec
+    solver.forward(u=u, rec=rec)
+    c = calls[-1]
+    assert c['kind'] == 'iso' and c['fs'] == 1 and c['so'] == 4 and c['R'] == 2 and c['ndim'] == 3
+    assert c['u_data'] == u._data.ctypes.data and c['u_dmap'] is None          # the reference's own array
+    assert c['u_size'] == list(u._data.shape) == [3, 40, 40, 34]
+    assert c['damp_data'] == model.damp._data.ctypes.data
+    assert c['param_kind'] == 1 and c['param_data'] == model.vp._data.ctypes.data
+    assert c['rec']['data'] == rec._data.ctypes.data and c['rec']['nrec'] == rec.npoint
+    assert c['src']['r'] == 1 and c['src']['p'] == (0, 0)
+    assert abs(c['dt'] - float(model.critical_dt)) < 1e-6
+    assert c['time'] == (1, geometry.nt - 2) and c['box'] == (0, 31, 0, 31, 0, 25)
+    # scalar velocity: the Constant travels as a number; runtime overrides go through the reference's arguments()
+    m2 = demo_model('constant-isotropic', space_order=8, **kw)
+    s2 = AcousticWaveSolver(m2, setup_geometry(m2, 100.0, interpolation='sinc'), space_order=8)
+    s2.forward()
+    assert calls[-1]['param_kind'] == 0 and abs(calls[-1]['vp'] - 1.5) < 1e-6 and calls[-1]['src']['r'] == 4
+    s2.forward(vp=2.0)
+    assert abs(calls[-1]['vp'] - 2.0) < 1e-6
+    s2.forward(vp=devito.Constant(name='v', value=2.5, dtype=np.float32))
+    assert abs(calls[-1]['vp'] - 2.5) < 1e-6
+    s2.adjoint(rec=s2.geometry.rec)
+    assert calls[-1]['adjoint'] == 1
+    # TTI
+    m3 = demo_model('constant-tti', space_order=8, **kw)
+    s3 = AnisotropicWaveSolver(m3, setup_geometry(m3, 100.0), space_order=8)
+    s3.forward()
+    c = calls[-1]
+    assert c['kind'] == 'tti' and c['R'] == 4 and not any(c['arrays'])
+    assert np.allclose(c['scal'], (1.5, .3, .2, .7, .35), atol=1e-6)
+    m4 = demo_model('layers-tti', space_order=4, **kw)
+    AnisotropicWaveSolver(m4, setup_geometry(m4, 100.0), space_order=4).forward()
+    assert calls[-1]['kind'] == 'tti' and all(calls[-1]['arrays'])
+    # the set-up operators stayed on the reference's CPU path (and ran: the damping profile is there)
+    assert float(np.max(model.damp.data)) > 0
+    print('REFPLUGIN-FFI-OK', len(calls))
+
+
+def gpu():
+    from examples.seismic.acoustic.acoustic_example import run as arun
+    from examples.seismic.tti.tti_example import run as trun
+    with open(os.path.join(ROOT, 'tests', 'golden', 'refplugin_norms.json')) as f:
+        gold = json.load(f)
+    L = L_.lib()
+    out = {}
+    n0 = L.b2_launch_count()
+    # the reference's own known answers (acoustic_example.py:80-87)
+    for interp, kat in (('linear', 369.955), ('sinc', 402.216)):
+        _, _, _, [rec, u] = arun(fs=True, dtype=np.float32, interpolation=interp)
+        got = float(norm(rec))
+        out[f'iso_fs_{interp}'] = got
+        assert np.isclose(got, kat, rtol=1e-3, atol=0), (interp, got, kat)
+        assert np.isclose(got, gold[f'iso_fs_{interp}']['norm_rec'], rtol=2e-4), (interp, got)
+    for tag, kw in [('iso_layers_so4', dict(fs=False)),
+                    ('iso_const_so8', dict(fs=False, preset='constant-isotropic', space_order=8, nbl=20)),
+                    ('iso_ot4_so8', dict(fs=False, space_order=8, kernel='OT4', nbl=20))]:
+        _, _, _, [rec, u] = arun(dtype=np.float32, **kw)
+        got = float(norm(rec)), float(np.linalg.norm(np.asarray(u, dtype=np.float64)))
+        out[tag] = got
+        assert np.isclose(got[0], gold[tag]['norm_rec'], rtol=2e-4), (tag, got, gold[tag])
+        assert np.isclose(got[1], gold[tag]['norm_u'], rtol=2e-4), (tag, got, gold[tag])
+    for tag, kw in [('tti_layers_so4', dict()), ('tti_const_so8', dict(preset='constant-tti', space_order=8))]:
+        _, _, _, [rec, u, v] = trun(dtype=np.float32, **kw)
+        got = float(norm(rec)), float(norm(u)), float(norm(v))
+        out[tag] = got
+        assert np.isclose(got[0], gold[tag]['norm_rec'], rtol=1e-3), (tag, got, gold[tag])
+        assert np.isclose(got[1], gold[tag]['norm_u'], rtol=1e-3), (tag, got, gold[tag])
+        assert np.isclose(got[2], gold[tag]['norm_v'], rtol=1e-3), (tag, got, gold[tag])
+    launches = int(L.b2_launch_count() - n0)
+    assert launches > 1000, launches                  # the propagators ran in libb200stencil.so
+    print('REFPLUGIN-GPU-OK', json.dumps({'launches': launches, 'norms': out}))
+
+
+if __name__ == '__main__':
+    {'ffi': ffi, 'gpu': gpu}[sys.argv[1]]()

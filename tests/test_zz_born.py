@@ -53,7 +53,6 @@ def test_born_lookalikes_are_refused():
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 def test_born_vs_reference_golden():
     g = load_golden('born3d_so8')
     model, geometry, solver = _solver(g)

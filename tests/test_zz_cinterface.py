@@ -235,7 +235,6 @@ def test_adapter_links_against_the_library(jitdir):
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 @needs_gcc
 def test_adapter_runs_on_the_gpu(jitdir):
     """`Forward(...)` called like the reference calls its generated function (host arrays, flat
@@ -296,7 +295,6 @@ def test_ndarray_override_is_checked():
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 def test_ndarray_override_runs_in_place():
     solver = _iso_solver(so=8, n=32, nbl=8)
     op = solver.op_fwd()

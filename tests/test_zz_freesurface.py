@@ -63,7 +63,6 @@ def test_free_surface_needs_the_matching_update(tmp_path, monkeypatch):
 
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.pending
 @pytest.mark.parametrize('kernel', [1, 0])
 @pytest.mark.parametrize('name,so,nlayers,interp', [('iso3d_so4_fs', 4, 3, 'linear'),
                                                     ('iso3d_so8_fs_sinc', 8, 2, 'sinc')])
@@ -77,7 +76,6 @@ def test_free_surface_vs_reference_golden(name, so, nlayers, interp, kernel):
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 @pytest.mark.parametrize('name,interp,kat', [('kat3d_fs_linear', 'linear', 369.955),
                                              ('kat3d_fs_sinc', 'sinc', 402.216)])
 def test_free_surface_known_answer_norms(name, interp, kat):
@@ -93,7 +91,6 @@ def test_free_surface_known_answer_norms(name, interp, kat):
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 def test_free_surface_adjoint_vs_reference_golden():
     g = load_golden('adj3d_so4_fs')
     model, geometry, solver = _solver(so=4, n=int(g['n']), nbl=int(g['nbl']), tn=float(g['tn']), nlayers=2)

@@ -53,7 +53,6 @@ def test_ot4_lookalikes_are_refused():
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 @pytest.mark.parametrize('name,preset,so', CASES)
 def test_ot4_vs_reference_golden(name, preset, so):
     g = load_golden(name)
@@ -64,7 +63,6 @@ def test_ot4_vs_reference_golden(name, preset, so):
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 def test_ot4_adjoint_vs_reference_golden():
     from devito_b200.seismic import AcousticWaveSolver, demo_model, setup_geometry
     g = load_golden('adj3d_so4_ot4')

@@ -1,6 +1,6 @@
 """Time-subsampled snapshots: `Eq(usave, u)` with `usave` saved on a
 ConditionalDimension — examples/seismic/tutorials/08_snapshotting.ipynb:455-505. CPU: the oracle stepped
-from Python reproduces the reference golden, the operator is recognised; GPU (pending):
+from Python reproduces the reference golden, the operator is recognised; GPU:
 `b2_iso_args.snap/snap_factor` against the golden."""
 import numpy as np
 import pytest
@@ -62,7 +62,6 @@ def test_snapshot_operator_is_recognised():
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 def test_snapshots_vs_reference_golden():
     g = load_golden('snap3d_so4')
     op, model, geometry, u, usave, rec, dt = _operator(g)
@@ -73,7 +72,6 @@ def test_snapshots_vs_reference_golden():
 
 
 @pytest.mark.gpu
-@pytest.mark.pending
 def test_snapshots_streamed_to_host_match_the_resident_run():
     """Host-resident snapshots are drained box by box on a copy stream while the stencil runs
     (SnapStreamer in b2_api_iso.cu); same values as the device-resident run, halo untouched."""
