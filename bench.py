@@ -274,6 +274,8 @@ class Bench:
         dv.configuration['deviceid'] = self.local
         self.dev = torch.device('cuda', self.local)
         self.L = _lib.lib()
+        from devito_b200.numa import bind_to_gpu
+        self.numa = bind_to_gpu(self.local)          # pinned host buffers on the GPU's own socket
         # The library enqueues on torch's current stream so that CUDA events recorded on that stream
         # bracket exactly its work (torch.cuda.Event only sees torch's current stream).
         self.stream = torch.cuda.Stream(device=self.dev)
@@ -382,15 +384,25 @@ class Bench:
         for _ in range(min(warmup, 1) or 1):
             hostcall()
         t = self.timed(hostcall, steps)
+        prof = (ctypes.c_double * 5)()
+        self.L.b2_last_call_profile(prof)
         h2d = u.storage.host_ro.nbytes + model.damp.storage.host_ro.nbytes + src.data.nbytes
         d2h = u.storage.host_ro.nbytes + rec.data.nbytes
+        streamed = prof[4] == 1.0
         return {"value": w['pts_step'] * steps / t / 1e9, "unit": "GPts/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": t / steps * 1e3}
+                "ms_per_step": t / steps * 1e3,
+                "mode": ("streamed: x-chunks uploaded / downloaded on copy streams while a skewed sweep time-steps the "
+                         "chunks already on the device" if streamed else
+                         "serial: host->device, time loop, device->host on one stream"),
+                "last_call_ms": {"before_loop": prof[0], "time_loop": prof[1], "after_loop": prof[2], "call": prof[3]},
+                "pinned_host": bool(getattr(u.storage, '_pinned', None) is not None),
+                "numa": self.numa}
 
     def release(self, w):
         w.clear()
         gc.collect()
+        self.L.b2_staging_cache_release()
         self.torch.cuda.empty_cache()
 
 

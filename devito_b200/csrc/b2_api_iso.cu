@@ -13,6 +13,8 @@
 #include <vector>
 #include <cstdlib>
 #include <string>
+#include <chrono>
+#include <algorithm>
 
 using namespace b2;
 
@@ -166,6 +168,187 @@ cudaEvent_t SnapStreamer::drained[2] = {nullptr, nullptr};
 
 }  // namespace b2
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Streamed time loop for a HOST-STAGED apply (the reference's per-apply copy semantics,
+// devito/passes/iet/definitions.py:636-671, without its serial copy-in / compute / copy-out):
+//
+// the x axis is cut into chunks of W planes. Chunk c of u (3 slots), damp and the parameter array travels
+// host -> device on a copy stream while the compute stream already time-steps the chunks that arrived —
+// skewed: in "phase" p, step s = 1..L updates x in [pW - (s-1)R, (p+1)W - (s-1)R), the dependency cone of
+// the R-point stencil, so every read is of planes that are uploaded and at the right time level, and the 3
+// rotating time slots are never overwritten early (the argument is spelled out in DESIGN.md §3.6). Planes
+// left of (p+1)W - (L-1)R are final after phase p and travel device -> host on a second copy stream while
+// the later phases compute (PCIe is full duplex). Injection deposits into the cells of the range just
+// updated; receivers add the partial sum over the cells of that range to their trace.
+//
+// Whole-call time ~ compute + first upload chunk + last download chunk instead of upload + compute + download.
+// ---------------------------------------------------------------------------------------------------------
+namespace b2 {
+
+static double g_last_profile[5] = {0, 0, 0, 0, 0};
+
+struct StreamedLoop {
+    cudaStream_t up = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    int init() {
+        if (!up) {
+            B2_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking), B2_ERR_DEVICE);
+            B2_CUDA(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking), B2_ERR_DEVICE);
+        }
+        used = 0;
+        return B2_OK;
+    }
+    cudaEvent_t next() {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            ev.push_back(e);
+        }
+        return ev[used++];
+    }
+};
+static StreamedLoop g_streamed;
+
+static bool streamed_wanted(const b2_iso_args *a, const IsoPlan &p, const DevArray &u) {
+    const char *e = getenv("B2_STREAM");
+    if (e && atoi(e) == 0) return false;
+    const bool forced = e && atoi(e) == 2;                 // tests: also on small grids
+    if (!u.owned || a->ndim != 3 || !p.use_tma || p.tsize != 3) return false;
+    if (a->halo || a->adjoint || a->free_surface || a->ot4 || a->born_U || a->snap || a->grad) return false;
+    const int L = a->time_M - a->time_m + 1;
+    if (L < 4 || p.n[0] < 8 * p.radius[0]) return false;
+    return forced || u.nbytes >= ((size_t)1 << 30);
+}
+
+static int iso_forward_streamed(const b2_iso_args *a, IsoPlan &p, FieldGeom g, DevArray &u, DevArray *damp,
+                                DevArray *param, SparseDev &src, SparseDev &rec, float scalar_scale, float dt2) {
+    int rc;
+    StreamedLoop &S = g_streamed;
+    if ((rc = S.init())) return rc;
+    const int n = p.n[0], R = p.radius[0], so = p.so, a0 = p.a[0];
+    const int L = a->time_M - a->time_m + 1;
+    const size_t plane = (size_t)p.sx;
+    int W = 128;
+    if (const char *e = getenv("B2_STREAM_W")) W = atoi(e);
+    W = std::max(W, 4 * R);
+    W = std::min(W, n);
+    const int K = (n + W - 1) / W;                                   // upload chunks
+    const int P = (n + (L - 1) * R + W - 1) / W;                     // phases of the skewed sweep
+    cudaStream_t cs = stream();
+
+    // everything the compute stream did so far (sparse tables, traces) precedes the copies
+    cudaEvent_t ev_start = S.next();
+    B2_CUDA(cudaEventRecord(ev_start, cs), B2_ERR_DEVICE);
+    B2_CUDA(cudaStreamWaitEvent(S.up, ev_start, 0), B2_ERR_DEVICE);
+    B2_CUDA(cudaStreamWaitEvent(S.down, ev_start, 0), B2_ERR_DEVICE);
+
+    // ---- enqueue every upload now: the copy stream works through them in order ----
+    std::vector<cudaEvent_t> up_ev(K);
+    std::vector<int> ulo(K), uhi(K);
+    for (int c = 0; c < K; ++c) {
+        ulo[c] = c == 0 ? 0 : uhi[c - 1];
+        uhi[c] = c == K - 1 ? a0 : std::min(a0, so + std::min(n, (c + 1) * W) + R);
+        const size_t off = (size_t)ulo[c] * plane, cnt = (size_t)(uhi[c] - ulo[c]) * plane * sizeof(float);
+        if (cnt) {
+            for (int t = 0; t < 3; ++t) {
+                const size_t o = (size_t)t * p.slot_elems + off;
+                B2_CUDA(cudaMemcpyAsync((float *)u.d + o, (const float *)u.h + o, cnt, cudaMemcpyHostToDevice, S.up),
+                        B2_ERR_MEMORY);
+            }
+            if (damp && damp->owned)
+                B2_CUDA(cudaMemcpyAsync((float *)damp->d + off, (const float *)damp->h + off, cnt,
+                                        cudaMemcpyHostToDevice, S.up), B2_ERR_MEMORY);
+            if (param && param->owned)
+                B2_CUDA(cudaMemcpyAsync((float *)param->d + off, (const float *)param->h + off, cnt,
+                                        cudaMemcpyHostToDevice, S.up), B2_ERR_MEMORY);
+        }
+        up_ev[c] = S.next();
+        B2_CUDA(cudaEventRecord(up_ev[c], S.up), B2_ERR_DEVICE);
+    }
+
+    // traces are accumulated range by range: clear the rows this call writes
+    if (rec.present) {
+        const int r0 = std::max(a->time_m, 0), r1 = std::min(a->time_M, rec.nt - 1);
+        if (r1 >= r0)
+            B2_CUDA(cudaMemsetAsync((float *)rec.data.d + (size_t)r0 * rec.npoint_total, 0,
+                                    (size_t)(r1 - r0 + 1) * rec.npoint_total * sizeof(float), cs), B2_ERR_MEMORY);
+    }
+
+    auto range_geom = [&](int xa, int xb) {
+        FieldGeom q = g;
+        q.lo[0] = xa;
+        q.hi[0] = xb - 1;
+        q.nb_lo = xa > 0;            // an interior cut: the cells beyond it belong to another range
+        q.nb_hi = xb < n;
+        q.restrict_x = true;
+        return q;
+    };
+
+    int dlo = 0;                                                     // allocated planes already sent back
+    for (int ph = 0; ph < P; ++ph) {
+        if (ph < K) {
+            B2_CUDA(cudaStreamWaitEvent(cs, up_ev[ph], 0), B2_ERR_DEVICE);
+            if ((rc = iso_coef_tabulate_planes(p, ulo[ph], uhi[ph]))) return rc;
+            if (rec.present && !a->rec_toff) {
+                // the initial time level is complete on the planes that just arrived
+                const int xa = std::max(0, ulo[ph] - so), xb = std::min(n, uhi[ph] - so);
+                if (xb > xa) {
+                    const int t0 = ((a->time_m % 3) + 3) % 3;
+                    if ((rc = launch_interp(rec, range_geom(xa, xb), p.u + (size_t)t0 * p.slot_elems, nullptr, a->time_m)))
+                        return rc;
+                }
+            }
+        }
+        for (int s = 1; s <= L; ++s) {
+            const int shift = (s - 1) * R;
+            const int xb = std::min(n, (ph + 1) * W - shift);
+            if (xb <= 0) break;
+            const int xa = std::max(0, ph * W - shift);
+            if (xa >= xb) continue;
+            const int time = a->time_m + s - 1;
+            const int t0 = ((time % 3) + 3) % 3, t1 = (((time + 1) % 3) + 3) % 3, t2 = (((time - 1) % 3) + 3) % 3;
+            if ((rc = iso_step(p, t0, t2, t1, xa, xb - xa))) return rc;
+            float *f1 = p.u + (size_t)t1 * p.slot_elems;
+            const FieldGeom q = range_geom(xa, xb);
+            if ((rc = launch_inject(src, q, f1, nullptr, time, p.param_kind, p.param, scalar_scale, dt2))) return rc;
+            // time level time+1 is now complete on [xa, xb)
+            if (rec.present) {
+                const int row = a->rec_toff ? time : time + 1;
+                if (row <= a->time_M && (rc = launch_interp(rec, q, f1, nullptr, row))) return rc;
+            }
+        }
+        // planes left of (ph+1)W - (L-1)R have seen all L steps: send them home while the sweep goes on
+        int dhi = ph == P - 1 ? a0 : std::min(a0, std::max(0, so + (ph + 1) * W - (L - 1) * R));
+        if (ph == P - 1 || dhi - dlo >= W / 2) {
+            if (dhi > dlo) {
+                cudaEvent_t e = S.next();
+                B2_CUDA(cudaEventRecord(e, cs), B2_ERR_DEVICE);
+                B2_CUDA(cudaStreamWaitEvent(S.down, e, 0), B2_ERR_DEVICE);
+                const size_t off = (size_t)dlo * plane, cnt = (size_t)(dhi - dlo) * plane * sizeof(float);
+                for (int t = 0; t < 3; ++t) {
+                    const size_t o = (size_t)t * p.slot_elems + off;
+                    B2_CUDA(cudaMemcpyAsync((float *)u.h + o, (const float *)u.d + o, cnt, cudaMemcpyDeviceToHost, S.down),
+                            B2_ERR_MEMORY);
+                }
+                dlo = dhi;
+            }
+        }
+    }
+    // the call returns when the last planes are home
+    cudaEvent_t ev_down = S.next();
+    B2_CUDA(cudaEventRecord(ev_down, S.down), B2_ERR_DEVICE);
+    B2_CUDA(cudaStreamWaitEvent(cs, ev_down, 0), B2_ERR_DEVICE);
+    return B2_OK;
+}
+
+}  // namespace b2
+
+extern "C" void b2_last_call_profile(double out[5]) {
+    for (int i = 0; i < 5; ++i) out[i] = b2::g_last_profile[i];
+}
+
 extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     if (!a || !a->u) { set_error("b2_iso_forward: NULL args"); return B2_ERR_INVALID; }
     if (a->ndim != 2 && a->ndim != 3) { set_error("b2_iso_forward: ndim must be 2 or 3"); return B2_ERR_INVALID; }
@@ -189,10 +372,16 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     IsoPlan p;
     FieldGeom g;
     bool staged_u = false, staged_damp = false, staged_param = false;
+    bool u_is_home = false;                       // the streamed loop already brought u back to the host
+    auto call_t0 = std::chrono::steady_clock::now();
+    for (double &v : g_last_profile) v = 0.0;
 
     auto cleanup = [&](int code) {
         // copy back what the reference would copy back (u and rec), free staged copies
-        int r1 = staged_u ? stage_out(u, code == B2_OK || code == B2_ERR_NAN) : B2_OK;
+        const auto d2h_t0 = std::chrono::steady_clock::now();
+        int r1 = staged_u ? stage_out(u, (code == B2_OK || code == B2_ERR_NAN) && !u_is_home) : B2_OK;
+        g_last_profile[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - d2h_t0).count();
+        g_last_profile[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - call_t0).count();
         if (staged_damp) stage_out(damp, false);
         if (staged_param) stage_out(param, false);
         if (staged_usave) stage_out(usave, false);
@@ -217,15 +406,27 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         return r1 ? r1 : r2;
     };
 
-    if ((rc = stage_in(a->u, nd + 1, u, true))) return cleanup(rc);
+    // A large host-staged wavefield is a candidate for the streamed time loop (copies overlapped with a
+    // skewed sweep, iso_forward_streamed): its uploads are then issued chunk by chunk, not here. Whether the
+    // call really streams is known once the plan exists; otherwise the deferred copies are issued below.
+    const bool maybe_stream = [&] {
+        const char *e = getenv("B2_STREAM");
+        if (e && atoi(e) == 0) return false;
+        if (nd != 3 || a->u->dmap || !a->u->data || !a->damp) return false;
+        if (a->halo || a->adjoint || a->free_surface || a->ot4 || a->born_U || a->born_dm || a->snap || a->grad || a->usave)
+            return false;
+        return true;
+    }();
+    call_t0 = std::chrono::steady_clock::now();
+    if ((rc = stage_in(a->u, nd + 1, u, !maybe_stream))) return cleanup(rc);
     staged_u = true;
     if (a->damp) {
-        if ((rc = stage_in(a->damp, nd, damp, true))) return cleanup(rc);
+        if ((rc = stage_in(a->damp, nd, damp, !maybe_stream))) return cleanup(rc);
         staged_damp = true;
     }
     if (a->param_kind != B2_PARAM_SCALAR) {
         if (!a->param) { set_error("b2_iso_forward: param array missing"); return cleanup(B2_ERR_INVALID); }
-        if ((rc = stage_in(a->param, nd, param, true))) return cleanup(rc);
+        if ((rc = stage_in(a->param, nd, param, !maybe_stream))) return cleanup(rc);
         staged_param = true;
     }
     if ((rc = sparse_stage_in(a->src, nd, src, true))) return cleanup(rc);
@@ -353,7 +554,21 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
                   "condition in this version");
         return cleanup(B2_ERR_INVALID);
     }
+    p.defer_coef = maybe_stream;
     if ((rc = iso_plan_init(p, a->kernel))) return cleanup(rc);
+    const bool streamed = maybe_stream && streamed_wanted(a, p, u);
+    if (maybe_stream && !streamed) {
+        // not streaming after all: the classic order — whole arrays in, tabulate, loop, whole arrays out
+        DevArray *arrs[3] = {&u, staged_damp ? &damp : nullptr, staged_param ? &param : nullptr};
+        for (DevArray *x : arrs)
+            if (x && x->owned)
+                if (cudaMemcpyAsync(x->d, x->h, x->nbytes, cudaMemcpyHostToDevice, stream()) != cudaSuccess) {
+                    set_error("b2_iso_forward: host -> device copy failed");
+                    return cleanup(B2_ERR_MEMORY);
+                }
+        p.defer_coef = false;
+        if (p.use_tma && (rc = iso_coef_tabulate_planes(p, 0, p.a[0]))) return cleanup(rc);
+    }
     // Born: a second plan for the linearised field (same geometry and coefficient tables, own tensor maps)
     IsoPlan pU = p;
     int dmh = 0;
@@ -405,6 +620,18 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     }
     if (a->halo) a->halo->p2p_primed = false;       // first step of a call exchanges through NCCL
     const int dir = a->adjoint ? -1 : 1;
+    // profile: [0] staging issued before the loop, [1] the loop (device clock)
+    cudaEvent_t pe_in = se.next(), pe_loop0 = nullptr, pe_loop1 = nullptr;
+    (void)pe_in;
+    pe_loop0 = se.next();
+    if (streamed) {
+        if ((rc = iso_forward_streamed(a, p, g, u, staged_damp ? &damp : nullptr, staged_param ? &param : nullptr, src, rec,
+                                       scalar_scale, dt2)))
+            return cleanup(rc);
+        u_is_home = true;
+        g_last_profile[4] = 1.0;
+    }
+    if (!streamed)
     for (int time = a->adjoint ? a->time_M : a->time_m; a->adjoint ? time >= a->time_m : time <= a->time_M;
          time += dir) {
         const int t0 = ((time % T) + T) % T;
@@ -506,11 +733,24 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     }
     if (a->halo && (rc = halo_p2p_drain(a->halo))) return cleanup(rc);
     if (timing && !per_step_events) ev_end = se.next();
+    pe_loop1 = se.next();
+    if (streamed && a->errctl) {
+        bool bad = false;
+        const int tl = (((a->time_M + 1) % T) + T) % T;
+        if ((rc = check_finite(p.u + (size_t)tl * p.slot_elems, p.slot_elems, bad))) return cleanup(rc);
+        if (bad) { set_error("NaN/Inf detected in u at time=%d", a->time_M); return cleanup(B2_ERR_NAN); }
+    }
 
     cudaError_t e = cudaStreamSynchronize(stream());
     if (e != cudaSuccess) {
         set_error("b2_iso_forward: device error: %s", cudaGetErrorString(e));
         return cleanup(B2_ERR_LAUNCH);
+    }
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pe_loop0, pe_loop1) == cudaSuccess) g_last_profile[1] = ms;
+        g_last_profile[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - call_t0).count()
+                            - g_last_profile[1];          // everything before the loop (staging in), host clock
     }
     if (timing) {
         if (per_step_events) {

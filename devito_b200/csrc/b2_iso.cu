@@ -481,19 +481,28 @@ static int coef_buffer(int which, size_t elems, float **out) {
     return B2_OK;
 }
 
+// tabulate the allocated x-planes [plane_lo, plane_hi) (the streamed time loop does it chunk by chunk, as
+// the damping / parameter planes arrive from the host)
+int iso_coef_tabulate_planes(const IsoPlan &p, int plane_lo, int plane_hi) {
+    if (plane_hi <= plane_lo) return B2_OK;
+    const float inv_dt = 1.0f / p.dt, inv_dt2 = 1.0f / (p.dt * p.dt);
+    const float md = (1.0f / (p.vp * p.vp)) * inv_dt2;
+    const size_t off = (size_t)plane_lo * (size_t)p.sx, cnt = (size_t)(plane_hi - plane_lo) * (size_t)p.sx;
+    k_iso_coef<<<148 * 8, 256, 0, stream()>>>(p.damp + off, p.param ? p.param + off : nullptr, p.param_kind, md, inv_dt,
+                                               inv_dt2, p.coefA + off, p.coefB ? p.coefB + off : nullptr, cnt);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
 static int iso_coef_tabulate(IsoPlan &p) {
     int rc;
     if ((rc = coef_buffer(0, p.slot_elems, &p.coefA))) return rc;
     p.coefB = nullptr;
     if (p.param_kind != B2_PARAM_SCALAR)
         if ((rc = coef_buffer(1, p.slot_elems, &p.coefB))) return rc;
-    const float inv_dt = 1.0f / p.dt, inv_dt2 = 1.0f / (p.dt * p.dt);
-    const float md = (1.0f / (p.vp * p.vp)) * inv_dt2;
-    k_iso_coef<<<148 * 8, 256, 0, stream()>>>(p.damp, p.param, p.param_kind, md, inv_dt, inv_dt2,
-                                               p.coefA, p.coefB, p.slot_elems);
-    count_launch();
-    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
-    return B2_OK;
+    if (p.defer_coef) return B2_OK;          // the caller tabulates plane ranges itself
+    return iso_coef_tabulate_planes(p, 0, p.a[0]);
 }
 
 template <int R>

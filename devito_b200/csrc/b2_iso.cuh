@@ -24,6 +24,7 @@ struct IsoPlan {
     bool use_tma = false;
     CUtensorMap tm_uh, tm_uc, tm_damp, tm_par;   // tm_damp/tm_par map coefA/coefB
     float *coefA = nullptr, *coefB = nullptr;    // tabulated update coefficients (library scratch)
+    bool defer_coef = false;                     // plan init only allocates them (streamed loop: per chunk)
     int lx = 0;
     // OT4 (b2_iso_args.ot4): generic two-pass path, W = lap(u)/m in library scratch
     bool ot4 = false;
@@ -44,6 +45,9 @@ struct IsoFuse {
 // Prepare the plan (decides generic vs TMA kernel, encodes tensor maps). `kernel`: 0 auto,
 // 1 force generic, 2 force TMA (error if the layout does not qualify).
 int iso_plan_init(IsoPlan &p, int kernel);
+
+// (Re)tabulate the coefficient tables on the allocated x-planes [plane_lo, plane_hi).
+int iso_coef_tabulate_planes(const IsoPlan &p, int plane_lo, int plane_hi);
 
 // One time step over x in [xlo, xlo + xcount) (relative to the iteration origin):
 // u[slot1] = update(u[slot0], u[slotm]).

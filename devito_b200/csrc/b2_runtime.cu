@@ -4,6 +4,7 @@
 // launch counter, kernel timing, small device-memory utilities.
 #include "b2_common.cuh"
 #include <cstdarg>
+#include <cstdlib>
 #include <vector>
 
 namespace b2 {
@@ -77,25 +78,60 @@ void timing_end() {
 // Small staging buffers (sparse tables, source/receiver traces) are recycled through a size-keyed
 // pool instead of cudaMalloc/cudaFree per call: cudaFree synchronises the whole device and both
 // cost ~0.1-1 ms, which showed up as a fixed per-apply overhead in the first benchmark.
+// Large staging buffers (the wavefields of a host-staged apply: 13.5 GB at 1024^3) are recycled too — a
+// production run applies the same operator shot after shot — up to B2_STAGING_CACHE_GB (default 64) of
+// cached bytes; beyond that, or when an allocation fails, the cache is drained.
 static std::vector<std::pair<size_t, void *>> g_pool_free;
-static const size_t kPoolMax = 64u << 20;
+static const size_t kPoolSmall = 64u << 20;
+static size_t g_pool_big_bytes = 0;
 
-static cudaError_t pool_alloc(void **p, size_t nbytes) {
-    if (nbytes <= kPoolMax) {
-        for (size_t i = 0; i < g_pool_free.size(); ++i) {
-            if (g_pool_free[i].first == nbytes) {
-                *p = g_pool_free[i].second;
-                g_pool_free.erase(g_pool_free.begin() + i);
-                return cudaSuccess;
-            }
+static size_t pool_big_cap() {
+    static size_t cap = 0;
+    static bool init = false;
+    if (!init) {
+        const char *e = getenv("B2_STAGING_CACHE_GB");
+        cap = (size_t)((e ? atof(e) : 64.0) * (double)(1ull << 30));
+        init = true;
+    }
+    return cap;
+}
+
+static void pool_drain_big() {
+    for (size_t i = 0; i < g_pool_free.size();) {
+        if (g_pool_free[i].first > kPoolSmall) {
+            cudaFree(g_pool_free[i].second);
+            g_pool_big_bytes -= g_pool_free[i].first;
+            g_pool_free.erase(g_pool_free.begin() + i);
+        } else {
+            ++i;
         }
     }
-    return cudaMalloc(p, nbytes);
+}
+
+static cudaError_t pool_alloc(void **p, size_t nbytes) {
+    for (size_t i = 0; i < g_pool_free.size(); ++i) {
+        if (g_pool_free[i].first == nbytes) {
+            *p = g_pool_free[i].second;
+            if (nbytes > kPoolSmall) g_pool_big_bytes -= nbytes;
+            g_pool_free.erase(g_pool_free.begin() + i);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, nbytes);
+    if (e != cudaSuccess && g_pool_big_bytes) {       // make room: drop what we cached and retry once
+        cudaGetLastError();
+        pool_drain_big();
+        e = cudaMalloc(p, nbytes);
+    }
+    return e;
 }
 
 static void pool_release(void *p, size_t nbytes) {
-    if (nbytes <= kPoolMax && g_pool_free.size() < 256) {
+    if (nbytes <= kPoolSmall) {
+        if (g_pool_free.size() < 256) { g_pool_free.emplace_back(nbytes, p); return; }
+    } else if (g_pool_big_bytes + nbytes <= pool_big_cap() && g_pool_free.size() < 256) {
         g_pool_free.emplace_back(nbytes, p);
+        g_pool_big_bytes += nbytes;
         return;
     }
     cudaFree(p);
@@ -153,6 +189,12 @@ int b2_device_count(void) {
 }
 
 const char *b2_last_error(void) { return g_last_error.c_str(); }
+
+int b2_device_pci_bus_id(int deviceid, char *out, int len) {
+    if (!out || len < 16) return B2_ERR_INVALID;
+    if (cudaDeviceGetPCIBusId(out, len, deviceid) != cudaSuccess) { cudaGetLastError(); return B2_ERR_DEVICE; }
+    return B2_OK;
+}
 
 const char *b2_version(void) { return "b200stencil 0.1 (sm_100a)"; }
 
@@ -216,5 +258,10 @@ int b2_synchronize(int deviceid) {
 }
 
 void b2_set_stream(void *s) { g_user_stream = (cudaStream_t)s; }
+
+void b2_staging_cache_release(void) {
+    std::lock_guard<std::mutex> lock(api_mutex());
+    pool_drain_big();
+}
 
 }  // extern "C"

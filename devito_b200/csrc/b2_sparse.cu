@@ -99,7 +99,7 @@ k_inject(SparseK k, float *__restrict__ f0, float *__restrict__ f1, int time, in
 
 __global__ void __launch_bounds__(128)
 k_interp(SparseK k, const float *__restrict__ f0, const float *__restrict__ f1,
-         float *__restrict__ out, int time) {
+         float *__restrict__ out, int time, int accumulate) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= k.p_cnt) return;
@@ -118,13 +118,17 @@ k_interp(SparseK k, const float *__restrict__ f0, const float *__restrict__ f1,
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) out[(long long)time * k.npoint_total + p] = sum;
+    if (lane == 0) {
+        // streamed time loop: the support of a point is sampled x-range by x-range (partial sums)
+        if (accumulate) { if (sum != 0.f) atomicAdd(out + (long long)time * k.npoint_total + p, sum); }
+        else out[(long long)time * k.npoint_total + p] = sum;
+    }
 }
 
 static SparseK make_k(const SparseDev &s, const FieldGeom &g, bool injecting) {
     SparseK k;
-    k.ext_lo0 = (injecting && g.nb_lo) ? 0 : s.r;
-    k.ext_hi0 = (injecting && g.nb_hi) ? 0 : s.r;
+    k.ext_lo0 = ((injecting || g.restrict_x) && g.nb_lo) ? 0 : s.r;
+    k.ext_hi0 = ((injecting || g.restrict_x) && g.nb_hi) ? 0 : s.r;
     k.peer_lo = injecting ? g.peer_lo : nullptr;
     k.peer_hi = injecting ? g.peer_hi : nullptr;
     k.off_lo = g.off_lo; k.off_hi = g.off_hi;
@@ -213,7 +217,7 @@ int launch_interp(const SparseDev &s, const FieldGeom &g, const float *f0, const
     SparseK k = make_k(s, g, false);
     const int warps = k.p_cnt;
     const int blocks = (warps * 32 + 127) / 128;
-    k_interp<<<blocks, 128, 0, stream()>>>(k, f0, f1, (float *)s.data.d, time);
+    k_interp<<<blocks, 128, 0, stream()>>>(k, f0, f1, (float *)s.data.d, time, g.restrict_x ? 1 : 0);
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
     return B2_OK;

@@ -25,6 +25,9 @@ struct FieldGeom {
     // x-slab decomposition: a neighbour owns the cells beyond x_m / x_M, so injection must not
     // touch them (the owner injects and its boundary planes are then exchanged)
     bool nb_lo = false, nb_hi = false;
+    // streamed time loop (b2_api_iso.cu): [lo[0], hi[0]] is one x-range of a skewed sweep; interpolation then
+    // samples only the cells of that range and ADDS its partial sum to the trace
+    bool restrict_x = false;
     // fused halo step: cells injected into the first / last `pw` owned planes are mirrored into the
     // neighbour's halo copy (the sweep kernel stored those planes there before the injection)
     float *peer_lo = nullptr, *peer_hi = nullptr;

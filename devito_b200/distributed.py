@@ -50,6 +50,10 @@ def init_distributed(backend=None):
     world.size = dist.get_world_size()
     world.initialized = True
     configuration['mpi'] = True
+    if torch.cuda.is_available():
+        # one process per GPU: live on the socket the GPU hangs off (what `mpirun --bind-to` does for the reference)
+        from .numa import bind_to_gpu
+        world.numa = bind_to_gpu(int(os.environ.get('LOCAL_RANK', '0')))
     return world
 
 

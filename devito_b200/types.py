@@ -377,6 +377,13 @@ class FieldStorage:
             if torch.cuda.is_available() and n * self.dtype.itemsize >= (1 << 20):
                 tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
                        np.dtype(np.float64): torch.float64}[self.dtype]
+                try:
+                    from .numa import bind_to_gpu
+                    from .parameters import configuration
+                    dev = configuration['deviceid']
+                    bind_to_gpu(torch.cuda.current_device() if dev is None or dev < 0 else dev)
+                except Exception:
+                    pass
                 self._pinned = torch.zeros(self.shape, dtype=tdt, pin_memory=True)
                 self._host = self._pinned.numpy()
                 return

@@ -242,6 +242,9 @@ int   b2_halo_p2p_register(b2_halo_ctx *ctx, void *local_base, void *left_base, 
 
 /* ---- utilities ---------------------------------------------------------------------------- */
 int         b2_device_count(void);
+/* PCI bus id ("0000:3b:00.0") of a device: the host side uses it to place its pinned buffers and threads
+ * on the NUMA node next to the GPU (devito_b200/numa.py). */
+int         b2_device_pci_bus_id(int deviceid, char *out, int len);
 const char *b2_last_error(void);
 const char *b2_version(void);
 /* number of kernels launched by this library since load (for bench.py `gpu_launches`) */
@@ -261,6 +264,13 @@ int   b2_synchronize(int deviceid);
 /* make the library enqueue its work on an externally owned CUDA stream (cudaStream_t as
  * void*); NULL -> the library's own non-blocking stream. */
 void  b2_set_stream(void *stream);
+/* Host-staged applies recycle their device staging buffers across calls (up to B2_STAGING_CACHE_GB,
+ * default 64): release what is cached. */
+void  b2_staging_cache_release(void);
+/* Phase times (ms) of the last b2_iso_forward call on this process: [0] host->device staging issued
+ * before the time loop, [1] time loop, [2] device->host after the loop, [3] whole call (device clock);
+ * [4] = 1 when the call ran the streamed (skewed, copy-overlapped) time loop. */
+void  b2_last_call_profile(double out[5]);
 
 #ifdef __cplusplus
 }

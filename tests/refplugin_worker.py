@@ -130,7 +130,7 @@ def gpu():
         got = float(norm(rec)), float(np.linalg.norm(np.asarray(u, dtype=np.float64)))
         out[tag] = got
         assert np.isclose(got[0], gold[tag]['norm_rec'], rtol=2e-4), (tag, got, gold[tag])
-        assert np.isclose(got[1], gold[tag]['norm_u'], rtol=2e-4), (tag, got, gold[tag])
+        assert np.isclose(got[1], gold[tag]['norm_u'], rtol=1e-3 if 'ot4' in tag else 2e-4), (tag, got, gold[tag])
     for tag, kw in [('tti_layers_so4', dict()), ('tti_const_so8', dict(preset='constant-tti', space_order=8))]:
         _, _, _, [rec, u, v] = trun(dtype=np.float32, **kw)
         got = float(norm(rec)), float(norm(u)), float(norm(v))

@@ -140,6 +140,55 @@ def test_host_staged_call_equals_resident_call():
     assert np.array_equal(np.asarray(rec1.data), np.asarray(rec2.data))
 
 
+def _last_call_streamed():
+    import ctypes
+    from devito_b200 import _lib
+    prof = (ctypes.c_double * 5)()
+    _lib.lib().b2_last_call_profile(prof)
+    return prof[4] == 1.0
+
+
+@pytest.mark.parametrize('interp,so,W', [('linear', 8, 16), ('sinc', 8, 24), ('linear', 4, 16)])
+def test_streamed_time_loop_equals_resident_call(interp, so, W, monkeypatch):
+    """Host-staged applies of large grids run the streamed time loop (uploads / downloads overlapped with a
+    skewed sweep, b2_api_iso.cu::iso_forward_streamed). Forced here on a small grid with narrow chunks
+    (several x-ranges cut through the source and receiver supports): the wavefield must be bit-identical to
+    the resident call, the traces equal up to the summation order of the partial sums."""
+    model, geometry, solver = _solver('iso', so, 40, 12, 130.0, interp)
+    rec1, u1, _ = solver.forward()
+    assert not _last_call_streamed()
+    monkeypatch.setenv('B2_STREAM', '2')
+    monkeypatch.setenv('B2_STREAM_W', str(W))
+    rec2, u2, _ = solver.forward(resident=False)
+    assert _last_call_streamed()
+    assert np.array_equal(np.asarray(u1.data_with_halo), np.asarray(u2.data_with_halo))
+    assert rel_linf(rec2.data, rec1.data) < 1e-6
+    # sub-ranges of the time axis (restart) and a trace that samples the updated level (rec_toff)
+    from devito_b200 import TimeFunction
+    u3 = TimeFunction(name='u', grid=model.grid, time_order=2, space_order=so)
+    rec3 = geometry.rec
+    mid = geometry.nt // 2
+    solver.forward(u=u3, rec=rec3, time_m=1, time_M=mid, resident=False)
+    assert _last_call_streamed()
+    solver.forward(u=u3, rec=rec3, time_m=mid + 1, time_M=geometry.nt - 2, resident=False)
+    assert np.array_equal(np.asarray(u1.data), np.asarray(u3.data))
+    assert rel_linf(rec3.data, rec1.data) < 1e-6
+
+
+def test_streamed_time_loop_array_velocity(monkeypatch):
+    g = load_golden('iso3d_so4_layers')
+    from devito_b200.seismic import demo_model, setup_geometry, AcousticWaveSolver
+    model = demo_model('layers-isotropic', spacing=(10., 10., 10.), shape=(20, 20, 20), nbl=8,
+                       space_order=4, nlayers=3)
+    solver = AcousticWaveSolver(model, setup_geometry(model, float(g['tn'])), space_order=4)
+    monkeypatch.setenv('B2_STREAM', '2')
+    monkeypatch.setenv('B2_STREAM_W', '12')
+    rec, u, _ = solver.forward(resident=False)
+    assert _last_call_streamed()
+    assert rel_linf(u.data, g['u']) < 1e-5
+    assert rel_linf(rec.data, g['rec']) < 1e-5
+
+
 def test_restart_on_time_subranges():
     """Second caller of the C ABI in the reference (checkpointing/checkpoint.py:30-46): the loop
     must be restartable on arbitrary [time_m, time_M] sub-ranges."""
