@@ -92,6 +92,64 @@ __device__ __forceinline__ void st_release_sys(int *p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) -----------------------------------------
+// One instruction does two fp32 operations on an aligned register pair. The FP32 pipe rate is unchanged
+// (profiles/r2b_micro_*: 127 FMA/clk/SM either way); what it halves is ISSUE SLOTS — the limiter of the
+// TTI kernel (ncu r1g: 169 instructions/point, 66 % issue utilisation, HBM at 51 %).
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a float4 as two packed pairs (x,y) (z,w): what LDS.128 / LDG.128 deliver in aligned register quads
+struct F4 {
+    u64 a, b;
+};
+__device__ __forceinline__ F4 f4pack(const float4 &v) { return F4{pk2(v.x, v.y), pk2(v.z, v.w)}; }
+__device__ __forceinline__ float4 f4unpack(const F4 &p) {
+    float4 v;
+    upk2(p.a, v.x, v.y);
+    upk2(p.b, v.z, v.w);
+    return v;
+}
+__device__ __forceinline__ F4 f4zero() { return F4{0ull, 0ull}; }
+__device__ __forceinline__ void f4fma2(F4 &acc, float2 w, const F4 &v) {     // w = {w, w}
+    const u64 ww = pk2(w.x, w.y);
+    acc.a = fma2(ww, v.a, acc.a);
+    acc.b = fma2(ww, v.b, acc.b);
+}
+__device__ __forceinline__ F4 f4add2(const F4 &x, const F4 &y) { return F4{add2(x.a, y.a), add2(x.b, y.b)}; }
+__device__ __forceinline__ F4 f4sub2(const F4 &x, const F4 &y) { return F4{sub2(x.a, y.a), sub2(x.b, y.b)}; }
+__device__ __forceinline__ F4 f4mul2(float2 w, const F4 &v) {
+    const u64 ww = pk2(w.x, w.y);
+    return F4{mul2(ww, v.a), mul2(ww, v.b)};
+}
+
 __device__ __forceinline__ float4 lds128(const float *p) {
     return *reinterpret_cast<const float4 *>(p);
 }

@@ -172,6 +172,9 @@ struct TtiFK {
     float e2, sd;              // 1+2eps, sqrt(1+2delta)
     float w2x[5], w2y[5], w2z[5];
     float w1x[4], w1y[4], w1z[4];      // already multiplied by cx, cy, cz
+    // {w, w} pairs for the packed fp32x2 arithmetic of k_tti_ws (they sit in uniform registers)
+    float2 p_w2x[5], p_w2y[5], p_w1x[4], p_w1y[4];
+    float2 p_wc, p_e2, p_sd, p_mdt2;
 };
 
 template <int R, int TY>
@@ -489,7 +492,7 @@ struct TtiWsCfg {
     static constexpr size_t SMEM = (size_t)((NUU + NUV) * PLANE + 2 * NG * GPLANE) * 4 + 2 * NB * 8 + 128;
 };
 
-template <int TY>
+template <int TY, int PF>
 __global__ void __launch_bounds__(TY * 16 + 128, 1)
 k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v, const TtiFK k) {
     using C = TtiWsCfg<TY>;
@@ -636,75 +639,89 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
     const int my_goff = (ty + H) * BZ + RZ + 4 * tz4;
     const long long gidx0 = (long long)(k.oy + gy) * k.sy + (k.oz + gz);
 
-    float4 uq[2 * R + 1], vq[R], gqu[R], gqv[R];
+    using b2ptx::F4;
+    // Register queues with STATIC slots: the loop is unrolled 4x, plane x+k of a 4-deep queue lives in slot
+    // (p + k) & 3 with p = it & 3, so advancing the sweep by one plane moves no data (the first version
+    // shifted 18 float4 per iteration: a fifth of the main warps' instructions). The 9-plane x-history of u is
+    // split into fut (planes x+1..x+4), cen (plane x) and pst (planes x-4..x-1): two float4 copies per plane.
+    static_assert(R == 4 && NB == 4, "static queue slots assume 4-deep queues");
+    F4 fut[4], pst[4], cen = b2ptx::f4zero(), vq[4], gqu[4], gqv[4];
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i <= 2 * R; ++i) uq[i] = zero4;
-#pragma unroll
-    for (int i = 0; i < R; ++i) { vq[i] = zero4; gqu[i] = zero4; gqv[i] = zero4; }
-    const float wc = k.w2x[0] + k.w2y[0] + k.w2z[0];
+    for (int i = 0; i < 4; ++i) {
+        fut[i] = b2ptx::f4zero(); pst[i] = b2ptx::f4zero();
+        vq[i] = b2ptx::f4zero(); gqu[i] = b2ptx::f4zero(); gqv[i] = b2ptx::f4zero();
+    }
     long long gi = (long long)(k.ox + xs - PRE) * k.sx + gidx0;
     int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
         ig = ((xs - PRE) % NG + NG) % NG;
     float4 nu = zero4, nv = zero4, na = zero4;      // prefetched u[t-1], v[t-1], A of plane x+1
     float4 mu = zero4, mv = zero4, ma = zero4;      // ... and of plane x+2
 
-    for (int it = 0; it < NIT; ++it) {
+    for (int itb = 0; itb < NIT; itb += 4) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int it = itb + p;
+        if (it >= NIT) break;
         const int x = xs - PRE + it;
-        b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
-        // queues: uq[i] = u plane x-R+i, vq[i] = v plane x+i, gq*[i] = Gz plane x-H+i
-#pragma unroll
-        for (int i = 0; i < 2 * R; ++i) uq[i] = uq[i + 1];
-#pragma unroll
-        for (int i = 0; i < R - 1; ++i) { vq[i] = vq[i + 1]; gqu[i] = gqu[i + 1]; gqv[i] = gqv[i + 1]; }
-        uq[2 * R] = b2ptx::lds128(s_u + wrap(iu + R, NUU) * PLANE + my_off);
-        vq[R - 1] = b2ptx::lds128(s_v + wrap(iv + R - 1, NUV) * PLANE + my_off);
+        b2ptx::mbar_wait(&full[p], (itb >> 2) & 1);
+        // u plane x+k: fut[(p+k)&3] (k = 1..4), cen (k = 0), pst[(p+k)&3] (k = -4..-1);
+        // v plane x+k: vq[(p+k)&3] (k = 0..3); Gz plane x+k: gq*[(p+k)&3] (k = -2..1)
+        pst[(p + 3) & 3] = cen;
+        cen = fut[p];
+        fut[p] = b2ptx::f4pack(b2ptx::lds128(s_u + wrap(iu + R, NUU) * PLANE + my_off));
+        vq[(p + 3) & 3] = b2ptx::f4pack(b2ptx::lds128(s_v + wrap(iv + R - 1, NUV) * PLANE + my_off));
 
         // ---- stage A: own-column Gz(u), Gz(v) at plane g = x + 1 ----
+        // x and y taps in packed fp32x2 (two FMAs per instruction), the z taps — whose operands straddle
+        // the register pairs — in scalar form
         {
-            float4 ru = zero4, rv = zero4;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {            // x taps: planes x+j, from registers
-                f4fma_(ru, k.w1x[j], uq[R + j]);
-                f4fma_(rv, k.w1x[j], vq[j]);
-            }
             const float *uc = s_u + wrap(iu + 1, NUU) * PLANE + my_off;
             const float *vc = s_v + wrap(iv + 1, NUV) * PLANE + my_off;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {            // y taps: rows y-1..y+2 (own row from registers)
-                const float4 a = (j == H - 1) ? uq[R + 1] : b2ptx::lds128(uc + (j - H + 1) * BZ);
-                const float4 c = (j == H - 1) ? vq[1] : b2ptx::lds128(vc + (j - H + 1) * BZ);
-                f4fma_(ru, k.w1y[j], a);
-                f4fma_(rv, k.w1y[j], c);
-            }
+            float4 ru, rv;
             {
                 // D+z needs z-1 .. z+5 of the row: one float left, two floats right (4-byte and
                 // 8-byte shared loads cost 1 and 2 wavefronts per warp instead of 4)
                 const float lu = uc[-1], lv = vc[-1];
                 const float2 ru_ = *reinterpret_cast<const float2 *>(uc + 4);
                 const float2 rv_ = *reinterpret_cast<const float2 *>(vc + 4);
-                const float4 cu = uq[R + 1], cv = vq[1];
+                const float4 cu = b2ptx::f4unpack(fut[(p + 1) & 3]), cv = b2ptx::f4unpack(vq[(p + 1) & 3]);
                 const float zu[7] = {lu, cu.x, cu.y, cu.z, cu.w, ru_.x, ru_.y};
                 const float zv[7] = {lv, cv.x, cv.y, cv.z, cv.w, rv_.x, rv_.y};
+                ru = make_float4(k.w1z[0] * zu[0], k.w1z[0] * zu[1], k.w1z[0] * zu[2], k.w1z[0] * zu[3]);
+                rv = make_float4(k.w1z[0] * zv[0], k.w1z[0] * zv[1], k.w1z[0] * zv[2], k.w1z[0] * zv[3]);
 #pragma unroll
-                for (int j = 0; j < R; ++j) {          // offsets j-1 relative to each of the 4 points
+                for (int j = 1; j < R; ++j) {          // offsets j-1 relative to each of the 4 points
                     ru.x = fmaf(k.w1z[j], zu[j + 0], ru.x); ru.y = fmaf(k.w1z[j], zu[j + 1], ru.y);
                     ru.z = fmaf(k.w1z[j], zu[j + 2], ru.z); ru.w = fmaf(k.w1z[j], zu[j + 3], ru.w);
                     rv.x = fmaf(k.w1z[j], zv[j + 0], rv.x); rv.y = fmaf(k.w1z[j], zv[j + 1], rv.y);
                     rv.z = fmaf(k.w1z[j], zv[j + 2], rv.z); rv.w = fmaf(k.w1z[j], zv[j + 3], rv.w);
                 }
             }
-            gqu[R - 1] = ru;
-            gqv[R - 1] = rv;
+            F4 pu_ = b2ptx::f4pack(ru), pv_ = b2ptx::f4pack(rv);
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // x taps: planes x+j, from registers
+                b2ptx::f4fma2(pu_, k.p_w1x[j], j == 0 ? cen : fut[(p + j) & 3]);
+                b2ptx::f4fma2(pv_, k.p_w1x[j], vq[(p + j) & 3]);
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // y taps: rows y-1..y+2 (own row from registers)
+                const F4 a = (j == H - 1) ? fut[(p + 1) & 3] : b2ptx::f4pack(b2ptx::lds128(uc + (j - H + 1) * BZ));
+                const F4 c = (j == H - 1) ? vq[(p + 1) & 3] : b2ptx::f4pack(b2ptx::lds128(vc + (j - H + 1) * BZ));
+                b2ptx::f4fma2(pu_, k.p_w1y[j], a);
+                b2ptx::f4fma2(pv_, k.p_w1y[j], c);
+            }
+            gqu[(p + 1) & 3] = pu_;
+            gqv[(p + 1) & 3] = pv_;
             const int sgz = wrap(ig + 1, NG) * GPLANE + my_goff;
-            *reinterpret_cast<float4 *>(s_gu + sgz) = ru;
-            *reinterpret_cast<float4 *>(s_gv + sgz) = rv;
+            *reinterpret_cast<float4 *>(s_gu + sgz) = b2ptx::f4unpack(pu_);
+            *reinterpret_cast<float4 *>(s_gv + sgz) = b2ptx::f4unpack(pv_);
         }
         // u[t-1], v[t-1], A: loaded one full iteration before they are used (the registers are
         // there: the main warpgroups own 152 each after setmaxnreg)
         const float4 pu = nu, pv = nv, pa = na;
-        nu = mu; nv = mv; na = ma;
-        {
+        if (PF == 2) {
+            nu = mu; nv = mv; na = ma;
             // two-deep register prefetch; full 16-byte loads even on overhanging tiles (the row's
             // halo makes them safe, stores are masked)
             const long long gn = gi + 2 * k.sx;             // plane x + 2
@@ -713,80 +730,91 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
                 mv = *reinterpret_cast<const float4 *>(k.vm + gn);
                 ma = *reinterpret_cast<const float4 *>(k.A + gn);
             }
+        } else {
+            // one-deep: 12 registers less (the 4x unrolled body with static queue slots is register-bound)
+            const long long gn = gi + k.sx;                 // plane x + 1
+            if (x + 1 >= xs && x + 1 < xe && zcnt > 0) {
+                nu = *reinterpret_cast<const float4 *>(k.um + gn);
+                nv = *reinterpret_cast<const float4 *>(k.vm + gn);
+                na = *reinterpret_cast<const float4 *>(k.A + gn);
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NSYNC) : "memory");
 
         // ---- stage B: output plane x ----
         if (x >= xs) {
             const float *cpl = s_u + iu * PLANE + my_off;
-            const float4 c = uq[R];
-            const float4 vcn = vq[0];
-            float4 lap = make_float4(wc * c.x, wc * c.y, wc * c.z, wc * c.w);
-            {
-                const float4 l = b2ptx::lds128(cpl - 4), r = b2ptx::lds128(cpl + 4);
-                const float zr[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int i = 1; i <= R; ++i) {
-                    lap.x = fmaf(k.w2z[i], zr[4 - i] + zr[4 + i], lap.x);
-                    lap.y = fmaf(k.w2z[i], zr[5 - i] + zr[5 + i], lap.y);
-                    lap.z = fmaf(k.w2z[i], zr[6 - i] + zr[6 + i], lap.z);
-                    lap.w = fmaf(k.w2z[i], zr[7 - i] + zr[7 + i], lap.w);
-                }
-            }
-#pragma unroll
-            for (int i = 1; i <= R; ++i) {
-                const float4 a = b2ptx::lds128(cpl - i * BZ), bb = b2ptx::lds128(cpl + i * BZ);
-                lap.x = fmaf(k.w2y[i], a.x + bb.x, lap.x); lap.y = fmaf(k.w2y[i], a.y + bb.y, lap.y);
-                lap.z = fmaf(k.w2y[i], a.z + bb.z, lap.z); lap.w = fmaf(k.w2y[i], a.w + bb.w, lap.w);
-            }
-#pragma unroll
-            for (int i = 1; i <= R; ++i) {
-                const float4 a = uq[R - i], bb = uq[R + i];
-                lap.x = fmaf(k.w2x[i], a.x + bb.x, lap.x); lap.y = fmaf(k.w2x[i], a.y + bb.y, lap.y);
-                lap.z = fmaf(k.w2x[i], a.z + bb.z, lap.z); lap.w = fmaf(k.w2x[i], a.w + bb.w, lap.w);
-            }
-            float4 zu4 = zero4, zv4 = zero4;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {            // x direction: own Gz history (registers)
-                f4fma_(zu4, k.w1x[j], gqu[j]);
-                f4fma_(zv4, k.w1x[j], gqv[j]);
-            }
+            const F4 c = cen;
+            const F4 vcn = vq[p];
             const float *gpu_ = s_gu + ig * GPLANE + my_goff;
             const float *gpv_ = s_gv + ig * GPLANE + my_goff;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {            // y direction: rows y-2..y+1 (own row from registers)
-                const float4 a = (j == H) ? gqu[H] : b2ptx::lds128(gpu_ + (j - H) * BZ);
-                const float4 bb = (j == H) ? gqv[H] : b2ptx::lds128(gpv_ + (j - H) * BZ);
-                f4fma_(zu4, k.w1y[j], a);
-                f4fma_(zv4, k.w1y[j], bb);
-            }
+            // z direction (scalar): Laplacian taps and D-z of Gz
+            float4 lapz, zuz, zvz;
             {
+                const float4 cc = b2ptx::f4unpack(c);
+                const float4 l = b2ptx::lds128(cpl - 4), r = b2ptx::lds128(cpl + 4);
+                const float zr[12] = {l.x, l.y, l.z, l.w, cc.x, cc.y, cc.z, cc.w, r.x, r.y, r.z, r.w};
+                lapz.x = k.w2z[1] * (zr[3] + zr[5]); lapz.y = k.w2z[1] * (zr[4] + zr[6]);
+                lapz.z = k.w2z[1] * (zr[5] + zr[7]); lapz.w = k.w2z[1] * (zr[6] + zr[8]);
+#pragma unroll
+                for (int i = 2; i <= R; ++i) {
+                    lapz.x = fmaf(k.w2z[i], zr[4 - i] + zr[4 + i], lapz.x);
+                    lapz.y = fmaf(k.w2z[i], zr[5 - i] + zr[5 + i], lapz.y);
+                    lapz.z = fmaf(k.w2z[i], zr[6 - i] + zr[6 + i], lapz.z);
+                    lapz.w = fmaf(k.w2z[i], zr[7 - i] + zr[7 + i], lapz.w);
+                }
                 // D-z needs z-2 .. z+4: two floats left, one float right
                 const float2 lu = *reinterpret_cast<const float2 *>(gpu_ - 2);
                 const float2 lv = *reinterpret_cast<const float2 *>(gpv_ - 2);
                 const float ru_ = gpu_[4], rv_ = gpv_[4];
-                const float4 cu = gqu[H], cv = gqv[H];
+                const float4 cu = b2ptx::f4unpack(gqu[p]), cv = b2ptx::f4unpack(gqv[p]);
                 const float au[7] = {lu.x, lu.y, cu.x, cu.y, cu.z, cu.w, ru_};
                 const float av[7] = {lv.x, lv.y, cv.x, cv.y, cv.z, cv.w, rv_};
+                zuz = make_float4(k.w1z[0] * au[0], k.w1z[0] * au[1], k.w1z[0] * au[2], k.w1z[0] * au[3]);
+                zvz = make_float4(k.w1z[0] * av[0], k.w1z[0] * av[1], k.w1z[0] * av[2], k.w1z[0] * av[3]);
 #pragma unroll
-                for (int j = 0; j < R; ++j) {          // offsets j-2
-                    zu4.x = fmaf(k.w1z[j], au[j + 0], zu4.x); zu4.y = fmaf(k.w1z[j], au[j + 1], zu4.y);
-                    zu4.z = fmaf(k.w1z[j], au[j + 2], zu4.z); zu4.w = fmaf(k.w1z[j], au[j + 3], zu4.w);
-                    zv4.x = fmaf(k.w1z[j], av[j + 0], zv4.x); zv4.y = fmaf(k.w1z[j], av[j + 1], zv4.y);
-                    zv4.z = fmaf(k.w1z[j], av[j + 2], zv4.z); zv4.w = fmaf(k.w1z[j], av[j + 3], zv4.w);
+                for (int j = 1; j < R; ++j) {          // offsets j-2
+                    zuz.x = fmaf(k.w1z[j], au[j + 0], zuz.x); zuz.y = fmaf(k.w1z[j], au[j + 1], zuz.y);
+                    zuz.z = fmaf(k.w1z[j], au[j + 2], zuz.z); zuz.w = fmaf(k.w1z[j], au[j + 3], zuz.w);
+                    zvz.x = fmaf(k.w1z[j], av[j + 0], zvz.x); zvz.y = fmaf(k.w1z[j], av[j + 1], zvz.y);
+                    zvz.z = fmaf(k.w1z[j], av[j + 2], zvz.z); zvz.w = fmaf(k.w1z[j], av[j + 3], zvz.w);
                 }
             }
-            float4 ou, ov;
-#define B2_TTI_UPD(F)                                                              \
-            {                                                                      \
-                const float gh = lap.F - zu4.F;                                    \
-                const float H0 = fmaf(k.e2, gh, k.sd * zv4.F);                     \
-                const float Hz = fmaf(k.sd, gh, zv4.F);                            \
-                ou.F = fmaf(pa.F, fmaf(k.m_dt2, c.F - pu.F, H0), c.F);             \
-                ov.F = fmaf(pa.F, fmaf(k.m_dt2, vcn.F - pv.F, Hz), vcn.F);         \
+            // x and y directions, packed
+            F4 lap = b2ptx::f4pack(lapz);
+            b2ptx::f4fma2(lap, k.p_wc, c);
+#pragma unroll
+            for (int i = 1; i <= R; ++i) {
+                const F4 a = b2ptx::f4pack(b2ptx::lds128(cpl - i * BZ)), bb = b2ptx::f4pack(b2ptx::lds128(cpl + i * BZ));
+                b2ptx::f4fma2(lap, k.p_w2y[i], b2ptx::f4add2(a, bb));
             }
-            B2_TTI_UPD(x) B2_TTI_UPD(y) B2_TTI_UPD(z) B2_TTI_UPD(w)
-#undef B2_TTI_UPD
+#pragma unroll
+            for (int i = 1; i <= R; ++i) b2ptx::f4fma2(lap, k.p_w2x[i], b2ptx::f4add2(pst[(p + 4 - i) & 3], fut[(p + i) & 3]));
+            F4 zu4 = b2ptx::f4pack(zuz), zv4 = b2ptx::f4pack(zvz);
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // x direction: own Gz history (registers)
+                b2ptx::f4fma2(zu4, k.p_w1x[j], gqu[(p + 2 + j) & 3]);
+                b2ptx::f4fma2(zv4, k.p_w1x[j], gqv[(p + 2 + j) & 3]);
+            }
+#pragma unroll
+            for (int j = 0; j < R; ++j) {            // y direction: rows y-2..y+1 (own row from registers)
+                const F4 a = (j == H) ? gqu[p] : b2ptx::f4pack(b2ptx::lds128(gpu_ + (j - H) * BZ));
+                const F4 bb = (j == H) ? gqv[p] : b2ptx::f4pack(b2ptx::lds128(gpv_ + (j - H) * BZ));
+                b2ptx::f4fma2(zu4, k.p_w1y[j], a);
+                b2ptx::f4fma2(zv4, k.p_w1y[j], bb);
+            }
+            // coupled update: f+ = f + A (m/dt^2 (f - f-) + H), H0 = e2 gh + sd Gzz(v), Hz = sd gh + Gzz(v)
+            const F4 gh = b2ptx::f4sub2(lap, zu4);
+            F4 H0 = b2ptx::f4mul2(k.p_sd, zv4);
+            b2ptx::f4fma2(H0, k.p_e2, gh);
+            F4 Hz = zv4;
+            b2ptx::f4fma2(Hz, k.p_sd, gh);
+            const F4 ppa = b2ptx::f4pack(pa);
+            b2ptx::f4fma2(H0, k.p_mdt2, b2ptx::f4sub2(c, b2ptx::f4pack(pu)));
+            b2ptx::f4fma2(Hz, k.p_mdt2, b2ptx::f4sub2(vcn, b2ptx::f4pack(pv)));
+            const F4 ou_ = F4{b2ptx::fma2(ppa.a, H0.a, c.a), b2ptx::fma2(ppa.b, H0.b, c.b)};
+            const F4 ov_ = F4{b2ptx::fma2(ppa.a, Hz.a, vcn.a), b2ptx::fma2(ppa.b, Hz.b, vcn.b)};
+            const float4 ou = b2ptx::f4unpack(ou_), ov = b2ptx::f4unpack(ov_);
             if (zcnt == 4) {
                 *reinterpret_cast<float4 *>(k.u1 + gi) = ou;
                 *reinterpret_cast<float4 *>(k.v1 + gi) = ov;
@@ -796,11 +824,12 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
             }
         }
         __syncwarp();
-        if (lane == 0) b2ptx::mbar_arrive(&empty[it % NB]);
+        if (lane == 0) b2ptx::mbar_arrive(&empty[p]);
         iu = wrap(iu + 1, NUU);
         iv = wrap(iv + 1, NUV);
         ig = wrap(ig + 1, NG);
         gi += k.sx;
+    }
     }
 }
 
@@ -925,11 +954,13 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     using C = TtiCfg<R, TYF>;
     using CW = TtiWsCfg<kTtiWsTY>;
     auto kern = k_tti_fused<R, TYF>;
-    auto kern_ws = k_tti_ws<kTtiWsTY>;
+    static const int pf = env_int_tti("B2_TTI_PF", 1);   // measured: one-deep 2.94 ms, two-deep (spills) 3.83 ms at 768^3
+    auto kern_ws = pf == 1 ? k_tti_ws<kTtiWsTY, 1> : k_tti_ws<kTtiWsTY, 2>;
     static bool attr_set = false;
     if (!attr_set) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM), B2_ERR_LAUNCH);
-        B2_CUDA(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM), B2_ERR_LAUNCH);
+        B2_CUDA(cudaFuncSetAttribute(k_tti_ws<kTtiWsTY, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM), B2_ERR_LAUNCH);
+        B2_CUDA(cudaFuncSetAttribute(k_tti_ws<kTtiWsTY, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CW::SMEM), B2_ERR_LAUNCH);
         attr_set = true;
     }
     TtiFK k;
@@ -964,6 +995,15 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     k.sd = sqrtf(1.0f + 2.0f * p.delta);
     for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
     for (int i = 0; i < R; ++i) { k.w1x[i] = k.cx * p.w1[0][i]; k.w1y[i] = k.cy * p.w1[1][i]; k.w1z[i] = k.cz * p.w1[2][i]; }
+    for (int i = 0; i <= R && i < 5; ++i) { k.p_w2x[i] = make_float2(k.w2x[i], k.w2x[i]); k.p_w2y[i] = make_float2(k.w2y[i], k.w2y[i]); }
+    for (int i = 0; i < R && i < 4; ++i) { k.p_w1x[i] = make_float2(k.w1x[i], k.w1x[i]); k.p_w1y[i] = make_float2(k.w1y[i], k.w1y[i]); }
+    {
+        const float wc = k.w2x[0] + k.w2y[0] + k.w2z[0];
+        k.p_wc = make_float2(wc, wc);
+        k.p_e2 = make_float2(k.e2, k.e2);
+        k.p_sd = make_float2(k.sd, k.sd);
+        k.p_mdt2 = make_float2(k.m_dt2, k.m_dt2);
+    }
     timing_begin();
     if (ws)
         kern_ws<<<(unsigned)(k.ntz * k.nty * ntx), kTtiWsTY * 16 + 128, CW::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
