@@ -451,9 +451,9 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
 
     const bool born = a->born_U || a->born_dm;
     if (born) {
-        if (!a->born_U || !a->born_dm || nd != 3 || a->adjoint || a->grad || a->free_surface || a->ot4 || a->halo) {
+        if (!a->born_U || !a->born_dm || nd != 3 || a->adjoint || a->grad || a->free_surface || a->ot4) {
             set_error("b2_iso_forward: Born modelling needs born_U and born_dm, 3-D, forward in time, and is "
-                      "not combined with halo exchange, free surface, OT4 or the imaging condition");
+                      "not combined with a free surface, OT4 or the imaging condition");
             return cleanup(B2_ERR_INVALID);
         }
         if ((rc = stage_in(a->born_U, 4, bornU, true))) return cleanup(rc);
@@ -469,8 +469,8 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
 
     int snap_h = 0;
     if (a->snap) {
-        if (a->snap_factor < 1 || a->adjoint || a->halo) {
-            set_error("b2_iso_forward: snapshots need snap_factor >= 1, forward time stepping, single device");
+        if (a->snap_factor < 1 || a->adjoint) {
+            set_error("b2_iso_forward: snapshots need snap_factor >= 1 and forward time stepping");
             return cleanup(B2_ERR_INVALID);
         }
         const bool stream_out = !a->snap->dmap && a->snap->data && nd == 3 &&
@@ -549,9 +549,8 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         for (int i = 0; i <= a->radius; ++i) p.w[di][i] = a->w[d][i];
     }
     p.ot4 = a->ot4 != 0;
-    if (p.ot4 && (a->halo || a->free_surface || a->grad)) {
-        set_error("b2_iso_forward: OT4 is not combined with halo exchange, a free surface or the imaging "
-                  "condition in this version");
+    if (p.ot4 && (a->free_surface || a->grad)) {
+        set_error("b2_iso_forward: OT4 is not combined with a free surface or the imaging condition in this version");
         return cleanup(B2_ERR_INVALID);
     }
     p.defer_coef = maybe_stream;
@@ -610,7 +609,8 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
 
     const bool p2p = a->halo && halo_p2p_active(a->halo, p.u);
     // halo step fused into the sweep kernel (peer stores + flag acquire inside k_iso_tma)
-    const bool fused = p2p && halo_fused_ok(a->halo, p) && !a->free_surface;
+    // (free-surface rows are redone after the sweep and Born steps a second field: those use the copy path)
+    const bool fused = p2p && halo_fused_ok(a->halo, p) && !a->free_surface && !born;
     IsoFuse fz;
     if (fused && (rc = halo_fuse_desc(a->halo, p, fz))) return cleanup(rc);
     if (a->halo && nd == 3 && (a->x_m != 0 || a->x_M != p.a[0] - 2 * so - 1)) {
@@ -618,7 +618,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
                   "(x_m=%d, x_M=%d, %d owned planes)", a->x_m, a->x_M, p.a[0] - 2 * so);
         return cleanup(B2_ERR_INVALID);
     }
-    if (a->halo) a->halo->p2p_primed = false;       // first step of a call exchanges through NCCL
+    if (a->halo) a->halo->reset_primed();           // first step of a call exchanges through NCCL
     const int dir = a->adjoint ? -1 : 1;
     // profile: [0] staging issued before the loop, [1] the loop (device clock)
     cudaEvent_t pe_in = se.next(), pe_loop0 = nullptr, pe_loop1 = nullptr;
@@ -657,24 +657,32 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
             return cleanup(rc);
         if (fused) {
             // the sweep stored the boundary planes, the injection patched them: release the flags
-            if ((rc = halo_fused_signal(a->halo))) return cleanup(rc);
+            if ((rc = halo_fused_signal(a->halo, p.u))) return cleanup(rc);
             if (a->rec_toff && rec.present && (rc = halo_p2p_wait(a->halo))) return cleanup(rc);
         } else if (p2p) {
             // boundary planes of u[t1] are final: store them into the neighbours' halos, signal
             if ((rc = halo_p2p_publish(a->halo, p.u, nullptr, p.slot_elems, t1, (size_t)p.sx, p.o[0], p.n[0],
-                                       p.radius[0])))
+                                       halo_width_iso(p))))
                 return cleanup(rc);
-            a->halo->p2p_primed = true;
             // receivers that sample the just-written time level may touch halo cells: those
             // arrive with the neighbours' stores of this same step
             if (a->rec_toff && rec.present && (rc = halo_p2p_wait(a->halo))) return cleanup(rc);
         }
         if (born) {
             // eqn2 of the reference's Born operator comes after the source injection into u[t+1]
-            if ((rc = iso_step(pU, t0, t2, t1, 0, pU.n[0]))) return cleanup(rc);
+            if (a->halo) {
+                if ((rc = halo_exchange_and_step_iso(a->halo, pU, t0, t2, t1))) return cleanup(rc);
+            } else if ((rc = iso_step(pU, t0, t2, t1, 0, pU.n[0]))) {
+                return cleanup(rc);
+            }
             if ((rc = iso_born_source(p, t0, t2, t1, pU.u + (size_t)t1 * p.slot_elems, (const float *)borndm.d,
                                       (long long)borndm.size[1] * borndm.size[2], borndm.size[2],
                                       a->x_m + dmh, a->y_m + dmh, a->z_m + dmh)))
+                return cleanup(rc);
+            // the linearised field's boundary planes are final: publish them like u's
+            if (a->halo && halo_p2p_active(a->halo, pU.u) &&
+                (rc = halo_p2p_publish(a->halo, pU.u, nullptr, pU.slot_elems, t1, (size_t)pU.sx, pU.o[0], pU.n[0],
+                                       halo_width_iso(pU))))
                 return cleanup(rc);
         }
         if (a->snap && time % a->snap_factor == 0) {

@@ -126,7 +126,7 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
         cudaEventRecord(e0, stream());
     }
     const bool p2p = a->halo && halo_p2p_active(a->halo, p.u) && halo_p2p_active(a->halo, p.v);
-    if (a->halo) a->halo->p2p_primed = false;
+    if (a->halo) a->halo->reset_primed();
     for (int time = a->time_m; time <= a->time_M; ++time) {
         const int t0 = ((time % T) + T) % T;
         const int t1 = (((time + 1) % T) + T) % T;
@@ -144,7 +144,8 @@ extern "C" int b2_tti_forward(const struct b2_tti_args *a) {
         if (p2p) {
             if ((rc = halo_p2p_publish(a->halo, p.u, p.v, p.slot_elems, t1, (size_t)p.sx, p.o[0], p.n[0], p.R)))
                 return cleanup(rc);
-            a->halo->p2p_primed = true;
+            a->halo->set_primed(p.u);
+            a->halo->set_primed(p.v);
             // receivers that sample the just-written time level may touch halo cells: those
             // arrive with the neighbours' stores of this same step
             if (a->rec_toff && rec.present && (rc = halo_p2p_wait(a->halo))) return cleanup(rc);

@@ -165,9 +165,10 @@ int halo_p2p_publish(b2_halo_ctx *ctx, const float *f0, const float *f1, size_t 
     }
     for (int i = 0; i < 2; ++i) {
         if (!fs[i]) continue;
-        const b2_halo_ctx::Reg *rg = ctx->find(fs[i]);
+        b2_halo_ctx::Reg *rg = ctx->find(fs[i]);
         if (!rg) { set_error("p2p: field not registered"); return B2_ERR_COMM; }
         if ((rc = p2p_push(ctx, *rg, fs[i], slot_elems, slot1, plane, lo, n, width))) return rc;
+        rg->primed = true;
     }
     if ((rc = p2p_signal(ctx))) return rc;
     if (ctx->p2p_async) {
@@ -186,14 +187,18 @@ int halo_p2p_drain(b2_halo_ctx *ctx) {
     return B2_OK;
 }
 
+// planes a step needs from each neighbour: the stencil radius, twice that for the OT4 scheme (its update reads
+// W = lap(u)/m at +-R, which reads u at +-2R)
+int halo_width_iso(const IsoPlan &p) { return p.ot4 ? 2 * p.radius[0] : p.radius[0]; }
+
 int halo_exchange_and_step_iso(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1) {
-    const int R = p.radius[0];
+    const int R = halo_width_iso(p);
     const int n = p.n[0];
     if (n < 2 * R) {
-        set_error("halo: local slab of %d planes is thinner than 2*radius=%d", n, 2 * R);
+        set_error("halo: local slab of %d planes is thinner than twice the halo width %d", n, R);
         return B2_ERR_INVALID;
     }
-    if (halo_p2p_active(ctx, p.u) && ctx->p2p_primed) {
+    if (halo_p2p_active(ctx, p.u) && ctx->primed(p.u)) {
         // halos of u[t0] were stored by the neighbours at the end of their previous step: the
         // interior needs none of them; the boundary strips wait on the flags
         int rc;
@@ -249,7 +254,7 @@ int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int 
     IsoFuse f;
     int rc = halo_fuse_desc(ctx, p, f);
     if (rc) return rc;
-    if (ctx->p2p_primed) {
+    if (ctx->primed(p.u)) {
         f.want = ctx->step;               // the neighbours released `step` after publishing u[t0]
     } else {
         cudaStream_t main = stream();
@@ -263,10 +268,10 @@ int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int 
     return iso_step_fused(p, t0, t2, t1, f);
 }
 
-int halo_fused_signal(b2_halo_ctx *ctx) {
+int halo_fused_signal(b2_halo_ctx *ctx, const void *field) {
     int rc = p2p_signal(ctx);
     if (rc) return rc;
-    ctx->p2p_primed = true;
+    ctx->set_primed(field);
     return B2_OK;
 }
 
@@ -278,7 +283,7 @@ int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t
         set_error("halo: local slab of %d planes is thinner than 2*radius=%d", n, 2 * R);
         return B2_ERR_INVALID;
     }
-    if (halo_p2p_active(ctx, p.u) && halo_p2p_active(ctx, p.v) && ctx->p2p_primed) {
+    if (halo_p2p_active(ctx, p.u) && halo_p2p_active(ctx, p.v) && ctx->primed(p.u) && ctx->primed(p.v)) {
         int rc;
         if ((rc = tti_step(p, t0, t2, t1, R, n - 2 * R))) return rc;
         if ((rc = halo_p2p_drain(ctx))) return rc;
@@ -385,7 +390,7 @@ int b2_halo_p2p_setup(b2_halo_ctx *ctx, void *flags_local, void *fl, void *fr) {
     ctx->flag_right_remote = (int *)fr;
     ctx->p2p = true;
     ctx->step = 0;
-    ctx->p2p_primed = false;
+    ctx->reset_primed();
     const char *as = getenv("B2_P2P_ASYNC");
     if (as && atoi(as) != 0 && !ctx->push_stream) {
         B2_CUDA(cudaSetDevice(ctx->deviceid), B2_ERR_DEVICE);
@@ -403,8 +408,8 @@ int b2_halo_p2p_register(b2_halo_ctx *ctx, void *local_base, void *left_base, vo
                          int n_right) {
     if (!ctx || !ctx->p2p) { b2::set_error("b2_halo_p2p_register: p2p not set up"); return B2_ERR_INVALID; }
     for (auto &r : ctx->regs)
-        if (r.local == local_base) { r = {local_base, left_base, right_base, n_left, n_right}; return B2_OK; }
-    ctx->regs.push_back({local_base, left_base, right_base, n_left, n_right});
+        if (r.local == local_base) { r = {local_base, left_base, right_base, n_left, n_right, false}; return B2_OK; }
+    ctx->regs.push_back({local_base, left_base, right_base, n_left, n_right, false});
     return B2_OK;
 }
 

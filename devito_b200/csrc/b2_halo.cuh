@@ -25,12 +25,17 @@ struct b2_halo_ctx {
     cudaStream_t push_stream = nullptr;
     cudaEvent_t ev_final = nullptr, ev_push = nullptr;
     bool push_pending = false;
-    struct Reg { void *local, *left, *right; int n_left, n_right; };
+    // `primed`: the halos of this field's current time level were stored by the peers (false at the start of
+    // a call: the first step exchanges through NCCL). Per field: Born modelling steps two wavefields.
+    struct Reg { void *local, *left, *right; int n_left, n_right; bool primed; };
     std::vector<Reg> regs;
-    const Reg *find(const void *local) const {
-        for (const Reg &r : regs) if (r.local == local) return &r;
+    Reg *find(const void *local) {
+        for (Reg &r : regs) if (r.local == local) return &r;
         return nullptr;
     }
+    void reset_primed() { for (Reg &r : regs) r.primed = false; p2p_primed = false; }
+    bool primed(const void *local) { Reg *r = find(local); return r && r->primed; }
+    void set_primed(const void *local) { if (Reg *r = find(local)) r->primed = true; p2p_primed = true; }
 };
 
 namespace b2 {
@@ -59,7 +64,8 @@ int halo_p2p_drain(b2_halo_ctx *ctx);
 bool halo_fused_ok(b2_halo_ctx *ctx, const IsoPlan &p);
 int halo_fuse_desc(b2_halo_ctx *ctx, const IsoPlan &p, IsoFuse &f);
 int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1);
-int halo_fused_signal(b2_halo_ctx *ctx);
+int halo_fused_signal(b2_halo_ctx *ctx, const void *field);
+int halo_width_iso(const IsoPlan &p);
 
 // Same for the coupled TTI fields: u and v boundary planes travel in one NCCL group.
 int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t2, int t1);

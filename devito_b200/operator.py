@@ -1199,8 +1199,6 @@ class Operator:
             sn = args['snap']
             if not isinstance(sn, TimeFunction) or sn.is_buffered or sn.grid.shape != grid.shape:
                 raise InvalidArgument("the snapshot override must be a saved TimeFunction on the same grid")
-            if grid.distributor.is_parallel:
-                raise InvalidArgument("snapshots are not yet combined with domain decomposition")
         args['born_U'] = self._resolve(kwargs, p.get('born_U'), post)
         args['born_dm'] = self._resolve(kwargs, p.get('born_dm'), post)
         if args['born_U'] is not None:
@@ -1209,8 +1207,6 @@ class Operator:
                 raise InvalidArgument("incompatible override for the linearised wavefield")
             if not isinstance(args['born_dm'], Function):
                 raise InvalidArgument("`dm` must be a Function or an array of its allocated shape")
-            if grid.distributor.is_parallel:
-                raise InvalidArgument("Born modelling is not yet combined with domain decomposition")
         args['grad'] = self._resolve(kwargs, p.get('grad'), post)
         args['usave'] = self._resolve(kwargs, p.get('usave'), post)
         if args['usave'] is not None:
@@ -1279,9 +1275,8 @@ class Operator:
             lo.append(int(a))
             hi.append(int(b))
         args['lo'], args['hi'] = lo, hi
-        if p.get('ot4') and (grid.distributor.is_parallel or p.get('free_surface') or p.get('grad') is not None):
-            raise InvalidArgument("the OT4 kernel is not yet combined with domain decomposition, a free "
-                                  "surface or the imaging condition")
+        if p.get('ot4') and (p.get('free_surface') or p.get('grad') is not None):
+            raise InvalidArgument("the OT4 kernel is not yet combined with a free surface or the imaging condition")
         if p.get('free_surface') and lo[-1] != 0:
             raise InvalidArgument("a free-surface operator must iterate from the surface row (lower bound 0 "
                                   "on the last dimension)")
@@ -1379,7 +1374,7 @@ class Operator:
         if resident:
             dist_ = fn.grid.distributor if fn.grid is not None else None
             p2p_field = (written and dist_ is not None and dist_.is_parallel and distributed.p2p_enabled()
-                         and getattr(fn, 'is_TimeFunction', False))
+                         and getattr(fn, 'is_TimeFunction', False) and getattr(fn, 'is_buffered', False))
             if p2p_field:
                 st.raw = True        # plain cudaMalloc: exportable through CUDA IPC
             t = st.to_device(torch.device('cuda', dev))

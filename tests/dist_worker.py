@@ -66,21 +66,17 @@ def host_mode():
 def gpu_mode(kind):
     import torch
     import torch.distributed as dist
+    from dist_cases import run_case
     w = dv.init_distributed()
     local = int(os.environ.get('LOCAL_RANK', '0'))
     dv.configuration['deviceid'] = local
-    so, nbl, n, tn = 8, 10, (24 * w.size - 4, 28, 28), 150.0        # 24 owned planes per rank
-    preset = 'constant-isotropic' if kind == 'iso' else 'constant-tti'
-    cls = AcousticWaveSolver if kind == 'iso' else AnisotropicWaveSolver
-    model = demo_model(preset, spacing=(10., 10., 10.), shape=n, nbl=nbl, space_order=so, topology=('*', 1, 1))
-    geometry = setup_geometry(model, tn)
-    out = cls(model, geometry, space_order=so).forward()
-    rec, u = out[0], out[1]
-    lo, hi = model.grid.distributor.x_range
-    np.save(f'/tmp/b2_dist_{kind}_u_{w.rank}.npy', np.asarray(u.data))
-    if w.rank == 0:
-        np.save(f'/tmp/b2_dist_{kind}_rec.npy', np.asarray(rec.data))
-        np.save(f'/tmp/b2_dist_{kind}_ranges.npy', np.array([lo, hi]))
+    res, model = run_case(kind, w.size, topology=('*', 1, 1))
+    for name, arr in res.items():
+        if name == 'rec':
+            if w.rank == 0:
+                np.save(f'/tmp/b2_dist_{kind}_rec.npy', np.asarray(arr))
+        else:
+            np.save(f'/tmp/b2_dist_{kind}_{name}_{w.rank}.npy', np.asarray(arr))
     dist.barrier()
     from devito_b200.distributed import finalize_distributed
     finalize_distributed()

@@ -46,17 +46,16 @@ def _decomposed_vs_single(kind, tol, env, nproc):
     assert 'DIST-GPU-DONE' in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
     sys.path.insert(0, HERE)
     from helpers import rel_linf
-    from devito_b200.seismic import demo_model, setup_geometry, AcousticWaveSolver, AnisotropicWaveSolver
-    so, nbl, n, tn = 8, 10, (24 * nproc - 4, 28, 28), 150.0
-    preset = 'constant-isotropic' if kind == 'iso' else 'constant-tti'
-    cls = AcousticWaveSolver if kind == 'iso' else AnisotropicWaveSolver
-    model = demo_model(preset, spacing=(10., 10., 10.), shape=n, nbl=nbl, space_order=so)
-    out = cls(model, setup_geometry(model, tn), space_order=so).forward()
-    rec, u = out[0], out[1]
-    ud = np.concatenate([np.load(f'/tmp/b2_dist_{kind}_u_{r}.npy') for r in range(nproc)], axis=1)
-    assert ud.shape == u.data.shape
-    assert rel_linf(ud, u.data) < tol
-    assert rel_linf(np.load(f'/tmp/b2_dist_{kind}_rec.npy'), rec.data) < tol
+    from dist_cases import run_case, AXIS
+    res, _ = run_case(kind, nproc)
+    for name, want in res.items():
+        want = np.asarray(want)
+        if AXIS[name] is None:
+            got = np.load(f'/tmp/b2_dist_{kind}_rec.npy')
+        else:
+            got = np.concatenate([np.load(f'/tmp/b2_dist_{kind}_{name}_{r}.npy') for r in range(nproc)], axis=AXIS[name])
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        assert rel_linf(got, want) < tol, (kind, name, rel_linf(got, want))
 
 
 @pytest.mark.gpu
@@ -79,3 +78,19 @@ def test_four_gpu_halo_exchange_matches_single_gpu(kind, tol, path, env):
     if torch.cuda.device_count() < 4:
         pytest.skip("needs 4 GPUs")
     _decomposed_vs_single(kind, tol, env, 4)
+
+
+# the schemes that ride on the isotropic update: free surface (copy path: the surface rows are redone after the
+# sweep), OT4 (halo of 2*radius planes), Born (two wavefields), gradient (adjoint + imaging), snapshots
+_SCHEMES = [('fs', {}), ('ot4', {}), ('born', {}), ('grad', {}), ('snap', {}), ('ot4', {'B2_HALO': 'nccl'}),
+            ('born', {'B2_HALO': 'nccl'}), ('fs', {'B2_HALO': 'nccl'})]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind,env', _SCHEMES, ids=[k + ('-nccl' if e else '') for k, e in _SCHEMES])
+def test_two_gpu_schemes_match_single_gpu(kind, env):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from dist_cases import TOL
+    _decomposed_vs_single(kind, TOL[kind], env, 2)
