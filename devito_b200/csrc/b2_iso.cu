@@ -112,6 +112,10 @@ struct IsoTK {
     int slot0, slotm;
     float m_dt2;
     float wx[R + 1], wy[R + 1], wz[R + 1];
+    // k_iso_tma2 (two y rows per thread): u[t-1] and the coefficient tables are read straight from global memory
+    // (coalesced 16-byte loads, prefetched into registers), packed fp32x2 weights {w, w}
+    const float *um, *cA, *cB;
+    float2 p_wx[R + 1], p_wy[R + 1], p_mdt2, p_wc;
     // ---- x-slab decomposition, halo step fused into the sweep (all zero / null on a single device) ----
     // The CTAs that produce a boundary plane also store it into the neighbour GPU's halo through the
     // CUDA-IPC mapped peer pointer (16-byte stores over NVLink), and the producer lane of a CTA that
@@ -385,6 +389,280 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k_iso_tma2: the same 2.5-D sweep with TWO y rows per consumer thread — for the large radii.
+// ------------------------------------------------------------------------------------------
+// k_iso_tma at so=12 (R=6) had to shrink its tile to 16x64 to fit the 13-stage plane ring plus the tile
+// ring, and became shared-memory-bandwidth bound (ncu r1c: L1/TEX 80.6 %, HBM 75 %): 12 y-tap LDS.128 per
+// float4 of output. Here
+//   * a thread owns rows 2*tr and 2*tr+1: the 2R rows around them are loaded ONCE for both (7 LDS.128 per
+//     output float4 instead of 12), each own row is the other's nearest y neighbour (registers);
+//   * u[t-1] and the coefficient tables do not go through shared memory at all (coalesced LDG.128,
+//     prefetched two planes ahead into registers), which frees the room for a 32x64 tile — halo
+//     re-reads 1.72x instead of 2.19x;
+//   * the x-history of the own columns is kept in register queues with static slots (planes c+1..c+R in
+//     fut[(p+k) mod R], c-R..c-1 in pst[...], the loop unrolled R times — not 2R+1 = 13 times, which is
+//     what made the first "taller tile" experiment of round 1 miss the instruction cache);
+//   * y/x taps and the update in packed fp32x2 arithmetic.
+// Halo step under decomposition: identical to k_iso_tma (peer stores, flag acquire, chunk 0 backwards).
+template <int R, int TY, int TZ4>
+struct IsoTma2Cfg {
+    static constexpr int RZ = ceil4(R);
+    static constexpr int TZ = 4 * TZ4;
+    static constexpr int BY = TY + 2 * R;
+    static constexpr int BZ = TZ + 2 * RZ;
+    static constexpr int NU = 2 * R + 1;
+    static constexpr int PLANE = align32f(BY * BZ);
+    static constexpr int NCT = (TY / 2) * TZ4;          // consumer threads
+    static constexpr int NCW = NCT / 32;
+    static constexpr size_t SMEM = (size_t)(NU * PLANE) * 4 + 2 * NU * 8 + 128;
+};
+
+template <int R, int TY, int TZ4, int PK>
+__global__ void __launch_bounds__((TY / 2) * TZ4 + 32, 1)
+k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
+    using C = IsoTma2Cfg<R, TY, TZ4>;
+    using b2ptx::F4;
+    constexpr int RZ = C::RZ, TZ = C::TZ, BZ = C::BZ, NU = C::NU, PLANE = C::PLANE, NCW = C::NCW;
+    static_assert(TY % 2 == 0 && C::NCT % 32 == 0, "two rows per thread, whole warps");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_u = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_u + NU * PLANE);
+    uint64_t *empty = full + NU;
+
+    int b = blockIdx.x;
+    const int iz = b % k.ntz;
+    b /= k.ntz;
+    const int iy = b % k.nty;
+    const int ix = b / k.nty;
+    const int z0 = iz * TZ, y0 = iy * TY;
+    const int xs = k.xlo + ix * k.lx;
+    const int xe = min(xs + k.lx, k.xlo + k.xcount);
+    const int NP = (xe - xs) + 2 * R;
+    const bool back = (ix == 0) && k.back0;
+    const int dx = back ? -1 : 1;
+    const int xb = back ? xe - 1 + R : xs - R;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < NU; ++i) {
+            b2ptx::mbar_init(&full[i], 1);
+            b2ptx::mbar_init(&empty[i], NCW);
+        }
+        b2ptx::fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        if (lane == 0) {
+            b2ptx::tma_prefetch_desc(&tm_uh);
+            int slot = 0, round = 0;
+            bool need_lo = k.want >= 0 && k.flag_lo != nullptr, need_hi = k.want >= 0 && k.flag_hi != nullptr;
+            for (int j = 0; j < NP; ++j) {
+                if (round > 0) b2ptx::mbar_wait(&empty[slot], (round - 1) & 1);
+                const int xj = xb + dx * j;
+                if (need_lo && xj < 0) {
+                    while (b2ptx::ld_acquire_sys(k.flag_lo) < k.want) __nanosleep(40);
+                    b2ptx::fence_proxy_async_global();
+                    need_lo = false;
+                }
+                if (need_hi && xj >= k.nown) {
+                    while (b2ptx::ld_acquire_sys(k.flag_hi) < k.want) __nanosleep(40);
+                    b2ptx::fence_proxy_async_global();
+                    need_hi = false;
+                }
+                b2ptx::mbar_arrive_expect_tx(&full[slot], (uint32_t)(C::BY * BZ * 4));
+                b2ptx::tma_load_4d(s_u + slot * PLANE, &tm_uh, &full[slot], k.oz + z0 - RZ, k.oy + y0 - R,
+                                   k.ox + xj, k.slot0);
+                if (++slot == NU) { slot = 0; ++round; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: rows (2 tr, 2 tr + 1), four z points ----------------
+    const int tr = tid / TZ4, tz4 = tid % TZ4;
+    const int gz = z0 + 4 * tz4;
+    const int gy0 = y0 + 2 * tr;
+    int zc[2];
+    long long row[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        zc[r] = (gy0 + r < k.ny) ? min(max(k.nz - gz, 0), 4) : 0;
+        row[r] = (long long)(k.oy + gy0 + r) * k.sy + (k.oz + gz);
+    }
+    const int col = (2 * tr + R) * BZ + RZ + 4 * tz4;      // row 0 of this thread inside a shared plane
+    const long long osx = dx * k.sx;
+    const long long gbase = (long long)(k.ox + xb - dx * R) * k.sx;   // + j * osx = the output plane of iteration j
+    const bool fuse = (k.peer_lo != nullptr) | (k.peer_hi != nullptr);
+
+    F4 fut[2][R], pst[2][R], cen[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        cen[r] = b2ptx::f4zero();
+#pragma unroll
+        for (int i = 0; i < R; ++i) { fut[r][i] = b2ptx::f4zero(); pst[r][i] = b2ptx::f4zero(); }
+    }
+    // u[t-1], A (and B) of the output plane of iteration j, loaded two iterations ahead
+    float4 pv[2][2], pa[2][2], pb[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int d = 0; d < 2; ++d) { pv[r][d] = pa[r][d] = pb[r][d] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    auto prefetch = [&](int j, int d) {
+        // output plane of iteration j: x = xb + dx * (j - R), valid for 2R <= j < NP
+        if (j < 2 * R || j >= NP) return;
+        const long long g = gbase + (long long)j * osx;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (zc[r] > 0) {
+                pv[r][d] = *reinterpret_cast<const float4 *>(k.um + g + row[r]);
+                pa[r][d] = *reinterpret_cast<const float4 *>(k.cA + g + row[r]);
+                if (PK != B2_PARAM_SCALAR) pb[r][d] = *reinterpret_cast<const float4 *>(k.cB + g + row[r]);
+            }
+        }
+    };
+    prefetch(2 * R, 0);
+    prefetch(2 * R + 1, 1);
+
+    int st_new = 0, st_cen = 0;           // shared-memory stage of plane j and of the centre plane j - R
+    uint32_t par_new = 0;
+
+    for (int jb = 0; jb < NP; jb += R) {
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+            const int j = jb + p;
+            if (j >= NP) break;
+            // slot of plane c + kk (c = j - R, c mod R == p): compile-time
+#define B2_SLOT(kk) ((((p) + (kk)) % R + R) % R)
+            b2ptx::mbar_wait(&full[st_new], par_new);
+            {
+                const float *np_ = s_u + st_new * PLANE + col;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    pst[r][B2_SLOT(-1)] = cen[r];                        // plane c-1 (overwrites plane c-1-R)
+                    cen[r] = fut[r][p];                                  // plane c
+                    fut[r][p] = b2ptx::f4pack(b2ptx::lds128(np_ + r * BZ));   // plane c+R = j
+                }
+            }
+            if (j >= 2 * R) {
+                const float *cp0 = s_u + st_cen * PLANE + col;
+                F4 acc[2];
+                // z direction (scalar: the operands straddle register pairs)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float *cp = cp0 + r * BZ;
+                    const float4 c = b2ptx::f4unpack(cen[r]);
+                    float zr[4 + 2 * RZ];
+#pragma unroll
+                    for (int m = 0; m < RZ / 4; ++m) {
+                        if (R % 4 == 2 && m == 0) {
+                            const float2 l = *reinterpret_cast<const float2 *>(cp - RZ + 2);
+                            zr[0] = 0.f; zr[1] = 0.f; zr[2] = l.x; zr[3] = l.y;
+                        } else {
+                            const float4 l = b2ptx::lds128(cp - RZ + 4 * m);
+                            zr[4 * m + 0] = l.x; zr[4 * m + 1] = l.y; zr[4 * m + 2] = l.z; zr[4 * m + 3] = l.w;
+                        }
+                        if (R % 4 == 2 && m == RZ / 4 - 1) {
+                            const float2 q = *reinterpret_cast<const float2 *>(cp + 4 + 4 * m);
+                            zr[RZ + 4 + 4 * m + 0] = q.x; zr[RZ + 4 + 4 * m + 1] = q.y;
+                            zr[RZ + 4 + 4 * m + 2] = 0.f; zr[RZ + 4 + 4 * m + 3] = 0.f;
+                        } else {
+                            const float4 q = b2ptx::lds128(cp + 4 + 4 * m);
+                            zr[RZ + 4 + 4 * m + 0] = q.x; zr[RZ + 4 + 4 * m + 1] = q.y;
+                            zr[RZ + 4 + 4 * m + 2] = q.z; zr[RZ + 4 + 4 * m + 3] = q.w;
+                        }
+                    }
+                    zr[RZ + 0] = c.x; zr[RZ + 1] = c.y; zr[RZ + 2] = c.z; zr[RZ + 3] = c.w;
+                    const float wc = k.p_wc.x;
+                    float4 a = make_float4(wc * c.x, wc * c.y, wc * c.z, wc * c.w);
+#pragma unroll
+                    for (int i = 1; i <= R; ++i) {
+                        a.x = fmaf(k.wz[i], zr[RZ + 0 - i] + zr[RZ + 0 + i], a.x);
+                        a.y = fmaf(k.wz[i], zr[RZ + 1 - i] + zr[RZ + 1 + i], a.y);
+                        a.z = fmaf(k.wz[i], zr[RZ + 2 - i] + zr[RZ + 2 + i], a.z);
+                        a.w = fmaf(k.wz[i], zr[RZ + 3 - i] + zr[RZ + 3 + i], a.w);
+                    }
+                    acc[r] = b2ptx::f4pack(a);
+                }
+                // y direction: rows -R..-1 and +2..R+1 (relative to row 0) are loaded once for both rows;
+                // each own row is the other's +-1 neighbour (registers)
+                b2ptx::f4fma2(acc[0], k.p_wy[1], cen[1]);
+                b2ptx::f4fma2(acc[1], k.p_wy[1], cen[0]);
+#pragma unroll
+                for (int d = -R; d <= R + 1; ++d) {
+                    if (d == 0 || d == 1) continue;
+                    const F4 v = b2ptx::f4pack(b2ptx::lds128(cp0 + d * BZ));
+                    const int a0 = d < 0 ? -d : d, a1 = d - 1 < 0 ? 1 - d : d - 1;
+                    if (a0 <= R) b2ptx::f4fma2(acc[0], k.p_wy[a0], v);
+                    if (a1 <= R) b2ptx::f4fma2(acc[1], k.p_wy[a1], v);
+                }
+                // x direction: own columns, register queues
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int i = 1; i <= R; ++i)
+                        b2ptx::f4fma2(acc[r], k.p_wx[i], b2ptx::f4add2(pst[r][B2_SLOT(-i)], fut[r][B2_SLOT(i)]));
+                // update  u+ = u + A (m/dt^2 (u - u-) + lap)   |   u + B (u - u-) + A lap
+                const int d = (j - 2 * R) & 1;
+                const long long g = gbase + (long long)j * osx;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const F4 c = cen[r];
+                    const F4 dcp = b2ptx::f4sub2(c, b2ptx::f4pack(pv[r][d]));
+                    const F4 ca = b2ptx::f4pack(pa[r][d]);
+                    F4 o;
+                    if (PK == B2_PARAM_SCALAR) {
+                        F4 t = acc[r];
+                        b2ptx::f4fma2(t, k.p_mdt2, dcp);
+                        o = F4{b2ptx::fma2(ca.a, t.a, c.a), b2ptx::fma2(ca.b, t.b, c.b)};
+                    } else {
+                        const F4 cb = b2ptx::f4pack(pb[r][d]);
+                        const F4 t = F4{b2ptx::fma2(cb.a, dcp.a, c.a), b2ptx::fma2(cb.b, dcp.b, c.b)};
+                        o = F4{b2ptx::fma2(ca.a, acc[r].a, t.a), b2ptx::fma2(ca.b, acc[r].b, t.b)};
+                    }
+                    const float4 of = b2ptx::f4unpack(o);
+                    float *dst = k.u1 + g + row[r];
+                    if (zc[r] == 4) {
+                        *reinterpret_cast<float4 *>(dst) = of;
+                    } else if (zc[r] > 0) {
+                        dst[0] = of.x;
+                        if (zc[r] > 1) dst[1] = of.y;
+                        if (zc[r] > 2) dst[2] = of.z;
+                    }
+                    if (fuse) {
+                        const int xo = xb + dx * (j - R);
+                        float *pd = nullptr;
+                        const long long ro = row[r] - (long long)0;
+                        if (k.peer_lo && xo < k.pw) pd = k.peer_lo + (k.off_lo + (long long)xo * k.sx + ro);
+                        if (k.peer_hi && xo >= k.nown - k.pw) pd = k.peer_hi + (k.off_hi + (long long)xo * k.sx + ro);
+                        if (pd) {
+                            if (zc[r] == 4) {
+                                *reinterpret_cast<float4 *>(pd) = of;
+                            } else if (zc[r] > 0) {
+                                pd[0] = of.x;
+                                if (zc[r] > 1) pd[1] = of.y;
+                                if (zc[r] > 2) pd[2] = of.z;
+                            }
+                        }
+                    }
+                }
+                prefetch(j + 2, d);
+            }
+            if (j >= R) {
+                __syncwarp();
+                if (lane == 0) b2ptx::mbar_arrive(&empty[st_cen]);
+                if (++st_cen == NU) st_cen = 0;
+            }
+            if (++st_new == NU) { st_new = 0; par_new ^= 1; }
+#undef B2_SLOT
+        }
+    }
+}
+
 // A = 1/(m/dt^2 + damp/dt), B = m/dt^2 * A on the full allocated array (halo included; halo
 // values are never used by the stencil)
 __global__ void __launch_bounds__(256)
@@ -460,6 +738,12 @@ template <> struct TileOf<4> { static constexpr int TY = 32, TZ4 = 16; };
 template <> struct TileOf<6> { static constexpr int TY = 16, TZ4 = 16; };
 template <> struct TileOf<8> { static constexpr int TY = 8, TZ4 = 16; };
 
+// k_iso_tma2 (two rows per thread, no tile ring): the radii whose k_iso_tma tile had to shrink
+template <int R> struct Tile2Of { static constexpr bool on = false; static constexpr int TY = 32, TZ4 = 16; };
+// 28 x 64: 14 x 16 = 224 consumer threads + the producer warp = 8 warps, so that the register file splits
+// into 255 registers per thread (9 warps would be allocated as 12: 168 registers, and the queues spill)
+template <> struct Tile2Of<6> { static constexpr bool on = true; static constexpr int TY = 28, TZ4 = 16; };
+
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -512,6 +796,11 @@ static int plan_tma(IsoPlan &p) {
     const int dims4[4] = {p.a[2], p.a[1], p.a[0], p.tsize};
     const int dims3[3] = {p.a[2], p.a[1], p.a[0]};
     int rc;
+    p.v2 = Tile2Of<R>::on && env_int("B2_ISO_V2", 1) != 0 && p.n[1] >= 16;
+    if (p.v2) {
+        using T2 = Tile2Of<R>;
+        return make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T2::TZ4 + 2 * RZ, T2::TY + 2 * R);
+    }
     if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T::TZ4 + 2 * RZ, T::TY + 2 * R))) return rc;
     if ((rc = make_tmap(&p.tm_uc, p.u, 4, dims4, 4 * T::TZ4, T::TY))) return rc;
     if ((rc = make_tmap(&p.tm_damp, p.coefA, 3, dims3, 4 * T::TZ4, T::TY))) return rc;
@@ -569,14 +858,21 @@ template <int R, int PK>
 static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount,
                       const IsoFuse *fz = nullptr) {
     using T = TileOf<R>;
+    using T2 = Tile2Of<R>;
     using C = IsoTmaCfg<R, T::TY, T::TZ4, PK>;
+    using C2 = IsoTma2Cfg<R, T2::TY, T2::TZ4>;
     auto kern = k_iso_tma<R, T::TY, T::TZ4, PK>;
     static bool attr_set = false;
     if (!attr_set) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),
                 B2_ERR_LAUNCH);
+        if constexpr (T2::on)
+            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C2::SMEM), B2_ERR_LAUNCH);
         attr_set = true;
     }
+    const bool v2 = T2::on && p.v2;
+    const int TYeff = v2 ? T2::TY : T::TY;
     IsoTK<R> k;
     k.u1 = p.u + (size_t)slot1 * p.slot_elems;
     k.sx = p.sx;
@@ -589,7 +885,7 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     k.xlo = xlo;
     k.xcount = xcount;
     k.ntz = (p.n[2] + C::TZ - 1) / C::TZ;
-    k.nty = (p.n[1] + T::TY - 1) / T::TY;
+    k.nty = (p.n[1] + TYeff - 1) / TYeff;
     // x-chunk length: enough CTAs for ~16 waves of 148 SMs, but chunks of at least 32 planes
     int lx = env_int("B2_ISO_LX", 0);
     if (lx <= 0) lx = choose_chunk_len(k.ntz * k.nty, xcount, 2 * R, 32);
@@ -624,10 +920,28 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
         k.wx[i] = p.w[0][i];
         k.wy[i] = p.w[1][i];
         k.wz[i] = p.w[2][i];
+        k.p_wx[i] = make_float2(k.wx[i], k.wx[i]);
+        k.p_wy[i] = make_float2(k.wy[i], k.wy[i]);
     }
+    k.p_mdt2 = make_float2(k.m_dt2, k.m_dt2);
+    {
+        const float wc = k.wx[0] + k.wy[0] + k.wz[0];
+        k.p_wc = make_float2(wc, wc);
+    }
+    k.um = p.u + (size_t)slotm * p.slot_elems;
+    k.cA = p.coefA;
+    k.cB = p.coefB;
     const unsigned grid = (unsigned)(k.ntz * k.nty * ntx);
     timing_begin();
-    kern<<<grid, T::TY * T::TZ4 + 32, C::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
+    bool launched = false;
+    if constexpr (T2::on) {
+        if (v2) {
+            k_iso_tma2<R, T2::TY, T2::TZ4, PK><<<grid, (T2::TY / 2) * T2::TZ4 + 32, C2::SMEM, stream()>>>(p.tm_uh, k);
+            launched = true;
+        }
+    }
+    if (!launched)
+        kern<<<grid, T::TY * T::TZ4 + 32, C::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
     timing_end();
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);

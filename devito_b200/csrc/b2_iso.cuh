@@ -22,6 +22,7 @@ struct IsoPlan {
     float w[3][B2_MAX_RADIUS + 1] = {};
     // TMA path
     bool use_tma = false;
+    bool v2 = false;             // k_iso_tma2 (two rows per thread; radius 6 / 8)
     CUtensorMap tm_uh, tm_uc, tm_damp, tm_par;   // tm_damp/tm_par map coefA/coefB
     float *coefA = nullptr, *coefB = nullptr;    // tabulated update coefficients (library scratch)
     bool defer_coef = false;                     // plan init only allocates them (streamed loop: per chunk)

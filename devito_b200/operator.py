@@ -1413,9 +1413,25 @@ class Operator:
         if dist.is_parallel:
             off = dist.offsets
             gp = np.ascontiguousarray((gp - np.asarray(off, dtype=np.int32)[None, :]).astype(np.int32))
+            nloc = grid.shape[0]
+            if not written:
+                # scatter (devito/types/sparse.py:608-730 routes every point to the ranks its support touches):
+                # this rank keeps only the points whose (2r)-wide support reaches its own cells; the kernel's
+                # guards then deposit into the owned cells only
+                r_ = int(sf.r)
+                keep = np.nonzero((gp[:, 0] + r_ >= 0) & (gp[:, 0] - r_ + 1 <= nloc - 1))[0]
+                if len(keep) == 0:
+                    return None
+                if len(keep) < gp.shape[0]:
+                    gp = np.ascontiguousarray(gp[keep])
+                    ws = [np.ascontiguousarray(w[keep]) for w in ws]
+                    host = np.ascontiguousarray(host[:, keep])
             if written:
-                nloc = grid.shape[0]
-                mask = (gp[:, 0] >= 0) & (gp[:, 0] < nloc)
+                # a point is evaluated by the rank that owns its base cell (the physical boundary ranks also own
+                # what lies beyond the domain on their side)
+                lo_ok = (gp[:, 0] >= 0) | dist.is_boundary_left
+                hi_ok = (gp[:, 0] < nloc) | dist.is_boundary_right
+                mask = lo_ok & hi_ok
                 idx = np.nonzero(mask)[0]
                 gp = np.ascontiguousarray(gp[idx])
                 ws = [np.ascontiguousarray(w[idx]) for w in ws]
