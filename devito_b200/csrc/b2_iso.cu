@@ -419,13 +419,14 @@ struct IsoTma2Cfg {
     static constexpr size_t SMEM = (size_t)(NU * PLANE) * 4 + 2 * NU * 8 + 128;
 };
 
-template <int R, int TY, int TZ4, int PK>
+template <int R, int TY, int TZ4, int PK, int PF>
 __global__ void __launch_bounds__((TY / 2) * TZ4 + 32, 1)
 k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
     using C = IsoTma2Cfg<R, TY, TZ4>;
     using b2ptx::F4;
     constexpr int RZ = C::RZ, TZ = C::TZ, BZ = C::BZ, NU = C::NU, PLANE = C::PLANE, NCW = C::NCW;
     static_assert(TY % 2 == 0 && C::NCT % 32 == 0, "two rows per thread, whole warps");
+    static_assert(R % 2 == 0, "the prefetch buffers alternate with the parity of the unrolled iteration");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_u = reinterpret_cast<float *>(smem_raw);
@@ -507,11 +508,11 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
         for (int i = 0; i < R; ++i) { fut[r][i] = b2ptx::f4zero(); pst[r][i] = b2ptx::f4zero(); }
     }
     // u[t-1], A (and B) of the output plane of iteration j, loaded two iterations ahead
-    float4 pv[2][2], pa[2][2], pb[2][2];
+    float4 pv[2][PF], pa[2][PF], pb[2][PF];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int d = 0; d < 2; ++d) { pv[r][d] = pa[r][d] = pb[r][d] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int d = 0; d < PF; ++d) { pv[r][d] = pa[r][d] = pb[r][d] = make_float4(0.f, 0.f, 0.f, 0.f); }
     auto prefetch = [&](int j, int d) {
         // output plane of iteration j: x = xb + dx * (j - R), valid for 2R <= j < NP
         if (j < 2 * R || j >= NP) return;
@@ -526,7 +527,7 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
         }
     };
     prefetch(2 * R, 0);
-    prefetch(2 * R + 1, 1);
+    if (PF == 2) prefetch(2 * R + 1, PF - 1);
 
     int st_new = 0, st_cen = 0;           // shared-memory stage of plane j and of the centre plane j - R
     uint32_t par_new = 0;
@@ -607,7 +608,9 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
                     for (int i = 1; i <= R; ++i)
                         b2ptx::f4fma2(acc[r], k.p_wx[i], b2ptx::f4add2(pst[r][B2_SLOT(-i)], fut[r][B2_SLOT(i)]));
                 // update  u+ = u + A (m/dt^2 (u - u-) + lap)   |   u + B (u - u-) + A lap
-                const int d = (j - 2 * R) & 1;
+                // compile-time buffer index (jb and 2R are even): a run-time index into a register array makes the
+                // compiler select/copy right after the load, i.e. wait for it — the first version stalled on exactly that
+                const int d = PF == 2 ? (p & 1) : 0;
                 const long long g = gbase + (long long)j * osx;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -650,8 +653,9 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
                         }
                     }
                 }
-                prefetch(j + 2, d);
+                if (PF == 2) prefetch(j + 2, d);
             }
+            if (PF == 1 && j + 1 >= 2 * R) prefetch(j + 1, 0);    // (after the stores of this plane were issued)
             if (j >= R) {
                 __syncwarp();
                 if (lane == 0) b2ptx::mbar_arrive(&empty[st_cen]);
@@ -743,6 +747,8 @@ template <int R> struct Tile2Of { static constexpr bool on = false; static const
 // 28 x 64: 14 x 16 = 224 consumer threads + the producer warp = 8 warps, so that the register file splits
 // into 255 registers per thread (9 warps would be allocated as 12: 168 registers, and the queues spill)
 template <> struct Tile2Of<6> { static constexpr bool on = true; static constexpr int TY = 28, TZ4 = 16; };
+// experiment: 40 x 64 (20 x 16 = 320 consumers + producer = 11 warps, allocated as 12: 168 registers)
+template <int R> struct Tile2bOf { static constexpr int TY = 40, TZ4 = 16; };
 
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
@@ -796,10 +802,11 @@ static int plan_tma(IsoPlan &p) {
     const int dims4[4] = {p.a[2], p.a[1], p.a[0], p.tsize};
     const int dims3[3] = {p.a[2], p.a[1], p.a[0]};
     int rc;
-    p.v2 = Tile2Of<R>::on && env_int("B2_ISO_V2", 1) != 0 && p.n[1] >= 16;
+    p.v2 = Tile2Of<R>::on && p.n[1] >= 16 ? env_int("B2_ISO_V2", 0) : 0;   // experimental: slower than k_iso_tma so far
     if (p.v2) {
         using T2 = Tile2Of<R>;
-        return make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T2::TZ4 + 2 * RZ, T2::TY + 2 * R);
+        using T2b = Tile2bOf<R>;
+        return make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T2::TZ4 + 2 * RZ, (p.v2 == 3 ? T2b::TY : T2::TY) + 2 * R);
     }
     if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T::TZ4 + 2 * RZ, T::TY + 2 * R))) return rc;
     if ((rc = make_tmap(&p.tm_uc, p.u, 4, dims4, 4 * T::TZ4, T::TY))) return rc;
@@ -866,13 +873,20 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     if (!attr_set) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),
                 B2_ERR_LAUNCH);
-        if constexpr (T2::on)
-            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if constexpr (T2::on) {
+            using T2b = Tile2bOf<R>;
+            using C2b = IsoTma2Cfg<R, T2b::TY, T2b::TZ4>;
+            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C2::SMEM), B2_ERR_LAUNCH);
+            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C2::SMEM), B2_ERR_LAUNCH);
+            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2b::TY, T2b::TZ4, PK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C2b::SMEM), B2_ERR_LAUNCH);
+        }
         attr_set = true;
     }
-    const bool v2 = T2::on && p.v2;
-    const int TYeff = v2 ? T2::TY : T::TY;
+    const int v2 = T2::on ? p.v2 : 0;
+    const int TYeff = v2 == 3 ? Tile2bOf<R>::TY : v2 ? T2::TY : T::TY;
     IsoTK<R> k;
     k.u1 = p.u + (size_t)slot1 * p.slot_elems;
     k.sx = p.sx;
@@ -935,10 +949,12 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     timing_begin();
     bool launched = false;
     if constexpr (T2::on) {
-        if (v2) {
-            k_iso_tma2<R, T2::TY, T2::TZ4, PK><<<grid, (T2::TY / 2) * T2::TZ4 + 32, C2::SMEM, stream()>>>(p.tm_uh, k);
-            launched = true;
-        }
+        using T2b = Tile2bOf<R>;
+        using C2b = IsoTma2Cfg<R, T2b::TY, T2b::TZ4>;
+        if (v2 == 1) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 2><<<grid, (T2::TY / 2) * T2::TZ4 + 32, C2::SMEM, stream()>>>(p.tm_uh, k);
+        if (v2 == 2) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 1><<<grid, (T2::TY / 2) * T2::TZ4 + 32, C2::SMEM, stream()>>>(p.tm_uh, k);
+        if (v2 == 3) k_iso_tma2<R, T2b::TY, T2b::TZ4, PK, 1><<<grid, (T2b::TY / 2) * T2b::TZ4 + 32, C2b::SMEM, stream()>>>(p.tm_uh, k);
+        launched = v2 != 0;
     }
     if (!launched)
         kern<<<grid, T::TY * T::TZ4 + 32, C::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
