@@ -15,6 +15,7 @@ import numpy as np
 from .exceptions import BackendUnavailable
 
 __all__ = ['lib', 'have_lib', 'have_gpu', 'Dataobj', 'Profiler', 'Sparse', 'IsoArgs', 'TtiArgs', 'Tap', 'LinearArgs',
+           'SysTap', 'SysStage', 'SysInject', 'SysInterp', 'SystemArgs',
            'make_dataobj', 'ForeignDataobj', 'ForeignSparse', 'nccl_library_path', 'LIB_PATH']
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libb200stencil.so')
@@ -74,6 +75,35 @@ class Tap(Structure):
     _fields_ = [('tshift', c_int), ('off', c_int * 3), ('coef', c_float)]
 
 
+class SysTap(Structure):
+    _fields_ = [('field', c_int), ('tshift', c_int), ('off', c_int * 3), ('coef', c_float), ('cfield', c_int)]
+
+
+class SysStage(Structure):
+    _fields_ = [('out_field', c_int), ('out_tshift', c_int), ('ntaps', c_int), ('taps', POINTER(SysTap))]
+
+
+class SysInject(Structure):
+    _fields_ = [('s', POINTER(Sparse)), ('nfields', c_int), ('fields', c_int * 3), ('tshift', c_int),
+                ('scale', c_float), ('param_kind', c_int), ('param', POINTER(Dataobj))]
+
+
+class SysInterp(Structure):
+    _fields_ = [('s', POINTER(Sparse)), ('field', c_int), ('tshift', c_int)]
+
+
+class SystemArgs(Structure):
+    _fields_ = [('ndim', c_int), ('halo', c_int), ('nfields', c_int), ('fields', POINTER(POINTER(Dataobj))),
+                ('ncoefs', c_int), ('coefs', POINTER(POINTER(Dataobj))),
+                ('nstages', c_int), ('stages', POINTER(SysStage)),
+                ('ninject', c_int), ('ninterp', c_int), ('inject', POINTER(SysInject)), ('interp', POINTER(SysInterp)),
+                ('x_m', c_int), ('x_M', c_int), ('y_m', c_int), ('y_M', c_int), ('z_m', c_int), ('z_M', c_int),
+                ('time_m', c_int), ('time_M', c_int), ('deviceid', c_int), ('timers', POINTER(Profiler))]
+
+
+SYS_MAX_FIELDS, SYS_MAX_COEFS, SYS_MAX_TAPS = 24, 48, 96
+
+
 class LinearArgs(Structure):
     _fields_ = [('ndim', c_int), ('f', POINTER(Dataobj)), ('halo', c_int), ('ntaps', c_int),
                 ('taps', POINTER(Tap)), ('wshift', c_int),
@@ -86,7 +116,7 @@ MAX_TAPS = 64
 _lib = None
 
 # every symbol include/b200stencil.h declares
-SYMBOLS = ['b2_iso_forward', 'b2_tti_forward', 'b2_linear_forward', 'b2_nccl_unique_id', 'b2_halo_create',
+SYMBOLS = ['b2_iso_forward', 'b2_tti_forward', 'b2_linear_forward', 'b2_system_forward', 'b2_nccl_unique_id', 'b2_halo_create',
            'b2_halo_destroy', 'b2_halo_update', 'b2_device_count', 'b2_last_error', 'b2_version',
            'b2_launch_count', 'b2_kernel_timing_reset', 'b2_kernel_timing_ms',
            'b2_kernel_timing_enable', 'b2_malloc_device', 'b2_free_device', 'b2_memcpy_h2d',
@@ -116,6 +146,8 @@ def load_library():
     L.b2_tti_forward.restype = c_int
     L.b2_linear_forward.argtypes = [POINTER(LinearArgs)]
     L.b2_linear_forward.restype = c_int
+    L.b2_system_forward.argtypes = [POINTER(SystemArgs)]
+    L.b2_system_forward.restype = c_int
     L.b2_nccl_unique_id.argtypes = [c_char_p, c_char_p]
     L.b2_nccl_unique_id.restype = c_int
     L.b2_halo_create.argtypes = [c_char_p, c_char_p, c_int, c_int, c_int]

@@ -235,6 +235,276 @@ def _restate(expressions, kwargs):
     return op
 
 
+
+# ---------------------------------------------------------------------------------------------
+# first-order systems on staggered grids (elastic, staggered TTI ...): tap tables for b2_system_forward
+# ---------------------------------------------------------------------------------------------
+class _SystemPlan:
+    """What `_restate_system` extracts from the reference's evaluated equations."""
+
+    def __init__(self):
+        self.fields = []            # reference TimeFunctions, index = field id
+        self.scratch = []           # (field id, name) of scratch fields (interpolated expressions)
+        self.stages = []            # (out id, out_tshift, [(fid, tshift, off, coef, key|None)])
+        self.coef_exprs = {}        # key -> sympy expression of a coefficient array
+        self.injections = []        # (sparse function, [fids], tshift, scale expression)
+        self.interpolations = []    # (sparse function, fid, tshift)
+        self.grid = None
+        self.so = None
+
+
+def _wave_accesses(expr, fset):
+    out = []
+    for a in sympy.preorder_traversal(expr):
+        if isinstance(a, AbstractFunction) and a.function.name in fset and a not in out:
+            out.append(a)
+    return out
+
+
+def _array_offsets(acc):
+    """(tshift, array offsets) of an access to a (staggered) TimeFunction: the symbolic offset in units of the
+    spacing minus the function's own half-cell stagger must be an integer."""
+    f = acc.function
+    stag = tuple(getattr(f, 'staggered', None) or (0,) * len(f.dimensions))
+    tshift, offs = 0, []
+    for i, d, sg in zip(acc.indices, f.dimensions, stag):
+        k = sympy.nsimplify(sympy.simplify((sympy.sympify(i) - d) / d.spacing), rational=True)
+        if not k.is_Rational:
+            raise _Unconvertible(f"index {i} of {f.name}")
+        if d.is_Time:
+            tshift = int(k)
+            continue
+        k = k - sympy.Rational(int(sg), 2) if sg else k
+        if k.q != 1:
+            raise _Unconvertible(f"{f.name}: offset {i} is not on the function's own (staggered) grid")
+        offs.append(int(k))
+    return tshift, tuple(offs)
+
+
+def _linear_parts(rhs, fset):
+    """rhs = sum_a coef_a * a over the wavefield accesses a; raises when it is not linear / has a rest.
+    (The expressions are devito's Differentiable nodes, on which `sympy.diff` stays unevaluated: the
+    coefficient of a is rhs[a = 1, others = 0] - rhs[all = 0]; linearity is probed numerically.)"""
+    accs = _wave_accesses(rhs, fset)
+    dummies = {a: sympy.Dummy(f"w{i}") for i, a in enumerate(accs)}
+    e = rhs.xreplace(dummies)
+    zero = {d: sympy.Integer(0) for d in dummies.values()}
+    rest = e.xreplace(zero)
+    parts = []
+    for a, dmy in dummies.items():
+        one = dict(zero)
+        one[dmy] = sympy.Integer(1)
+        c = e.xreplace(one) - rest
+        parts.append((a, c))
+    # numeric probe: every non-wavefield leaf (parameter accesses, SafeInv nodes, symbols) gets a random value
+    rng = np.random.default_rng(7)
+    vals = {d: rng.uniform(-1.0, 1.0) for d in dummies.values()}
+
+    def num(x):
+        if x in vals:
+            return vals[x]
+        if x.is_Number:
+            return float(x)
+        if isinstance(x, AbstractFunction) or type(x).__name__ in ('SafeInv', 'cos', 'sin', 'sqrt', 'exp', 'Abs') \
+                or x.is_Symbol:
+            return vals.setdefault(x, rng.uniform(0.5, 1.5))
+        if x.is_Add:
+            return sum(num(a) for a in x.args)
+        if x.is_Mul:
+            out = 1.0
+            for a in x.args:
+                out *= num(a)
+            return out
+        if x.is_Pow:
+            return num(x.base) ** num(x.exp)
+        raise _Unconvertible(f"expression node {type(x).__name__}")
+    full = num(e)
+    r0 = num(rest)
+    lin = r0 + sum(num(c) * vals[dummies[a]] for a, c in parts)
+    if abs(full - lin) > 1e-9 * max(1.0, abs(full)):
+        raise _Unconvertible("update is not linear in the wavefields")
+    if abs(r0) > 1e-12:
+        raise _Unconvertible("update has a term without a wavefield")
+    return [(a, c) for a, c in parts if c != 0]
+
+
+def _restate_system(expressions, kwargs):
+    """Tap tables for a sequence of explicit updates `f.forward = linear(fields)`; None when the operator has
+    no such form (the acoustic / TTI second-order schemes never come here: `_restate` takes them first)."""
+    plan = _SystemPlan()
+    subs = dict(kwargs.get('subs') or {})
+    updates, sparse_ops = [], []
+    for e in expressions:
+        if isinstance(e, (_RefInjection, _RefInterpolation)):
+            sparse_ops.append(e)
+        elif isinstance(e, _RefEq):
+            if e.subdomain is not None and getattr(e.subdomain, 'name', None) not in ('domain', 'physdomain'):
+                raise _Unconvertible(f"subdomain {getattr(e.subdomain, 'name', None)}")
+            ev = e.evaluate
+            flat = ev._flatten if hasattr(ev, '_flatten') else [ev]
+            for q in flat:
+                updates.append((q.lhs, q.rhs))
+        else:
+            raise _Unconvertible(f"{type(e).__name__} in the operator")
+    if not updates:
+        return None
+    for lhs, _ in updates:
+        f = getattr(lhs, 'function', None)
+        if f is None or not f.is_TimeFunction or f.time_order != 1 or f.save is not None:
+            raise _Unconvertible("lhs is not a buffered first-order-in-time TimeFunction")
+        if f.name not in [q.name for q in plan.fields]:
+            plan.fields.append(f)
+    grid = plan.fields[0].grid
+    so = plan.fields[0].space_order
+    if any(f.grid is not grid or f.space_order != so for f in plan.fields) or grid.dim not in (2, 3):
+        raise _Unconvertible("fields on different grids / space orders")
+    if 'physdomain' in grid.subdomains and any(getattr(d, 'is_Sub', False) for d in grid.subdomains['physdomain'].dimensions):
+        raise _Unconvertible("free-surface model")
+    plan.grid, plan.so = grid, so
+    plan.values = {str(k): float(v) for k, v in subs.items()}       # spacings substituted by the Operator (`subs=`)
+    fset = {f.name for f in plan.fields}           # by name: tensor components are re-created on access
+    fid = {f.name: i for i, f in enumerate(plan.fields)}
+
+    def taps_of(rhs):
+        taps = []
+        for acc, coef in _linear_parts(rhs, fset):
+            tshift, offs = _array_offsets(acc)
+            if tshift not in (0, 1) or any(abs(o) > so for o in offs):
+                raise _Unconvertible("tap outside the supported time levels / halo")
+            # coefficient = scalar part (numbers, dt, spacings: evaluated when the operator is applied) x field part
+            # (material parameters / damping at shifted positions: tabulated as one array per distinct expression)
+            coef = sympy.sympify(coef)
+            deps = {n for n in sympy.preorder_traversal(coef)
+                    if isinstance(n, AbstractFunction) or type(n).__name__ == 'SafeInv'}
+            scal, fieldpart = (coef.as_independent(*deps, as_Add=False) if deps else (coef, sympy.Integer(1)))
+            key = None
+            if fieldpart != 1:
+                key = sympy.srepr(fieldpart)
+                plan.coef_exprs.setdefault(key, fieldpart)
+            taps.append((fid[acc.function.name], tshift, offs, scal, key))
+        return taps
+
+    for lhs, rhs in updates:
+        tshift, offs = _array_offsets(lhs)
+        if tshift != 1 or any(offs):
+            raise _Unconvertible("lhs is not `f.forward` at the function's own position")
+        plan.stages.append((fid[lhs.function.name], 1, taps_of(rhs)))
+    dt = grid.stepping_dim.spacing
+    for e in sparse_ops:
+        sf = e.interpolator.sfunction
+        if type(e.interpolator).__name__ not in ('LinearInterpolator', 'SincInterpolator'):
+            raise _Unconvertible("interpolator")
+        if isinstance(e, _RefInjection):
+            flds = (list(e.field) if isinstance(e.field, (tuple, list, sympy.Tuple, sympy.MatrixBase)) or
+                    getattr(e.field, 'is_Matrix', False) else [e.field])
+            exprs = list(e.expr) if isinstance(e.expr, (tuple, list, sympy.Tuple)) else [e.expr] * len(flds)
+            if len(flds) > 3 or len({sympy.srepr(sympy.sympify(x)) for x in exprs}) != 1:
+                raise _Unconvertible("injection into more than 3 fields / with different expressions")
+            ids, shifts = [], set()
+            for a in flds:
+                if a.function.name not in fset:
+                    raise _Unconvertible("injection into a field that is not updated")
+                ts, offs = _array_offsets(a)
+                if any(offs) or any(getattr(a.function, 'staggered', None) or ()):
+                    raise _Unconvertible("injection into a staggered field")
+                ids.append(fid[a.function.name])
+                shifts.add(ts)
+            src_acc = [a for a in sympy.preorder_traversal(sympy.sympify(exprs[0]))
+                       if isinstance(a, AbstractFunction) and a.function.name == sf.name]
+            if len(shifts) != 1 or len(src_acc) != 1:
+                raise _Unconvertible("injection expression")
+            scale = sympy.simplify(sympy.sympify(exprs[0]) / src_acc[0])
+            pacc = [a for a in sympy.preorder_traversal(scale) if isinstance(a, AbstractFunction)]
+            pkind, pfn = 0, None
+            if pacc:
+                # src * dt * vp**2  /  src * dt / m : the injection kernel's two position-dependent scale modes
+                P = pacc[0]
+                if len(set(pacc)) != 1 or any(i != d for i, d in zip(P.indices, P.function.dimensions)) or \
+                        P.function.space_order != so:
+                    raise _Unconvertible("position-dependent injection scale")
+                for kind, q in ((1, sympy.simplify(scale / P ** 2)), (2, sympy.simplify(scale * P))):
+                    if not any(isinstance(a, AbstractFunction) for a in sympy.preorder_traversal(q)):
+                        pkind, pfn, scale = kind, P.function, q
+                        break
+                else:
+                    raise _Unconvertible("position-dependent injection scale")
+            plan.injections.append((sf, ids, shifts.pop(), scale, pkind, pfn))
+        else:
+            if e.increment:
+                raise _Unconvertible("incremental interpolation")
+            ex = sympy.sympify(e.expr)
+            if isinstance(ex, AbstractFunction) and ex.function.name in fset and \
+                    not any(getattr(ex.function, 'staggered', None) or ()):
+                ts, offs = _array_offsets(ex)
+                if any(offs):
+                    raise _Unconvertible("interpolation of a shifted field")
+                plan.interpolations.append((sf, fid[ex.function.name], ts))
+            else:
+                # an expression (div(v) ...): an extra stage fills a scratch field that is then sampled
+                evx = ex.evaluate
+                sid = len(plan.fields) + len(plan.scratch)
+                plan.scratch.append((sid, f"scratch_{sf.name}"))
+                plan.stages.append((sid, 0, taps_of(evx)))
+                plan.interpolations.append((sf, sid, 0))
+    if len(plan.fields) + len(plan.scratch) > 16:
+        raise _Unconvertible("too many fields")
+    # stages that fill scratch fields read time level t: run them BEFORE the updates overwrite nothing they need
+    # (they read tshift 0 only, the updates write tshift 1), order as given is fine
+    return plan
+
+
+def _eval_coef(expr, grid, values):
+    """NumPy evaluation of a coefficient expression (material parameters at shifted node positions, SafeInv,
+    numbers, dt) over the grid's domain, float32 like the reference's generated code."""
+    shape = tuple(grid.shape)
+
+    def rec(e):
+        if isinstance(e, AbstractFunction):
+            f = e.function
+            arr = f.data_with_halo.view(np.ndarray) if hasattr(f, 'data_with_halo') else None
+            sl = []
+            for i, d, (hl, hr), n in zip(e.indices, f.dimensions, f._size_halo, shape):
+                k = sympy.nsimplify(sympy.simplify((sympy.sympify(i) - d) / d.spacing), rational=True)
+                if not (k.is_Rational and k.q == 1) or abs(int(k)) > hl:
+                    raise _Unconvertible(f"parameter access {e}")
+                sl.append(slice(hl + int(k), hl + int(k) + n))
+            return np.asarray(arr[tuple(sl)], dtype=np.float32)
+        if getattr(e, 'is_Constant', False) and hasattr(e, 'data') and not e.is_Number:
+            return np.float32(e.data)
+        if e.is_Number:
+            return np.float32(float(e))
+        if e.is_Symbol:
+            if e.name in values:
+                return np.float32(values[e.name])
+            raise _Unconvertible(f"no value for {e}")
+        if e.is_Add:
+            out = rec(e.args[0])
+            for a in e.args[1:]:
+                out = out + rec(a)
+            return out
+        if e.is_Mul:
+            out = rec(e.args[0])
+            for a in e.args[1:]:
+                out = out * rec(a)
+            return out
+        if e.is_Pow:
+            b, x = rec(e.base), e.exp
+            if x == -1:
+                return np.float32(1.0) / b
+            return np.power(b, np.float32(float(x)))
+        if type(e).__name__ in ('cos', 'sin', 'sqrt', 'exp', 'Abs') and len(e.args) == 1:
+            fn = {'cos': np.cos, 'sin': np.sin, 'sqrt': np.sqrt, 'exp': np.exp, 'Abs': np.abs}[type(e).__name__]
+            return fn(rec(e.args[0])).astype(np.float32)
+        if type(e).__name__ == 'SafeInv':
+            # devito/passes/iet/misc.py:243-258: (a < eps || b < eps) ? 0 : 1/a with eps = resolution^2
+            a, b = rec(e.args[0]), rec(e.args[1])
+            eps = np.float32(np.finfo(np.float32).resolution ** 2)
+            with np.errstate(divide='ignore'):
+                return np.where((a < eps) | (b < eps), np.float32(0.0), np.float32(1.0) / a).astype(np.float32)
+        raise _Unconvertible(f"coefficient node {type(e).__name__}")
+    out = rec(sympy.sympify(expr))
+    return np.ascontiguousarray(np.broadcast_to(out, shape), dtype=np.float32)
+
 # ---------------------------------------------------------------------------------------------
 # the Operator
 # ---------------------------------------------------------------------------------------------
@@ -268,16 +538,86 @@ class B200CudaOperator(Cpu64AdvOmpOperator):
     def _build(cls, expressions, **kwargs):
         kwargs.pop('b200_target', None)
         op = super()._build(expressions, **kwargs)
+        op._b200_sys = None
         try:
             op._b200 = _restate(expressions, kwargs)
             op._b200_why = None
         except (_Unconvertible, ValueError, TypeError, KeyError, AttributeError) as e:
             op._b200, op._b200_why = None, f"{type(e).__name__}: {e}"
+        if op._b200 is None:
+            # not one of the second-order propagators: a first-order system on a staggered grid?
+            try:
+                op._b200_sys = _restate_system(expressions, kwargs)
+            except (_Unconvertible, ValueError, TypeError, KeyError, AttributeError, NotImplementedError) as e:
+                op._b200_why = f"{op._b200_why}; as a linear system: {type(e).__name__}: {e}"
         return op
 
     @property
     def backend(self):
-        return 'cuda-sm100a' if getattr(self, '_b200', None) is not None else 'reference-cpu'
+        if getattr(self, '_b200', None) is not None or getattr(self, '_b200_sys', None) is not None:
+            return 'cuda-sm100a'
+        return 'reference-cpu'
+
+    def _apply_system(self, plan, **kwargs):
+        """Run a staggered-grid system through `b2_system_forward` with the reference's own arrays."""
+        from devito_b200.system import LinearSystem, Stage, Tap
+        from devito_b200.operator import PerformanceSummary, PerfEntry
+        kwargs.pop('autotune', None)
+        with self._profiler.timer_on('arguments-preprocess'):
+            args = self.arguments(**kwargs)
+        grid, nd = plan.grid, plan.grid.dim
+        values = dict(getattr(plan, 'values', {}))
+        for sp in grid.spacing_symbols:
+            if sp.name in args:
+                values.setdefault(sp.name, float(args[sp.name]))
+        values[grid.stepping_dim.spacing.name] = float(args['dt'])
+        hold = []
+
+        def dataobj(name):
+            fo = L_.ForeignDataobj(_addr(args[name]), keep=args[name])
+            hold.append(fo)
+            return fo
+
+        fields = [dataobj(f.name) for f in plan.fields]
+        alloc = tuple(int(s) + 2 * plan.so for s in grid.shape)
+        for sid, name in plan.scratch:
+            arr = np.zeros((1,) + alloc, dtype=np.float32)
+            hold.append(arr)
+            fields.append(L_.make_dataobj(host=arr))
+        keys = list(plan.coef_exprs)
+        coefs = [_eval_coef(plan.coef_exprs[k], grid, values) for k in keys]
+        kid = {k: i for i, k in enumerate(keys)}
+        def scalar(ex):
+            ex = sympy.sympify(ex)
+            return float(ex.xreplace({q: values[q.name] for q in ex.free_symbols if q.name in values}))
+        stages = [Stage(out, ts, [Tap(f, t, o, scalar(c), kid[key] if key is not None else -1) for f, t, o, c, key in taps])
+                  for out, ts, taps in plan.stages]
+
+        def sparse(sf):
+            ws = [dataobj(f"{sf.name}_w{'xyz'[i]}" if f"{sf.name}_w{'xyz'[i]}" in args else f"wsincrp_{sf.name}{'xyz'[i]}")
+                  for i in range(nd)]
+            return L_.ForeignSparse(sf.name, dataobj(sf.name), dataobj(f"{sf.name}_gp"), ws,
+                                    p_m=int(args[f'p_{sf.name}_m']), p_M=int(args[f'p_{sf.name}_M']), r=int(sf.r))
+        inj = []
+        for sf, ids, ts, scale, pkind, pfn in plan.injections:
+            inj.append((sparse(sf), ids, ts, scalar(scale), pkind, dataobj(pfn.name) if pfn is not None else None))
+        itp = [(sparse(sf), fidx, ts) for sf, fidx, ts in plan.interpolations]
+        system = LinearSystem(nd, plan.so, len(fields), stages, inj, itp)
+        lo = [int(args[d.min_name]) for d in grid.dimensions]
+        hi = [int(args[d.max_name]) for d in grid.dimensions]
+        dev = dv.configuration['deviceid']
+        timers, wall = system.apply(fields, coefs, lo, hi, int(args['time_m']), int(args['time_M']),
+                                    deviceid=0 if dev is None or dev < 0 else dev)
+        nsteps = int(args['time_M']) - int(args['time_m']) + 1
+        pts = float(np.prod([h - l + 1 for l, h in zip(lo, hi)])) * nsteps
+        summary = PerformanceSummary()
+        for nm in ('section0', 'section1', 'section2'):
+            t = getattr(timers, nm)
+            summary[nm] = PerfEntry(t, gpointss=(pts / t / 1e9 if t > 0 and nm == 'section0' else None))
+        summary.globals['fdlike'] = PerfEntry(wall, gpointss=pts / wall / 1e9 if wall > 0 else None)
+        self._b200_last = {'wall': wall, 'stages': len(stages), 'coefficient_arrays': len(coefs),
+                           'taps': sum(len(s.taps) for s in stages)}
+        return summary
 
     def arguments(self, **kwargs):
         # thread-count defaults ask `configuration['platform']` — the GPU here — for its "cores"
@@ -291,6 +631,8 @@ class B200CudaOperator(Cpu64AdvOmpOperator):
 
     def apply(self, **kwargs):
         shadow = getattr(self, '_b200', None)
+        if shadow is None and getattr(self, '_b200_sys', None) is not None:
+            return self._apply_system(self._b200_sys, **kwargs)
         if shadow is None:
             return super().apply(**kwargs)
         kwargs.pop('autotune', None)

@@ -212,6 +212,69 @@ struct b2_linear_args {
 };
 int b2_linear_forward(const struct b2_linear_args *a);
 
+/* ---- generic explicit linear SYSTEM (staggered-grid schemes: elastic, TTI first-order form ...) ----------
+ * The time loops the reference generates for first-order systems on staggered grids
+ * (examples/seismic/elastic/operators.py:26-65 `ForwardElastic`: v.forward = damp (v + dt b div tau),
+ * tau.forward = damp (tau + dt (lam diag(div v.forward) + mu (grad v.forward + grad v.forward^T)));
+ * examples/seismic/tti/operators.py:280-428 staggered TTI) have one shape: per time step a sequence of
+ * STAGES, each writing one field as a linear combination of shifted reads of the fields,
+ *     out[t + out_tshift][p] = sum_k coef_k * C_{cfield_k}[p] * F_{field_k}[t + tshift_k][p + off_k],
+ * where C_j are coefficient arrays tabulated once per call (averaged / harmonically averaged material
+ * parameters times the damping mask, evaluated at the output's staggered position) and off_k are ARRAY
+ * offsets (the half-cell shifts of staggered fields are already folded in). Stages run in order, so a
+ * later stage may read what an earlier one wrote at t+1 (tshift = 1). After the stages of a step:
+ * injections (into up to 3 fields at once: the diagonal of the stress tensor) and interpolations
+ * (of a field, or of a scratch field that an extra stage filled, e.g. div(v)).
+ * All fields share the grid extents and the halo width `halo`; a field with 1 time slot is scratch. */
+struct b2_sys_tap {
+    int field;                        /* index into `fields`                                    */
+    int tshift;                       /* time level read: t + tshift (0 or 1)                   */
+    int off[3];                       /* array offsets                                          */
+    float coef;
+    int cfield;                       /* index into `coefs`, or -1                              */
+};
+struct b2_sys_stage {
+    int out_field;
+    int out_tshift;                   /* +1 for an update, 0 for a scratch field                */
+    int ntaps;
+    const struct b2_sys_tap *taps;
+};
+struct b2_sys_inject {
+    struct b2_sparse *s;
+    int nfields;                      /* 1..3                                                    */
+    int fields[3];
+    int tshift;                       /* level deposited into (normally +1)                      */
+    float scale;                      /* value = scale * src[time][p] * weights [* f(param)]     */
+    int param_kind;                   /* 0: none; B2_PARAM_VP: * param[cell]^2; B2_PARAM_M: / param[cell] */
+    struct b2_dataobj *param;         /* space array with the fields' allocated layout, or NULL  */
+};
+struct b2_sys_interp {
+    struct b2_sparse *s;
+    int field;
+    int tshift;
+};
+#define B2_SYS_MAX_FIELDS 24
+#define B2_SYS_MAX_COEFS 48
+#define B2_SYS_MAX_TAPS 96
+struct b2_system_args {
+    int ndim;                         /* 2 or 3                                                  */
+    int halo;                         /* halo width of every field on every space dimension      */
+    int nfields;
+    struct b2_dataobj **fields;       /* (tsize, x, y[, z]) each                                 */
+    int ncoefs;
+    struct b2_dataobj **coefs;        /* (x, y[, z]) each, NO halo (values at the output points) */
+    int nstages;
+    const struct b2_sys_stage *stages;
+    int ninject, ninterp;
+    const struct b2_sys_inject *inject;
+    const struct b2_sys_interp *interp;
+    int x_m, x_M, y_m, y_M, z_m, z_M;
+    int time_m, time_M;
+    int deviceid;
+    struct b2_profiler *timers;       /* section0 = stages, section1 = injection, section2 = interpolation */
+};
+int b2_system_forward(const struct b2_system_args *a);
+
 /* ---- halo exchange under x-slab decomposition (replaces `haloupdate0`/`sendrecv0`,
  *      devito/mpi/routines.py:285-552; printed examples/mpi/overview.ipynb:503-560) -------- */
 /* NCCL bootstrap: rank 0 calls b2_nccl_unique_id, the 128 bytes are broadcast by the host

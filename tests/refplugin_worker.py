@@ -58,6 +58,76 @@ def ffi():
                               arrays=[bool(x) for x in (a.vp_arr, a.epsilon_arr, a.delta_arr, a.theta_arr, a.phi_arr)]))
             return 0
 
+        def b2_system_forward(self, ref):
+            """NumPy emulation of the tap-table executor (csrc/b2_api_system.cu) on the structs that cross the ABI."""
+            a = ref._obj
+            nd, h = a.ndim, a.halo
+
+            def arr(dobj, ndim):
+                shape = tuple(dobj.size[i] for i in range(ndim))
+                n = int(np.prod(shape))
+                return np.ctypeslib.as_array((ctypes.c_float * n).from_address(dobj.data)).reshape(shape)
+            F = [arr(a.fields[i].contents, nd + 1) for i in range(a.nfields)]
+            C = [arr(a.coefs[i].contents, nd) for i in range(a.ncoefs)]
+            lo = [a.x_m, a.y_m, a.z_m][:nd]
+            hi = [a.x_M, a.y_M, a.z_M][:nd]
+            box = tuple(slice(l + h, u + h + 1) for l, u in zip(lo, hi))
+            cbox = tuple(slice(l, u + 1) for l, u in zip(lo, hi))
+            ntaps = 0
+            for time in range(a.time_m, a.time_M + 1):
+                for s in range(a.nstages):
+                    st = a.stages[s]
+                    acc = np.zeros([u - l + 1 for l, u in zip(lo, hi)], dtype=np.float32)
+                    for i in range(st.ntaps):
+                        t = st.taps[i]
+                        src = F[t.field][(time + t.tshift) % F[t.field].shape[0]]
+                        sl = tuple(slice(l + h + t.off[d], u + h + 1 + t.off[d]) for d, (l, u) in enumerate(zip(lo, hi)))
+                        c = np.float32(t.coef) * (C[t.cfield][cbox] if t.cfield >= 0 else np.float32(1.0))
+                        acc += c * src[sl]
+                        ntaps += 1
+                    out = F[st.out_field][(time + st.out_tshift) % F[st.out_field].shape[0]]
+                    out[box] = acc
+                for i in range(a.ninject):
+                    q = a.inject[i]
+                    sp = q.s.contents
+                    data = arr(sp.data.contents, 2)
+                    gp = np.ctypeslib.as_array((ctypes.c_int * (data.shape[1] * nd)).from_address(sp.gp.contents.data)).reshape(-1, nd)
+                    ws = [arr(sp.w[d].contents, 2) for d in range(nd)]
+                    r = sp.r
+                    for p in range(sp.p_m, sp.p_M + 1):
+                        for off in np.ndindex(*([2 * r] * nd)):
+                            cell = [gp[p, d] + off[d] - r + 1 for d in range(nd)]
+                            if any(c < l - r or c > u + r for c, l, u in zip(cell, lo, hi)):
+                                continue
+                            w = np.prod([ws[d][p, off[d]] for d in range(nd)])
+                            sc = q.scale
+                            if q.param_kind:
+                                pv = arr(q.param.contents, nd)[tuple(c + h for c in cell)]
+                                sc = q.scale * pv * pv if q.param_kind == 1 else q.scale / pv
+                            for j in range(q.nfields):
+                                f = F[q.fields[j]]
+                                f[(time + q.tshift) % f.shape[0]][tuple(c + h for c in cell)] += np.float32(w * data[time, p] * sc)
+                for i in range(a.ninterp):
+                    q = a.interp[i]
+                    sp = q.s.contents
+                    data = arr(sp.data.contents, 2)
+                    gp = np.ctypeslib.as_array((ctypes.c_int * (data.shape[1] * nd)).from_address(sp.gp.contents.data)).reshape(-1, nd)
+                    ws = [arr(sp.w[d].contents, 2) for d in range(nd)]
+                    r = sp.r
+                    f = F[q.field][(time + q.tshift) % F[q.field].shape[0]]
+                    if time >= data.shape[0]:
+                        continue
+                    for p in range(sp.p_m, sp.p_M + 1):
+                        tot = 0.0
+                        for off in np.ndindex(*([2 * r] * nd)):
+                            cell = [gp[p, d] + off[d] - r + 1 for d in range(nd)]
+                            if any(c < l - r or c > u + r for c, l, u in zip(cell, lo, hi)):
+                                continue
+                            tot += np.prod([ws[d][p, off[d]] for d in range(nd)]) * f[tuple(c + h for c in cell)]
+                        data[time, p] = tot
+            calls.append(dict(kind='system', nfields=a.nfields, ncoefs=a.ncoefs, nstages=a.nstages, ntaps=ntaps))
+            return 0
+
         def b2_last_error(self):
             return b''
 
@@ -103,6 +173,46 @@ def ffi():
     m4 = demo_model('layers-tti', space_order=4, **kw)
     AnisotropicWaveSolver(m4, setup_geometry(m4, 100.0), space_order=4).forward()
     assert calls[-1]['kind'] == 'tti' and all(calls[-1]['arrays'])
+    # first-order systems on staggered grids (elastic, viscoelastic, staggered TTI): the tap tables and coefficient
+    # arrays the plugin derives from the reference's evaluated equations, executed by the NumPy emulation of
+    # `b2_system_forward` above, must reproduce the reference's own CPU run of the same Operator object
+    from examples.seismic.elastic import ElasticWaveSolver
+    from examples.seismic.viscoelastic import ViscoelasticWaveSolver
+
+    def fields_of(out):
+        res = {}
+        for o in out:
+            if hasattr(o, 'values') and not hasattr(o, 'data'):       # TensorTimeFunction
+                res.update({f.name: np.array(f.data) for f in o.values()})
+            elif hasattr(o, '__iter__') and not hasattr(o, 'data'):   # VectorTimeFunction
+                res.update({f.name: np.array(f.data) for f in o})
+            elif hasattr(o, 'data'):
+                res[o.name] = np.array(o.data)
+        return res
+
+    cases = [('elastic-3d', ElasticWaveSolver, 'layers-elastic', (14, 12, 13), {}, 10, 10),
+             ('elastic-2d', ElasticWaveSolver, 'layers-elastic', (24, 21), {}, 6, 6),
+             ('viscoelastic-2d', ViscoelasticWaveSolver, 'layers-viscoelastic', (22, 20), {}, 9, 9),
+             ('tti-staggered-3d', AnisotropicWaveSolver, 'layers-tti', (13, 12, 14), dict(kernel='staggered'), None, None),
+             ('tti-staggered-2d', AnisotropicWaveSolver, 'layers-tti', (22, 20), dict(kernel='staggered'), None, None)]
+    for tag, cls, preset, shape, skw, nstages, nfields in cases:
+        nd = len(shape)
+        me = demo_model(preset, space_order=4, shape=shape, nbl=4, spacing=(10.,) * nd, dtype=np.float32)
+        se = cls(me, setup_geometry(me, 22.0), space_order=4, **skw)
+        ope = se.op_fwd()
+        assert ope.backend == 'cuda-sm100a' and ope._b200_sys is not None, (tag, ope._b200_why)
+        got = fields_of(se.forward()[:-1])
+        assert calls[-1]['kind'] == 'system', tag
+        if nstages is not None:
+            assert calls[-1]['nstages'] == nstages and calls[-1]['nfields'] == nfields, (tag, calls[-1])
+        ope._b200_sys = None                               # the same Operator object on the reference's CPU path
+        ref = fields_of(se.forward()[:-1])
+        assert set(ref) == set(got) and len(ref) >= 3, (tag, sorted(ref))
+        for name in ref:
+            scale = max(float(np.abs(ref[name]).max()), 1e-30)
+            err = float(np.abs(got[name] - ref[name]).max()) / scale
+            assert err < 5e-5, (tag, name, err)
+            assert float(np.abs(ref[name]).max()) > 0, (tag, name)
     # the set-up operators stayed on the reference's CPU path (and ran: the damping profile is there)
     assert float(np.max(model.damp.data)) > 0
     print('REFPLUGIN-FFI-OK', len(calls))
@@ -138,6 +248,54 @@ def gpu():
         assert np.isclose(got[0], gold[tag]['norm_rec'], rtol=1e-3), (tag, got, gold[tag])
         assert np.isclose(got[1], gold[tag]['norm_u'], rtol=1e-3), (tag, got, gold[tag])
         assert np.isclose(got[2], gold[tag]['norm_v'], rtol=1e-3), (tag, got, gold[tag])
+    # first-order systems on staggered grids through b2_system_forward: the reference's own examples against their
+    # known answers (elastic_example.py:44-45, viscoelastic_example.py:45-46), and GPU vs the reference's CPU run of
+    # the same Operator object (3-D elastic, staggered TTI 2-D / 3-D)
+    from examples.seismic.elastic.elastic_example import run as erun
+    from examples.seismic.viscoelastic.viscoelastic_example import run as verun
+    from examples.seismic.elastic import ElasticWaveSolver
+    from examples.seismic.viscoelastic import ViscoelasticWaveSolver
+    n1 = L.b2_launch_count()
+    _, _, _, [rec1, rec2, v, tau] = erun(dtype=np.float32)
+    out['elastic_2d'] = (float(norm(rec1)), float(norm(rec2)))
+    assert np.isclose(out['elastic_2d'][0], 19.9367, atol=1e-3, rtol=0), out['elastic_2d']
+    assert np.isclose(out['elastic_2d'][1], 0.6689, atol=1e-3, rtol=0), out['elastic_2d']
+    _, _, _, [rec1, rec2, v, tau] = verun(dtype=np.float32)
+    out['viscoelastic_2d'] = (float(norm(rec1)), float(norm(rec2)))
+    assert np.isclose(out['viscoelastic_2d'][0], 12.62339, atol=1e-3, rtol=0), out['viscoelastic_2d']
+    assert np.isclose(out['viscoelastic_2d'][1], 0.330103, atol=1e-3, rtol=0), out['viscoelastic_2d']
+    assert int(L.b2_launch_count() - n1) > 1000
+
+    def fields_of(res):
+        d = {}
+        for o in res:
+            if hasattr(o, 'values') and not hasattr(o, 'data'):
+                d.update({f.name: np.array(f.data) for f in o.values()})
+            elif hasattr(o, '__iter__') and not hasattr(o, 'data'):
+                d.update({f.name: np.array(f.data) for f in o})
+            elif hasattr(o, 'data'):
+                d[o.name] = np.array(o.data)
+        return d
+    for tag, cls, preset, shape, skw in [('elastic-3d', ElasticWaveSolver, 'layers-elastic', (40, 36, 38), {}),
+                                         ('viscoelastic-3d', ViscoelasticWaveSolver, 'layers-viscoelastic', (30, 28, 26), {}),
+                                         ('tti-staggered-3d', AnisotropicWaveSolver, 'layers-tti', (36, 40, 34), dict(kernel='staggered')),
+                                         ('tti-staggered-2d', AnisotropicWaveSolver, 'layers-tti', (80, 90), dict(kernel='staggered'))]:
+        nd = len(shape)
+        me = demo_model(preset, space_order=8 if 'tti' in tag else 4, shape=shape, nbl=10, spacing=(10.,) * nd, dtype=np.float32)
+        se = cls(me, setup_geometry(me, 120.0), space_order=8 if 'tti' in tag else 4, **skw)
+        ope = se.op_fwd()
+        assert ope.backend == 'cuda-sm100a' and ope._b200_sys is not None, (tag, ope._b200_why)
+        nb = L.b2_launch_count()
+        got = fields_of(se.forward()[:-1])
+        assert L.b2_launch_count() > nb
+        ope._b200_sys = None                               # the same Operator object on the reference's CPU path
+        ref = fields_of(se.forward()[:-1])
+        worst = 0.0
+        for name in ref:
+            scale = max(float(np.abs(ref[name]).max()), 1e-30)
+            worst = max(worst, float(np.abs(got[name] - ref[name]).max()) / scale)
+        out[tag] = worst
+        assert worst < 1e-4, (tag, worst)
     launches = int(L.b2_launch_count() - n0)
     assert launches > 1000, launches                  # the propagators ran in libb200stencil.so
     print('REFPLUGIN-GPU-OK', json.dumps({'launches': launches, 'norms': out}))
