@@ -48,7 +48,21 @@ from devito_b200 import _lib as L_
 from devito_b200.equation import FreeSurface
 from devito_b200.symbolics import Access, Index, Number, Call, _np_funcs
 
-__all__ = ['B200CudaOperator', 'register', 'activate']
+__all__ = ['B200CudaOperator', 'register', 'activate', 'reference_cpu']
+
+# tests: run recognised operators on the reference's own CPU path (same Operator objects)
+_force_cpu = [False]
+
+
+class reference_cpu:
+    """Context manager: inside it every B200CudaOperator applies through the reference's CPU code path."""
+
+    def __enter__(self):
+        self._old = _force_cpu[0]
+        _force_cpu[0] = True
+
+    def __exit__(self, *a):
+        _force_cpu[0] = self._old
 
 
 class _Unconvertible(Exception):
@@ -379,7 +393,7 @@ def _restate_system(expressions, kwargs):
             scal, fieldpart = (coef.as_independent(*deps, as_Add=False) if deps else (coef, sympy.Integer(1)))
             key = None
             if fieldpart != 1:
-                key = sympy.srepr(fieldpart)
+                key = str(fieldpart)            # (srepr does not print the names of devito Functions: collisions)
                 plan.coef_exprs.setdefault(key, fieldpart)
             taps.append((fid[acc.function.name], tshift, offs, scal, key))
         return taps
@@ -398,7 +412,7 @@ def _restate_system(expressions, kwargs):
             flds = (list(e.field) if isinstance(e.field, (tuple, list, sympy.Tuple, sympy.MatrixBase)) or
                     getattr(e.field, 'is_Matrix', False) else [e.field])
             exprs = list(e.expr) if isinstance(e.expr, (tuple, list, sympy.Tuple)) else [e.expr] * len(flds)
-            if len(flds) > 3 or len({sympy.srepr(sympy.sympify(x)) for x in exprs}) != 1:
+            if len(flds) > 3 or len({str(sympy.sympify(x)) for x in exprs}) != 1:
                 raise _Unconvertible("injection into more than 3 fields / with different expressions")
             ids, shifts = [], set()
             for a in flds:
@@ -432,7 +446,10 @@ def _restate_system(expressions, kwargs):
         else:
             if e.increment:
                 raise _Unconvertible("incremental interpolation")
+            # the interpolated expression is evaluated at the sparse points' (node) position
+            # (devito/operations/interpolators.py:527 `expr._eval_at(self.sfunction).evaluate`)
             ex = sympy.sympify(e.expr)
+            ex = ex._eval_at(sf) if hasattr(ex, '_eval_at') else ex
             if isinstance(ex, AbstractFunction) and ex.function.name in fset and \
                     not any(getattr(ex.function, 'staggered', None) or ()):
                 ts, offs = _array_offsets(ex)
@@ -630,6 +647,8 @@ class B200CudaOperator(Cpu64AdvOmpOperator):
         return super().arguments(**kwargs)
 
     def apply(self, **kwargs):
+        if _force_cpu[0]:
+            return super().apply(**kwargs)
         shadow = getattr(self, '_b200', None)
         if shadow is None and getattr(self, '_b200_sys', None) is not None:
             return self._apply_system(self._b200_sys, **kwargs)
