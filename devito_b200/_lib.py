@@ -101,7 +101,7 @@ class SystemArgs(Structure):
                 ('time_m', c_int), ('time_M', c_int), ('deviceid', c_int), ('timers', POINTER(Profiler))]
 
 
-SYS_MAX_FIELDS, SYS_MAX_COEFS, SYS_MAX_TAPS = 24, 48, 96
+SYS_MAX_FIELDS, SYS_MAX_COEFS, SYS_MAX_TAPS = 24, 48, 160
 
 
 class LinearArgs(Structure):

@@ -255,7 +255,7 @@ struct b2_sys_interp {
 };
 #define B2_SYS_MAX_FIELDS 24
 #define B2_SYS_MAX_COEFS 48
-#define B2_SYS_MAX_TAPS 96
+#define B2_SYS_MAX_TAPS 160
 struct b2_system_args {
     int ndim;                         /* 2 or 3                                                  */
     int halo;                         /* halo width of every field on every space dimension      */
