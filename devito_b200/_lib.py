@@ -52,7 +52,7 @@ class IsoArgs(Structure):
                 ('halo', c_void_p), ('timers', POINTER(Profiler)), ('adjoint', c_int),
                 ('grad', POINTER(Dataobj)), ('usave', POINTER(Dataobj)), ('free_surface', c_int), ('ot4', c_int),
                 ('born_U', POINTER(Dataobj)), ('born_dm', POINTER(Dataobj)),
-                ('snap', POINTER(Dataobj)), ('snap_factor', c_int), ('snap_toff', c_int)]
+                ('snap', POINTER(Dataobj)), ('snap_factor', c_int), ('snap_toff', c_int), ('host_io', c_int)]
 
 
 class TtiArgs(Structure):

@@ -211,25 +211,38 @@ struct StreamedLoop {
 };
 static StreamedLoop g_streamed;
 
-static bool streamed_wanted(const b2_iso_args *a, const IsoPlan &p, const DevArray &u) {
+static bool streamed_wanted(const b2_iso_args *a, const IsoPlan &p, const DevArray &u, bool host_io) {
     const char *e = getenv("B2_STREAM");
     if (e && atoi(e) == 0) return false;
     const bool forced = e && atoi(e) == 2;                 // tests: also on small grids
-    if (!u.owned || a->ndim != 3 || !p.use_tma || p.tsize != 3) return false;
-    if (a->halo || a->adjoint || a->free_surface || a->ot4 || a->born_U || a->snap || a->grad) return false;
+    if (!(u.owned || host_io) || a->ndim != 3 || !p.use_tma || p.tsize != 3) return false;
+    if (a->adjoint || a->free_surface || a->ot4 || a->born_U || a->snap || a->grad) return false;
+    // under x-slab decomposition the sweep is skewed along y and every sub-launch does the fused halo step
+    if (a->halo && !halo_fused_ok(a->halo, p)) return false;
     const int L = a->time_M - a->time_m + 1;
-    if (L < 4 || p.n[0] < 8 * p.radius[0]) return false;
+    const int dim = a->halo ? 1 : 0;
+    if (L < 4 || p.n[dim] < 8 * p.radius[dim]) return false;
     return forced || u.nbytes >= ((size_t)1 << 30);
 }
 
+// `dim` = the axis the sweep is cut and skewed along: 0 (x; chunks are contiguous plane blocks) on a single device,
+// 1 (y) under x-slab decomposition — orthogonal to the decomposed axis, so that every rank runs the SAME schedule
+// and each sub-launch is an ordinary fused halo step (peer stores + flag acquire inside the sweep kernel) restricted
+// to its rows. (Skewing along x would make a rank's low edge run ahead of its high edge in time, i.e. ahead of the
+// neighbour it has to exchange with.) Chunks along y are strided: one 2-D copy per time slot and chunk, contiguous
+// pieces of W rows x a2 floats.
 static int iso_forward_streamed(const b2_iso_args *a, IsoPlan &p, FieldGeom g, DevArray &u, DevArray *damp,
-                                DevArray *param, SparseDev &src, SparseDev &rec, float scalar_scale, float dt2) {
+                                DevArray *param, SparseDev &src, SparseDev &rec, float scalar_scale, float dt2,
+                                bool damp_io, bool param_io) {
     int rc;
     StreamedLoop &S = g_streamed;
     if ((rc = S.init())) return rc;
-    const int n = p.n[0], R = p.radius[0], so = p.so, a0 = p.a[0];
+    const bool decomposed = a->halo != nullptr;
+    int dim = decomposed ? 1 : 0;
+    if (!decomposed) if (const char *e = getenv("B2_STREAM_DIM")) dim = atoi(e) == 1 ? 1 : 0;
+    const int n = p.n[dim], R = p.radius[dim], so = p.so, ad = p.a[dim], a0 = p.a[0];
     const int L = a->time_M - a->time_m + 1;
-    const size_t plane = (size_t)p.sx;
+    const size_t plane = (size_t)p.sx, rowlen = (size_t)p.a[2];
     int W = 128;
     if (const char *e = getenv("B2_STREAM_W")) W = atoi(e);
     W = std::max(W, 4 * R);
@@ -237,6 +250,28 @@ static int iso_forward_streamed(const b2_iso_args *a, IsoPlan &p, FieldGeom g, D
     const int K = (n + W - 1) / W;                                   // upload chunks
     const int P = (n + (L - 1) * R + W - 1) / W;                     // phases of the skewed sweep
     cudaStream_t cs = stream();
+    // x planes that travel (dim 1): the halo planes next to a neighbour rank hold ITS data, not the host's
+    const int px0 = (dim == 1 && g.nb_lo) ? so : 0;
+    const int px1 = (dim == 1 && g.nb_hi) ? so + p.n[0] : a0;
+
+    // one chunk [lo, hi) (allocated index along `dim`) of a (slot, x, y, z) or (x, y, z) array, host <-> device
+    auto copy_chunk = [&](float *dev, float *host, size_t slot_off, int lo, int hi, bool to_device, cudaStream_t st) -> int {
+        if (hi <= lo) return B2_OK;
+        if (dim == 0) {
+            const size_t off = slot_off + (size_t)lo * plane, cnt = (size_t)(hi - lo) * plane * sizeof(float);
+            B2_CUDA(cudaMemcpyAsync(to_device ? (void *)(dev + off) : (void *)(host + off),
+                                    to_device ? (const void *)(host + off) : (const void *)(dev + off), cnt,
+                                    to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st), B2_ERR_MEMORY);
+        } else {
+            const size_t off = slot_off + (size_t)px0 * plane + (size_t)lo * rowlen;
+            B2_CUDA(cudaMemcpy2DAsync(to_device ? (void *)(dev + off) : (void *)(host + off), plane * sizeof(float),
+                                      to_device ? (const void *)(host + off) : (const void *)(dev + off),
+                                      plane * sizeof(float), (size_t)(hi - lo) * rowlen * sizeof(float),
+                                      (size_t)(px1 - px0), to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st),
+                    B2_ERR_MEMORY);
+        }
+        return B2_OK;
+    };
 
     // everything the compute stream did so far (sparse tables, traces) precedes the copies
     cudaEvent_t ev_start = S.next();
@@ -244,26 +279,38 @@ static int iso_forward_streamed(const b2_iso_args *a, IsoPlan &p, FieldGeom g, D
     B2_CUDA(cudaStreamWaitEvent(S.up, ev_start, 0), B2_ERR_DEVICE);
     B2_CUDA(cudaStreamWaitEvent(S.down, ev_start, 0), B2_ERR_DEVICE);
 
+    const int t0_first = ((a->time_m % 3) + 3) % 3;
+    if (decomposed) {
+        // the first sub-launch exchanges the initial level's boundary planes through NCCL (like the first step of a
+        // resident call): they must be on the device, all rows, before anything else
+        const int Rx = p.radius[0];
+        const size_t so0 = (size_t)t0_first * p.slot_elems;
+        const int lo_pl[2] = {so, so + p.n[0] - Rx};
+        for (int i = 0; i < 2; ++i) {
+            const size_t off = so0 + (size_t)lo_pl[i] * plane;
+            B2_CUDA(cudaMemcpyAsync((float *)u.d + off, (const float *)u.h + off, (size_t)Rx * plane * sizeof(float),
+                                    cudaMemcpyHostToDevice, S.up), B2_ERR_MEMORY);
+        }
+    }
+
+    if (decomposed) {
+        // ... and exchanged with the neighbours (NCCL, like the first step of a resident call) before the sweep starts
+        cudaEvent_t ev_b = S.next();
+        B2_CUDA(cudaEventRecord(ev_b, S.up), B2_ERR_DEVICE);
+        B2_CUDA(cudaStreamWaitEvent(cs, ev_b, 0), B2_ERR_DEVICE);
+        if ((rc = halo_exchange_initial(a->halo, p, t0_first))) return rc;
+    }
+
     // ---- enqueue every upload now: the copy stream works through them in order ----
     std::vector<cudaEvent_t> up_ev(K);
     std::vector<int> ulo(K), uhi(K);
     for (int c = 0; c < K; ++c) {
         ulo[c] = c == 0 ? 0 : uhi[c - 1];
-        uhi[c] = c == K - 1 ? a0 : std::min(a0, so + std::min(n, (c + 1) * W) + R);
-        const size_t off = (size_t)ulo[c] * plane, cnt = (size_t)(uhi[c] - ulo[c]) * plane * sizeof(float);
-        if (cnt) {
-            for (int t = 0; t < 3; ++t) {
-                const size_t o = (size_t)t * p.slot_elems + off;
-                B2_CUDA(cudaMemcpyAsync((float *)u.d + o, (const float *)u.h + o, cnt, cudaMemcpyHostToDevice, S.up),
-                        B2_ERR_MEMORY);
-            }
-            if (damp && damp->owned)
-                B2_CUDA(cudaMemcpyAsync((float *)damp->d + off, (const float *)damp->h + off, cnt,
-                                        cudaMemcpyHostToDevice, S.up), B2_ERR_MEMORY);
-            if (param && param->owned)
-                B2_CUDA(cudaMemcpyAsync((float *)param->d + off, (const float *)param->h + off, cnt,
-                                        cudaMemcpyHostToDevice, S.up), B2_ERR_MEMORY);
-        }
+        uhi[c] = c == K - 1 ? ad : std::min(ad, so + std::min(n, (c + 1) * W) + R);
+        for (int t = 0; t < 3; ++t)
+            if ((rc = copy_chunk((float *)u.d, (float *)u.h, (size_t)t * p.slot_elems, ulo[c], uhi[c], true, S.up))) return rc;
+        if (damp && damp_io && (rc = copy_chunk((float *)damp->d, (float *)damp->h, 0, ulo[c], uhi[c], true, S.up))) return rc;
+        if (param && param_io && (rc = copy_chunk((float *)param->d, (float *)param->h, 0, ulo[c], uhi[c], true, S.up))) return rc;
         up_ev[c] = S.next();
         B2_CUDA(cudaEventRecord(up_ev[c], S.up), B2_ERR_DEVICE);
     }
@@ -276,62 +323,89 @@ static int iso_forward_streamed(const b2_iso_args *a, IsoPlan &p, FieldGeom g, D
                                     (size_t)(r1 - r0 + 1) * rec.npoint_total * sizeof(float), cs), B2_ERR_MEMORY);
     }
 
-    auto range_geom = [&](int xa, int xb) {
+    auto range_geom = [&](int ra, int rb) {
         FieldGeom q = g;
-        q.lo[0] = xa;
-        q.hi[0] = xb - 1;
-        q.nb_lo = xa > 0;            // an interior cut: the cells beyond it belong to another range
-        q.nb_hi = xb < n;
-        q.restrict_x = true;
+        q.lo[dim] = ra;
+        q.hi[dim] = rb - 1;
+        if (dim == 0) {
+            q.nb_lo = ra > 0;        // an interior cut: the cells beyond it belong to another range
+            q.nb_hi = rb < n;
+            q.restrict_x = true;
+        } else {
+            q.cut_lo1 = ra > 0;
+            q.cut_hi1 = rb < n;
+            q.restrict_y = true;
+        }
         return q;
     };
+    IsoFuse fz;
+    if (decomposed && (rc = halo_fuse_desc(a->halo, p, fz))) return rc;
 
-    int dlo = 0;                                                     // allocated planes already sent back
+    int dlo = 0;                                                     // allocated index (along dim) already sent back
     for (int ph = 0; ph < P; ++ph) {
         if (ph < K) {
             B2_CUDA(cudaStreamWaitEvent(cs, up_ev[ph], 0), B2_ERR_DEVICE);
-            if ((rc = iso_coef_tabulate_planes(p, ulo[ph], uhi[ph]))) return rc;
+            if (dim == 0) rc = iso_coef_tabulate_planes(p, ulo[ph], uhi[ph]);
+            else rc = iso_coef_tabulate_rows(p, 0, a0, ulo[ph], uhi[ph]);
+            if (rc) return rc;
             if (rec.present && !a->rec_toff) {
-                // the initial time level is complete on the planes that just arrived
-                const int xa = std::max(0, ulo[ph] - so), xb = std::min(n, uhi[ph] - so);
-                if (xb > xa) {
-                    const int t0 = ((a->time_m % 3) + 3) % 3;
-                    if ((rc = launch_interp(rec, range_geom(xa, xb), p.u + (size_t)t0 * p.slot_elems, nullptr, a->time_m)))
+                // the initial time level is complete on the chunk that just arrived
+                const int ra = std::max(0, ulo[ph] - so), rb = std::min(n, uhi[ph] - so);
+                if (rb > ra)
+                    if ((rc = launch_interp(rec, range_geom(ra, rb), p.u + (size_t)t0_first * p.slot_elems, nullptr, a->time_m)))
                         return rc;
-                }
             }
         }
         for (int s = 1; s <= L; ++s) {
             const int shift = (s - 1) * R;
-            const int xb = std::min(n, (ph + 1) * W - shift);
-            if (xb <= 0) break;
-            const int xa = std::max(0, ph * W - shift);
-            if (xa >= xb) continue;
+            const int rb = std::min(n, (ph + 1) * W - shift);
+            if (rb <= 0) break;
+            const int ra = std::max(0, ph * W - shift);
+            if (ra >= rb) continue;
             const int time = a->time_m + s - 1;
             const int t0 = ((time % 3) + 3) % 3, t1 = (((time + 1) % 3) + 3) % 3, t2 = (((time - 1) % 3) + 3) % 3;
-            if ((rc = iso_step(p, t0, t2, t1, xa, xb - xa))) return rc;
             float *f1 = p.u + (size_t)t1 * p.slot_elems;
-            const FieldGeom q = range_geom(xa, xb);
+            FieldGeom q = range_geom(ra, rb);
+            if (dim == 0) {
+                if ((rc = iso_step(p, t0, t2, t1, ra, rb - ra))) return rc;
+            } else {
+                IsoPlan pr = p;                                   // the same plan restricted to the rows [ra, rb)
+                pr.o[1] = p.o[1] + ra;
+                pr.n[1] = rb - ra;
+                if (decomposed) {
+                    if ((rc = halo_step_iso_fused(a->halo, pr, t0, t2, t1))) return rc;
+                    q.peer_lo = fz.peer_lo; q.peer_hi = fz.peer_hi;
+                    q.off_lo = (long long)t1 * fz.slot_lo + (long long)(p.o[0] + fz.n_lo) * p.sx;
+                    q.off_hi = (long long)t1 * fz.slot_hi + (long long)(p.o[0] - p.n[0]) * p.sx;
+                    q.nown = p.n[0]; q.pw = p.radius[0];
+                } else if ((rc = iso_step(pr, t0, t2, t1, 0, p.n[0]))) {
+                    return rc;
+                }
+            }
             if ((rc = launch_inject(src, q, f1, nullptr, time, p.param_kind, p.param, scalar_scale, dt2))) return rc;
-            // time level time+1 is now complete on [xa, xb)
+            if (decomposed) {
+                if ((rc = halo_fused_signal(a->halo, p.u))) return rc;
+                // receivers next to a slab boundary sample halo cells of the level just written: the neighbour's
+                // stores of this very sub-launch must have landed
+                if (rec.present && (rc = halo_p2p_wait(a->halo))) return rc;
+            }
+            // time level time+1 is now complete on [ra, rb)
             if (rec.present) {
                 const int row = a->rec_toff ? time : time + 1;
-                if (row <= a->time_M && (rc = launch_interp(rec, q, f1, nullptr, row))) return rc;
+                FieldGeom qi = q;
+                qi.peer_lo = qi.peer_hi = nullptr;
+                if (row <= a->time_M && (rc = launch_interp(rec, qi, f1, nullptr, row))) return rc;
             }
         }
-        // planes left of (ph+1)W - (L-1)R have seen all L steps: send them home while the sweep goes on
-        int dhi = ph == P - 1 ? a0 : std::min(a0, std::max(0, so + (ph + 1) * W - (L - 1) * R));
+        // what lies left of (ph+1)W - (L-1)R has seen all L steps: send it home while the sweep goes on
+        int dhi = ph == P - 1 ? ad : std::min(ad, std::max(0, so + (ph + 1) * W - (L - 1) * R));
         if (ph == P - 1 || dhi - dlo >= W / 2) {
             if (dhi > dlo) {
                 cudaEvent_t e = S.next();
                 B2_CUDA(cudaEventRecord(e, cs), B2_ERR_DEVICE);
                 B2_CUDA(cudaStreamWaitEvent(S.down, e, 0), B2_ERR_DEVICE);
-                const size_t off = (size_t)dlo * plane, cnt = (size_t)(dhi - dlo) * plane * sizeof(float);
-                for (int t = 0; t < 3; ++t) {
-                    const size_t o = (size_t)t * p.slot_elems + off;
-                    B2_CUDA(cudaMemcpyAsync((float *)u.h + o, (const float *)u.d + o, cnt, cudaMemcpyDeviceToHost, S.down),
-                            B2_ERR_MEMORY);
-                }
+                for (int t = 0; t < 3; ++t)
+                    if ((rc = copy_chunk((float *)u.d, (float *)u.h, (size_t)t * p.slot_elems, dlo, dhi, false, S.down))) return rc;
                 dlo = dhi;
             }
         }
@@ -373,6 +447,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     FieldGeom g;
     bool staged_u = false, staged_damp = false, staged_param = false;
     bool u_is_home = false;                       // the streamed loop already brought u back to the host
+    bool u_host_io = false;                       // caller-provided device buffer next to the host array (host_io)
     auto call_t0 = std::chrono::steady_clock::now();
     for (double &v : g_last_profile) v = 0.0;
 
@@ -380,6 +455,11 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         // copy back what the reference would copy back (u and rec), free staged copies
         const auto d2h_t0 = std::chrono::steady_clock::now();
         int r1 = staged_u ? stage_out(u, (code == B2_OK || code == B2_ERR_NAN) && !u_is_home) : B2_OK;
+        if (staged_u && u_host_io && !u_is_home && (code == B2_OK || code == B2_ERR_NAN)) {
+            cudaError_t ce = cudaMemcpyAsync(u.h, u.d, u.nbytes, cudaMemcpyDeviceToHost, stream());
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream());
+            if (ce != cudaSuccess) { set_error("b2_iso_forward: device -> host copy failed"); r1 = B2_ERR_MEMORY; }
+        }
         g_last_profile[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - d2h_t0).count();
         g_last_profile[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - call_t0).count();
         if (staged_damp) stage_out(damp, false);
@@ -409,17 +489,24 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     // A large host-staged wavefield is a candidate for the streamed time loop (copies overlapped with a
     // skewed sweep, iso_forward_streamed): its uploads are then issued chunk by chunk, not here. Whether the
     // call really streams is known once the plan exists; otherwise the deferred copies are issued below.
+    // host_io: the caller passed BOTH a host array and its own device buffer for u (and possibly damp / the
+    // parameter array): the call moves data -> dmap before and dmap -> data after the loop (streamed when
+    // possible). Under x-slab decomposition this is how a host-staged apply keeps using the CUDA-IPC registered
+    // device allocations of the peer-memory halo path.
+    const bool host_io = a->host_io && a->u->dmap && a->u->data;
     const bool maybe_stream = [&] {
         const char *e = getenv("B2_STREAM");
         if (e && atoi(e) == 0) return false;
-        if (nd != 3 || a->u->dmap || !a->u->data || !a->damp) return false;
-        if (a->halo || a->adjoint || a->free_surface || a->ot4 || a->born_U || a->born_dm || a->snap || a->grad || a->usave)
+        if (nd != 3 || !a->u->data || !a->damp) return false;
+        if (a->u->dmap && !host_io) return false;
+        if (a->adjoint || a->free_surface || a->ot4 || a->born_U || a->born_dm || a->snap || a->grad || a->usave)
             return false;
         return true;
     }();
     call_t0 = std::chrono::steady_clock::now();
     if ((rc = stage_in(a->u, nd + 1, u, !maybe_stream))) return cleanup(rc);
     staged_u = true;
+    u_host_io = host_io;
     if (a->damp) {
         if ((rc = stage_in(a->damp, nd, damp, !maybe_stream))) return cleanup(rc);
         staged_damp = true;
@@ -553,14 +640,16 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
         set_error("b2_iso_forward: OT4 is not combined with a free surface or the imaging condition in this version");
         return cleanup(B2_ERR_INVALID);
     }
-    p.defer_coef = maybe_stream;
+    p.defer_coef = maybe_stream || host_io;       // the arrays are not on the device yet
     if ((rc = iso_plan_init(p, a->kernel))) return cleanup(rc);
-    const bool streamed = maybe_stream && streamed_wanted(a, p, u);
-    if (maybe_stream && !streamed) {
+    const bool damp_io = staged_damp && (damp.owned || (host_io && a->damp->dmap && a->damp->data));
+    const bool param_io = staged_param && (param.owned || (host_io && a->param->dmap && a->param->data));
+    const bool streamed = maybe_stream && streamed_wanted(a, p, u, host_io);
+    if ((maybe_stream || host_io) && !streamed) {
         // not streaming after all: the classic order — whole arrays in, tabulate, loop, whole arrays out
-        DevArray *arrs[3] = {&u, staged_damp ? &damp : nullptr, staged_param ? &param : nullptr};
+        DevArray *arrs[3] = {&u, damp_io ? &damp : nullptr, param_io ? &param : nullptr};
         for (DevArray *x : arrs)
-            if (x && x->owned)
+            if (x && (x->owned || host_io))
                 if (cudaMemcpyAsync(x->d, x->h, x->nbytes, cudaMemcpyHostToDevice, stream()) != cudaSuccess) {
                     set_error("b2_iso_forward: host -> device copy failed");
                     return cleanup(B2_ERR_MEMORY);
@@ -626,7 +715,7 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
     pe_loop0 = se.next();
     if (streamed) {
         if ((rc = iso_forward_streamed(a, p, g, u, staged_damp ? &damp : nullptr, staged_param ? &param : nullptr, src, rec,
-                                       scalar_scale, dt2)))
+                                       scalar_scale, dt2, damp_io, param_io)))
             return cleanup(rc);
         u_is_home = true;
         g_last_profile[4] = 1.0;

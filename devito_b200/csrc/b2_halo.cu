@@ -268,6 +268,20 @@ int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int 
     return iso_step_fused(p, t0, t2, t1, f);
 }
 
+// Exchange the boundary planes of time slot `t0` through NCCL (blocking the main stream) and mark the field as
+// primed: what the first step of a call does, as a separate step for the streamed loop.
+int halo_exchange_initial(b2_halo_ctx *ctx, const IsoPlan &p, int t0) {
+    cudaStream_t main = stream();
+    B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
+    B2_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0), B2_ERR_COMM);
+    int rc = halo_enqueue(ctx, p.u + (size_t)t0 * p.slot_elems, (size_t)p.sx, p.o[0], p.n[0], p.radius[0]);
+    if (rc) return rc;
+    B2_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream), B2_ERR_COMM);
+    B2_CUDA(cudaStreamWaitEvent(main, ctx->ev_comm, 0), B2_ERR_COMM);
+    ctx->set_primed(p.u);
+    return B2_OK;
+}
+
 int halo_fused_signal(b2_halo_ctx *ctx, const void *field) {
     int rc = p2p_signal(ctx);
     if (rc) return rc;

@@ -66,6 +66,7 @@ int halo_fuse_desc(b2_halo_ctx *ctx, const IsoPlan &p, IsoFuse &f);
 int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int t1);
 int halo_fused_signal(b2_halo_ctx *ctx, const void *field);
 int halo_width_iso(const IsoPlan &p);
+int halo_exchange_initial(b2_halo_ctx *ctx, const IsoPlan &p, int t0);
 
 // Same for the coupled TTI fields: u and v boundary planes travel in one NCCL group.
 int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t2, int t1);

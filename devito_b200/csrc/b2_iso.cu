@@ -771,6 +771,41 @@ static int coef_buffer(int which, size_t elems, float **out) {
     return B2_OK;
 }
 
+// rows [y0, y1) of the planes [x0, x1) (allocated indices): the y-skewed streamed loop tabulates row blocks
+__global__ void __launch_bounds__(256)
+k_iso_coef_rows(const float *__restrict__ damp, const float *__restrict__ param, int param_kind, float m_dt2_scalar,
+                float inv_dt, float inv_dt2, float *__restrict__ A, float *__restrict__ B, long long sx, int a2,
+                int x0, int y0, int ny) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= a2) return;
+    const int x = x0 + blockIdx.z;
+    for (int y = y0 + blockIdx.y; y < y0 + ny; y += gridDim.y) {
+        const size_t i = (size_t)x * (size_t)sx + (size_t)y * a2 + z;
+        float md = m_dt2_scalar;
+        if (param_kind == B2_PARAM_VP) {
+            const float v = param[i];
+            md = inv_dt2 / (v * v);
+        } else if (param_kind == B2_PARAM_M) {
+            md = param[i] * inv_dt2;
+        }
+        const float a = 1.0f / (md + damp[i] * inv_dt);
+        A[i] = a;
+        if (B) B[i] = md * a;
+    }
+}
+
+int iso_coef_tabulate_rows(const IsoPlan &p, int x0, int x1, int y0, int y1) {
+    if (x1 <= x0 || y1 <= y0) return B2_OK;
+    const float inv_dt = 1.0f / p.dt, inv_dt2 = 1.0f / (p.dt * p.dt);
+    const float md = (1.0f / (p.vp * p.vp)) * inv_dt2;
+    dim3 block(256, 1, 1), grid((p.a[2] + 255) / 256, (unsigned)std::min(y1 - y0, 1024), (unsigned)(x1 - x0));
+    k_iso_coef_rows<<<grid, block, 0, stream()>>>(p.damp, p.param, p.param_kind, md, inv_dt, inv_dt2, p.coefA, p.coefB,
+                                                  p.sx, p.a[2], x0, y0, y1 - y0);
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
 // tabulate the allocated x-planes [plane_lo, plane_hi) (the streamed time loop does it chunk by chunk, as
 // the damping / parameter planes arrive from the host)
 int iso_coef_tabulate_planes(const IsoPlan &p, int plane_lo, int plane_hi) {

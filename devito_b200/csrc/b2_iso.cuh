@@ -49,6 +49,7 @@ int iso_plan_init(IsoPlan &p, int kernel);
 
 // (Re)tabulate the coefficient tables on the allocated x-planes [plane_lo, plane_hi).
 int iso_coef_tabulate_planes(const IsoPlan &p, int plane_lo, int plane_hi);
+int iso_coef_tabulate_rows(const IsoPlan &p, int x0, int x1, int y0, int y1);
 
 // One time step over x in [xlo, xlo + xcount) (relative to the iteration origin):
 // u[slot1] = update(u[slot0], u[slotm]).

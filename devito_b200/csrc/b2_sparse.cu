@@ -26,6 +26,7 @@ struct SparseK {
     int so;
     int lo0, lo1, lo2, hi0, hi1, hi2;
     int ext_lo0, ext_hi0;     // how far beyond [lo0, hi0] the support may reach (r, or 0 next to a neighbour)
+    int ext_lo1, ext_hi1;     // same for dim 1 (r, or 0 at an interior cut of a y-skewed streamed sweep)
     // fused halo step (FieldGeom): mirror injected boundary cells into the neighbours' halos
     float *peer_lo, *peer_hi;
     long long off_lo, off_hi;
@@ -54,7 +55,7 @@ __device__ __forceinline__ bool sparse_cell(const SparseK &k, int p, int c, long
         c2 = g[1] + r2 - k.r + 1;
         w = k.w1[(long long)p * n + r1] * k.w2[(long long)p * n + r2];
     }
-    if (c1 < k.lo1 - k.r || c1 > k.hi1 + k.r) return false;
+    if (c1 < k.lo1 - k.ext_lo1 || c1 > k.hi1 + k.ext_hi1) return false;
     if (c2 < k.lo2 - k.r || c2 > k.hi2 + k.r) return false;
     const int s0 = (k.ndim == 3) ? k.so : 0;
     idx = (long long)(c0 + s0) * k.sx + (long long)(c1 + k.so) * k.sy + (c2 + k.so);
@@ -129,6 +130,8 @@ static SparseK make_k(const SparseDev &s, const FieldGeom &g, bool injecting) {
     SparseK k;
     k.ext_lo0 = ((injecting || g.restrict_x) && g.nb_lo) ? 0 : s.r;
     k.ext_hi0 = ((injecting || g.restrict_x) && g.nb_hi) ? 0 : s.r;
+    k.ext_lo1 = (g.restrict_y && g.cut_lo1) ? 0 : s.r;
+    k.ext_hi1 = (g.restrict_y && g.cut_hi1) ? 0 : s.r;
     k.peer_lo = injecting ? g.peer_lo : nullptr;
     k.peer_hi = injecting ? g.peer_hi : nullptr;
     k.off_lo = g.off_lo; k.off_hi = g.off_hi;
@@ -217,7 +220,7 @@ int launch_interp(const SparseDev &s, const FieldGeom &g, const float *f0, const
     SparseK k = make_k(s, g, false);
     const int warps = k.p_cnt;
     const int blocks = (warps * 32 + 127) / 128;
-    k_interp<<<blocks, 128, 0, stream()>>>(k, f0, f1, (float *)s.data.d, time, g.restrict_x ? 1 : 0);
+    k_interp<<<blocks, 128, 0, stream()>>>(k, f0, f1, (float *)s.data.d, time, (g.restrict_x || g.restrict_y) ? 1 : 0);
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
     return B2_OK;

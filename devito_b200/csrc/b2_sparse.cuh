@@ -28,6 +28,9 @@ struct FieldGeom {
     // streamed time loop (b2_api_iso.cu): [lo[0], hi[0]] is one x-range of a skewed sweep; interpolation then
     // samples only the cells of that range and ADDS its partial sum to the trace
     bool restrict_x = false;
+    // ... or a range of dim 1 (the streamed loop under x-slab decomposition skews along y): [lo[1], hi[1]] is the
+    // range, cut_lo1 / cut_hi1 say whether its ends are interior cuts (no reach beyond them)
+    bool restrict_y = false, cut_lo1 = false, cut_hi1 = false;
     // fused halo step: cells injected into the first / last `pw` owned planes are mirrored into the
     // neighbour's halo copy (the sweep kernel stored those planes there before the injection)
     float *peer_lo = nullptr, *peer_hi = nullptr;

@@ -1347,7 +1347,7 @@ class Operator:
         out[inner] = src
         return np.ascontiguousarray(out)
 
-    def _field_obj(self, fn, dev, resident, hold, so=None, written=False):
+    def _field_obj(self, fn, dev, resident, hold, so=None, written=False, host_io_ok=False):
         """b2_dataobj for a dense function: resident (dmap set) or host-staged."""
         import torch
         fo = getattr(fn, '_foreign_obj', None)
@@ -1385,7 +1385,21 @@ class Operator:
                 st.mark_device_written()
         else:
             host = st.host if written else st.host_ro
-            ob = L_.make_dataobj(host=host, halo=fn.halo)
+            dist_ = fn.grid.distributor if fn.grid is not None else None
+            if (host_io_ok and dist_ is not None and dist_.is_parallel and distributed.p2p_enabled()
+                    and (getattr(fn, 'is_buffered', False) or not getattr(fn, 'is_TimeFunction', False))):
+                # host-staged apply under decomposition: the library moves host <-> device itself (host_io), through
+                # a device buffer that stays registered with the neighbour ranks (peer-memory halo path)
+                import torch
+                if getattr(fn, 'is_TimeFunction', False):
+                    st.raw = True
+                t = st.device_scratch(torch.device('cuda', dev))
+                if getattr(fn, 'is_TimeFunction', False) and not st.p2p_registered:
+                    distributed.register_field(st, fn.grid, dev)
+                ob = L_.make_dataobj(host=host, dev_ptr=t.data_ptr(), halo=fn.halo)
+                self._host_io = True
+            else:
+                ob = L_.make_dataobj(host=host, halo=fn.halo)
         hold.append(ob)
         return ob
 
@@ -1540,10 +1554,13 @@ class Operator:
         a.radius = p['R']
         a.w = self._w_arrays(p['w'], hold)
         u = args['fields'][0]
-        a.u = self._field_obj(u, dev, res, hold, written=True).ptr
-        a.damp = self._field_obj(args['damp'], dev, res, hold, so=p['so']).ptr if args['damp'] is not None else None
+        self._host_io = False
+        a.u = self._field_obj(u, dev, res, hold, written=True, host_io_ok=True).ptr
+        a.damp = (self._field_obj(args['damp'], dev, res, hold, so=p['so'], host_io_ok=True).ptr
+                  if args['damp'] is not None else None)
         a.param_kind = args['param_kind']
-        a.param = self._field_obj(args['param'], dev, res, hold, so=p['so']).ptr if args['param'] is not None else None
+        a.param = (self._field_obj(args['param'], dev, res, hold, so=p['so'], host_io_ok=True).ptr
+                   if args['param'] is not None else None)
         a.vp = args['vp']
         a.dt = args['dt']
         lo, hi = args['lo'], args['hi']
@@ -1581,6 +1598,7 @@ class Operator:
             # injection used a literal dt**2 (not the `dt` symbol): it must agree with runtime dt
             if abs(p['inject_dt2'] - a.dt * a.dt) > 1e-5 * p['inject_dt2']:
                 raise InvalidArgument("literal dt in the injected expression differs from runtime dt")
+        a.host_io = 1 if self._host_io else 0
         t0 = _time.perf_counter()
         rc = L.b2_iso_forward(ctypes.byref(a))
         t_wall = _time.perf_counter() - t0

@@ -472,6 +472,27 @@ class FieldStorage:
             self.dev_valid = True
         return self.dev
 
+    def device_scratch(self, device):
+        """A device buffer of this array's size WITHOUT uploading: staging space for a host-staged apply that moves
+        the data itself (b2_iso_args.host_io). Raw (cudaMalloc) when `self.raw`, so that it can be CUDA-IPC
+        registered with the neighbour ranks; kept across calls."""
+        import torch
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        if self.raw:
+            if not isinstance(self.dev, RawDeviceBuffer):
+                if self.dev is not None and not self.host_valid:
+                    self.sync_to_host()
+                self.dev = RawDeviceBuffer(nbytes, device.index)
+                self.p2p_registered = False
+        elif self.dev is None or getattr(self.dev, 'device', None) != device:
+            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
+                   np.dtype(np.float64): torch.float64}[self.dtype]
+            if self.dev is not None and not self.host_valid:
+                self.sync_to_host()
+            self.dev = torch.empty(self.shape, dtype=tdt, device=device)
+        self.dev_valid = False
+        return self.dev
+
     def mark_device_written(self):
         self.dev_valid = True
         self.host_valid = False

@@ -152,6 +152,11 @@ struct b2_iso_args {
     struct b2_dataobj *snap;
     int snap_factor;
     int snap_toff;
+    /* != 0: `u` (and `damp` / `param` when they carry both pointers) come with a host array `data` AND the caller's
+     * own device buffer `dmap`: the call copies data -> dmap before and dmap -> data (u only) after the time loop —
+     * overlapped with a skewed sweep when the grid is large (streamed loop). Under x-slab decomposition this lets a
+     * host-staged apply use the CUDA-IPC registered device allocations of the peer-memory halo path.          */
+    int host_io;
 };
 int b2_iso_forward(const struct b2_iso_args *a);
 

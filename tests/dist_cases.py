@@ -28,6 +28,21 @@ def run_case(kind, nranks, topology=None):
         if kind == 'tti':
             res['v'] = out[2].data
         return res, model
+    if kind == 'stream':                                   # host-staged apply: streamed loop, skewed along y when decomposed
+        import os
+        model = demo_model('constant-isotropic', **kw)
+        solver = AcousticWaveSolver(model, setup_geometry(model, TN, interpolation='sinc'), space_order=SO)
+        if topology is not None:
+            os.environ['B2_STREAM'], os.environ['B2_STREAM_W'] = '2', '16'
+            rec, u, _ = solver.forward(resident=False)
+            import ctypes
+            from devito_b200 import _lib
+            prof = (ctypes.c_double * 5)()
+            _lib.lib().b2_last_call_profile(prof)
+            assert prof[4] == 1.0, "the decomposed host-staged apply did not stream"
+        else:
+            rec, u, _ = solver.forward()
+        return {'rec': rec.data, 'u': u.data}, model
     if kind == 'fs':                                       # free surface + layered velocity
         model = demo_model('layers-isotropic', fs=True, nlayers=3, **kw)
         rec, u, _ = AcousticWaveSolver(model, setup_geometry(model, TN), space_order=SO).forward()
@@ -72,4 +87,4 @@ def run_case(kind, nranks, topology=None):
     raise ValueError(kind)
 
 
-TOL = {'iso': 1e-5, 'tti': 1e-4, 'fs': 1e-5, 'ot4': 1e-5, 'born': 1e-4, 'grad': 1e-4, 'snap': 1e-5}
+TOL = {'stream': 1e-5, 'iso': 1e-5, 'tti': 1e-4, 'fs': 1e-5, 'ot4': 1e-5, 'born': 1e-4, 'grad': 1e-4, 'snap': 1e-5}

@@ -148,8 +148,9 @@ def _last_call_streamed():
     return prof[4] == 1.0
 
 
+@pytest.mark.parametrize('dim', [0, 1])
 @pytest.mark.parametrize('interp,so,W', [('linear', 8, 16), ('sinc', 8, 24), ('linear', 4, 16)])
-def test_streamed_time_loop_equals_resident_call(interp, so, W, monkeypatch):
+def test_streamed_time_loop_equals_resident_call(interp, so, W, dim, monkeypatch):
     """Host-staged applies of large grids run the streamed time loop (uploads / downloads overlapped with a
     skewed sweep, b2_api_iso.cu::iso_forward_streamed). Forced here on a small grid with narrow chunks
     (several x-ranges cut through the source and receiver supports): the wavefield must be bit-identical to
@@ -159,6 +160,7 @@ def test_streamed_time_loop_equals_resident_call(interp, so, W, monkeypatch):
     assert not _last_call_streamed()
     monkeypatch.setenv('B2_STREAM', '2')
     monkeypatch.setenv('B2_STREAM_W', str(W))
+    monkeypatch.setenv('B2_STREAM_DIM', str(dim))          # 0: skewed along x (single device), 1: along y (decomposed runs)
     rec2, u2, _ = solver.forward(resident=False)
     assert _last_call_streamed()
     assert np.array_equal(np.asarray(u1.data_with_halo), np.asarray(u2.data_with_halo))
