@@ -400,8 +400,9 @@ class Bench:
         return {"value": w['pts_step'] * steps / t / 1e9, "unit": "GPts/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": t / steps * 1e3,
-                "mode": ("streamed: x-chunks uploaded / downloaded on copy streams while a skewed sweep time-steps the "
-                         "chunks already on the device" if streamed else
+                "mode": (("streamed: chunks (x planes on one GPU, y rows under x-slab decomposition) uploaded / downloaded on "
+                          "copy streams while a skewed sweep time-steps the chunks already on the device"
+                          + ("; every sub-launch is a fused halo step" if self.nranks > 1 else "")) if streamed else
                          "serial: host->device, time loop, device->host on one stream"),
                 "last_call_ms": {"before_loop": prof[0], "time_loop": prof[1], "after_loop": prof[2], "call": prof[3]},
                 "pinned_host": bool(getattr(u.storage, '_pinned', None) is not None),
