@@ -795,6 +795,11 @@ extern "C" int b2_iso_forward(const struct b2_iso_args *a) {
             }
         }
         if (per_step_events) se.next();
+        if (a->halo && !p2p && a->rec_toff && rec.present) {
+            // NCCL path: receivers that sample the level just written may reach into the halo, which is only
+            // exchanged at the start of the next step -- exchange it now (the peer paths wait on the flags instead)
+            if ((rc = halo_exchange_slot(a->halo, born ? pU : p, t1))) return cleanup(rc);
+        }
         const float *fr = (born ? pU.u : p.u) + (size_t)(a->rec_toff ? t1 : t0) * p.slot_elems;
         if ((rc = launch_interp(rec, g, fr, nullptr, time))) return cleanup(rc);
         if (staged_grad) {

@@ -271,6 +271,14 @@ int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int 
 // Exchange the boundary planes of time slot `t0` through NCCL (blocking the main stream) and mark the field as
 // primed: what the first step of a call does, as a separate step for the streamed loop.
 int halo_exchange_initial(b2_halo_ctx *ctx, const IsoPlan &p, int t0) {
+    int rc = halo_exchange_slot(ctx, p, t0);
+    if (rc) return rc;
+    ctx->set_primed(p.u);
+    return B2_OK;
+}
+
+// Blocking (w.r.t. the main stream) NCCL exchange of one time slot's boundary planes.
+int halo_exchange_slot(b2_halo_ctx *ctx, const IsoPlan &p, int t0) {
     cudaStream_t main = stream();
     B2_CUDA(cudaEventRecord(ctx->ev_ready, main), B2_ERR_COMM);
     B2_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0), B2_ERR_COMM);
@@ -278,7 +286,6 @@ int halo_exchange_initial(b2_halo_ctx *ctx, const IsoPlan &p, int t0) {
     if (rc) return rc;
     B2_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream), B2_ERR_COMM);
     B2_CUDA(cudaStreamWaitEvent(main, ctx->ev_comm, 0), B2_ERR_COMM);
-    ctx->set_primed(p.u);
     return B2_OK;
 }
 

@@ -67,6 +67,7 @@ int halo_step_iso_fused(b2_halo_ctx *ctx, const IsoPlan &p, int t0, int t2, int 
 int halo_fused_signal(b2_halo_ctx *ctx, const void *field);
 int halo_width_iso(const IsoPlan &p);
 int halo_exchange_initial(b2_halo_ctx *ctx, const IsoPlan &p, int t0);
+int halo_exchange_slot(b2_halo_ctx *ctx, const IsoPlan &p, int slot);
 
 // Same for the coupled TTI fields: u and v boundary planes travel in one NCCL group.
 int halo_exchange_and_step_tti(b2_halo_ctx *ctx, const TtiPlan &p, int t0, int t2, int t1);

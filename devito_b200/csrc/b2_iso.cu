@@ -406,31 +406,39 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
 //     what made the first "taller tile" experiment of round 1 miss the instruction cache);
 //   * y/x taps and the update in packed fp32x2 arithmetic.
 // Halo step under decomposition: identical to k_iso_tma (peer stores, flag acquire, chunk 0 backwards).
-template <int R, int TY, int TZ4>
+template <int R, int TY, int TZ4, int PF = 2, int NT = 2>
 struct IsoTma2Cfg {
     static constexpr int RZ = ceil4(R);
     static constexpr int TZ = 4 * TZ4;
     static constexpr int BY = TY + 2 * R;
     static constexpr int BZ = TZ + 2 * RZ;
-    static constexpr int NU = 2 * R + 1;
+    // PF == 0: u[t-1] and the coefficient tiles travel by TMA with the planes (like k_iso_tma): the plane ring is
+    // R+1 live planes + 4 of prefetch, the tile ring 5 stages
+    static constexpr int NU = PF == 0 ? R + 5 : 2 * R + 1;
+    static constexpr int NS = PF == 0 ? 5 : 0;
     static constexpr int PLANE = align32f(BY * BZ);
+    static constexpr int TILE = TY * TZ;
     static constexpr int NCT = (TY / 2) * TZ4;          // consumer threads
     static constexpr int NCW = NCT / 32;
-    static constexpr size_t SMEM = (size_t)(NU * PLANE) * 4 + 2 * NU * 8 + 128;
+    static constexpr size_t SMEM = (size_t)(NU * PLANE + NS * NT * TILE) * 4 + 2 * NU * 8 + 128;
 };
 
 template <int R, int TY, int TZ4, int PK, int PF>
 __global__ void __launch_bounds__((TY / 2) * TZ4 + 32, 1)
-k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
-    using C = IsoTma2Cfg<R, TY, TZ4>;
+k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUtensorMap tm_uc,
+           const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const IsoTK<R> k) {
+    constexpr int NT = PK != B2_PARAM_SCALAR ? 3 : 2;
+    using C = IsoTma2Cfg<R, TY, TZ4, PF, NT>;
     using b2ptx::F4;
     constexpr int RZ = C::RZ, TZ = C::TZ, BZ = C::BZ, NU = C::NU, PLANE = C::PLANE, NCW = C::NCW;
+    constexpr int NS = C::NS, TILE = C::TILE;
     static_assert(TY % 2 == 0 && C::NCT % 32 == 0, "two rows per thread, whole warps");
     static_assert(R % 2 == 0, "the prefetch buffers alternate with the parity of the unrolled iteration");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_u = reinterpret_cast<float *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_u + NU * PLANE);
+    float *s_t = s_u + NU * PLANE;                       // tile ring (PF == 0): [stage][prev, A, (B)][TILE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_t + NS * NT * TILE);
     uint64_t *empty = full + NU;
 
     int b = blockIdx.x;
@@ -460,7 +468,7 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
     if (warp == NCW) {
         if (lane == 0) {
             b2ptx::tma_prefetch_desc(&tm_uh);
-            int slot = 0, round = 0;
+            int slot = 0, round = 0, ss = 0;
             bool need_lo = k.want >= 0 && k.flag_lo != nullptr, need_hi = k.want >= 0 && k.flag_hi != nullptr;
             for (int j = 0; j < NP; ++j) {
                 if (round > 0) b2ptx::mbar_wait(&empty[slot], (round - 1) & 1);
@@ -475,9 +483,20 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
                     b2ptx::fence_proxy_async_global();
                     need_hi = false;
                 }
-                b2ptx::mbar_arrive_expect_tx(&full[slot], (uint32_t)(C::BY * BZ * 4));
+                const bool tiles = PF == 0 && j >= 2 * R;
+                b2ptx::mbar_arrive_expect_tx(&full[slot], (uint32_t)(C::BY * BZ * 4) + (tiles ? (uint32_t)(TILE * 4 * NT) : 0u));
                 b2ptx::tma_load_4d(s_u + slot * PLANE, &tm_uh, &full[slot], k.oz + z0 - RZ, k.oy + y0 - R,
                                    k.ox + xj, k.slot0);
+                if (tiles) {
+                    // the tiles of the output plane of iteration j travel with plane j
+                    const int xo = xj - dx * R;
+                    float *t = s_t + ss * NT * TILE;
+                    b2ptx::tma_load_4d(t, &tm_uc, &full[slot], k.oz + z0, k.oy + y0, k.ox + xo, k.slotm);
+                    b2ptx::tma_load_3d(t + TILE, &tm_a, &full[slot], k.oz + z0, k.oy + y0, k.ox + xo);
+                    if (PK != B2_PARAM_SCALAR)
+                        b2ptx::tma_load_3d(t + 2 * TILE, &tm_b, &full[slot], k.oz + z0, k.oy + y0, k.ox + xo);
+                    if (++ss == NS) ss = 0;
+                }
                 if (++slot == NU) { slot = 0; ++round; }
             }
         }
@@ -508,11 +527,14 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
         for (int i = 0; i < R; ++i) { fut[r][i] = b2ptx::f4zero(); pst[r][i] = b2ptx::f4zero(); }
     }
     // u[t-1], A (and B) of the output plane of iteration j, loaded two iterations ahead
-    float4 pv[2][PF], pa[2][PF], pb[2][PF];
+    constexpr int PFB = PF > 0 ? PF : 1;
+    float4 pv[2][PFB], pa[2][PFB], pb[2][PFB];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int d = 0; d < PF; ++d) { pv[r][d] = pa[r][d] = pb[r][d] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int d = 0; d < PFB; ++d) { pv[r][d] = pa[r][d] = pb[r][d] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    int ts_off = 0;                                       // tile-ring stage of the current output plane (PF == 0)
+    const int tcol = (2 * tr) * TZ + 4 * tz4;
     auto prefetch = [&](int j, int d) {
         // output plane of iteration j: x = xb + dx * (j - R), valid for 2R <= j < NP
         if (j < 2 * R || j >= NP) return;
@@ -526,7 +548,7 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
             }
         }
     };
-    prefetch(2 * R, 0);
+    if (PF >= 1) prefetch(2 * R, 0);
     if (PF == 2) prefetch(2 * R + 1, PF - 1);
 
     int st_new = 0, st_cen = 0;           // shared-memory stage of plane j and of the centre plane j - R
@@ -612,6 +634,17 @@ k_iso_tma2(const __grid_constant__ CUtensorMap tm_uh, const IsoTK<R> k) {
                 // compiler select/copy right after the load, i.e. wait for it — the first version stalled on exactly that
                 const int d = PF == 2 ? (p & 1) : 0;
                 const long long g = gbase + (long long)j * osx;
+                if (PF == 0) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const float *t = s_t + ts_off + tcol + r * TZ;
+                        pv[r][0] = b2ptx::lds128(t);
+                        pa[r][0] = b2ptx::lds128(t + TILE);
+                        if (PK != B2_PARAM_SCALAR) pb[r][0] = b2ptx::lds128(t + 2 * TILE);
+                    }
+                    ts_off += NT * TILE;
+                    if (ts_off == NS * NT * TILE) ts_off = 0;
+                }
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const F4 c = cen[r];
@@ -841,7 +874,16 @@ static int plan_tma(IsoPlan &p) {
     if (p.v2) {
         using T2 = Tile2Of<R>;
         using T2b = Tile2bOf<R>;
-        return make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T2::TZ4 + 2 * RZ, (p.v2 == 3 ? T2b::TY : T2::TY) + 2 * R);
+        if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T2::TZ4 + 2 * RZ, (p.v2 == 3 ? T2b::TY : T2::TY) + 2 * R))) return rc;
+        // variant 4: u[t-1] and the coefficient tiles by TMA (28 x 64 tiles)
+        if ((rc = make_tmap(&p.tm_uc, p.u, 4, dims4, 4 * T2::TZ4, T2::TY))) return rc;
+        if ((rc = make_tmap(&p.tm_damp, p.coefA, 3, dims3, 4 * T2::TZ4, T2::TY))) return rc;
+        if (p.param_kind != B2_PARAM_SCALAR) {
+            if ((rc = make_tmap(&p.tm_par, p.coefB, 3, dims3, 4 * T2::TZ4, T2::TY))) return rc;
+        } else {
+            p.tm_par = p.tm_damp;
+        }
+        return B2_OK;
     }
     if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T::TZ4 + 2 * RZ, T::TY + 2 * R))) return rc;
     if ((rc = make_tmap(&p.tm_uc, p.u, 4, dims4, 4 * T::TZ4, T::TY))) return rc;
@@ -917,6 +959,9 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
                                          (int)C2::SMEM), B2_ERR_LAUNCH);
             B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2b::TY, T2b::TZ4, PK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C2b::SMEM), B2_ERR_LAUNCH);
+            using C2t = IsoTma2Cfg<R, T2::TY, T2::TZ4, 0, (PK != B2_PARAM_SCALAR ? 3 : 2)>;
+            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C2t::SMEM), B2_ERR_LAUNCH);
         }
         attr_set = true;
     }
@@ -986,9 +1031,12 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     if constexpr (T2::on) {
         using T2b = Tile2bOf<R>;
         using C2b = IsoTma2Cfg<R, T2b::TY, T2b::TZ4>;
-        if (v2 == 1) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 2><<<grid, (T2::TY / 2) * T2::TZ4 + 32, C2::SMEM, stream()>>>(p.tm_uh, k);
-        if (v2 == 2) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 1><<<grid, (T2::TY / 2) * T2::TZ4 + 32, C2::SMEM, stream()>>>(p.tm_uh, k);
-        if (v2 == 3) k_iso_tma2<R, T2b::TY, T2b::TZ4, PK, 1><<<grid, (T2b::TY / 2) * T2b::TZ4 + 32, C2b::SMEM, stream()>>>(p.tm_uh, k);
+        using C2t = IsoTma2Cfg<R, T2::TY, T2::TZ4, 0, (PK != B2_PARAM_SCALAR ? 3 : 2)>;
+        const unsigned nth = (T2::TY / 2) * T2::TZ4 + 32;
+        if (v2 == 1) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 2><<<grid, nth, C2::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
+        if (v2 == 2) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 1><<<grid, nth, C2::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
+        if (v2 == 3) k_iso_tma2<R, T2b::TY, T2b::TZ4, PK, 1><<<grid, (T2b::TY / 2) * T2b::TZ4 + 32, C2b::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
+        if (v2 == 4) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 0><<<grid, nth, C2t::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
         launched = v2 != 0;
     }
     if (!launched)
