@@ -82,7 +82,7 @@ def test_four_gpu_halo_exchange_matches_single_gpu(kind, tol, path, env):
 
 # the schemes that ride on the isotropic update: free surface (copy path: the surface rows are redone after the
 # sweep), OT4 (halo of 2*radius planes), Born (two wavefields), gradient (adjoint + imaging), snapshots
-_SCHEMES = [('stream', {}), ('fs', {}), ('ot4', {}), ('born', {}), ('grad', {}), ('snap', {}), ('ot4', {'B2_HALO': 'nccl'}),
+_SCHEMES = [('iso12', {}), ('stream', {}), ('fs', {}), ('ot4', {}), ('born', {}), ('grad', {}), ('snap', {}), ('ot4', {'B2_HALO': 'nccl'}),
             ('born', {'B2_HALO': 'nccl'}), ('fs', {'B2_HALO': 'nccl'})]
 
 

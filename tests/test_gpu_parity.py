@@ -202,8 +202,7 @@ def test_so12_two_row_kernel_matches_the_one_row_kernel(preset, n, monkeypatch):
     model = demo_model(preset, spacing=(10., 10., 10.), shape=(n, n, n - 2), nbl=nbl, space_order=so, **kw)
     geometry = setup_geometry(model, tn)
     solver = AcousticWaveSolver(model, geometry, space_order=so)
-    monkeypatch.setenv('B2_ISO_V2', '1')
-    rec2, u2, _ = solver.forward()                         # the two-row kernel
+    rec2, u2, _ = solver.forward()                         # default at so=12: the two-row kernel (variant 4)
     monkeypatch.setenv('B2_ISO_V2', '0')
     solver1 = AcousticWaveSolver(model, geometry, space_order=so)
     rec1, u1, _ = solver1.forward()
