@@ -398,9 +398,11 @@ k_iso_tma(const __grid_constant__ CUtensorMap tm_uh, const __grid_constant__ CUt
 // float4 of output. Here
 //   * a thread owns rows 2*tr and 2*tr+1: the 2R rows around them are loaded ONCE for both (7 LDS.128 per
 //     output float4 instead of 12), each own row is the other's nearest y neighbour (registers);
-//   * u[t-1] and the coefficient tables do not go through shared memory at all (coalesced LDG.128,
-//     prefetched two planes ahead into registers), which frees the room for a 32x64 tile — halo
-//     re-reads 1.72x instead of 2.19x;
+//   * the tile is 28 x 64 (halo re-reads 1.79x instead of 2.19x): the plane ring holds R+1 live planes + 4 of
+//     prefetch instead of 2R+1, u[t-1] and the coefficient tiles travel by TMA in a 5-stage tile ring (PF = 0,
+//     the default: 3.08 ms at 1024^3 vs 3.20 ms for k_iso_tma). The first version read them straight from global
+//     memory (LDG.128 prefetched two planes ahead, PF = 2): correct but 4.4 ms — with two warps per scheduler the
+//     prefetched loads stall (ncu profiles/r2i_*: long-scoreboard) — kept as B2_ISO_V2=1 for the record;
 //   * the x-history of the own columns is kept in register queues with static slots (planes c+1..c+R in
 //     fut[(p+k) mod R], c-R..c-1 in pst[...], the loop unrolled R times — not 2R+1 = 13 times, which is
 //     what made the first "taller tile" experiment of round 1 miss the instruction cache);
@@ -780,8 +782,7 @@ template <int R> struct Tile2Of { static constexpr bool on = false; static const
 // 28 x 64: 14 x 16 = 224 consumer threads + the producer warp = 8 warps, so that the register file splits
 // into 255 registers per thread (9 warps would be allocated as 12: 168 registers, and the queues spill)
 template <> struct Tile2Of<6> { static constexpr bool on = true; static constexpr int TY = 28, TZ4 = 16; };
-// experiment: 40 x 64 (20 x 16 = 320 consumers + producer = 11 warps, allocated as 12: 168 registers)
-template <int R> struct Tile2bOf { static constexpr int TY = 40, TZ4 = 16; };
+
 
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
@@ -873,8 +874,7 @@ static int plan_tma(IsoPlan &p) {
     p.v2 = Tile2Of<R>::on && p.n[1] >= 16 ? env_int("B2_ISO_V2", 4) : 0;   // so=12: variant 4 (3.08 vs 3.20 ms at 1024^3)
     if (p.v2) {
         using T2 = Tile2Of<R>;
-        using T2b = Tile2bOf<R>;
-        if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T2::TZ4 + 2 * RZ, (p.v2 == 3 ? T2b::TY : T2::TY) + 2 * R))) return rc;
+        if ((rc = make_tmap(&p.tm_uh, p.u, 4, dims4, 4 * T2::TZ4 + 2 * RZ, T2::TY + 2 * R))) return rc;
         // variant 4: u[t-1] and the coefficient tiles by TMA (28 x 64 tiles)
         if ((rc = make_tmap(&p.tm_uc, p.u, 4, dims4, 4 * T2::TZ4, T2::TY))) return rc;
         if ((rc = make_tmap(&p.tm_damp, p.coefA, 3, dims3, 4 * T2::TZ4, T2::TY))) return rc;
@@ -951,22 +951,16 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM),
                 B2_ERR_LAUNCH);
         if constexpr (T2::on) {
-            using T2b = Tile2bOf<R>;
-            using C2b = IsoTma2Cfg<R, T2b::TY, T2b::TZ4>;
             B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C2::SMEM), B2_ERR_LAUNCH);
-            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C2::SMEM), B2_ERR_LAUNCH);
-            B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2b::TY, T2b::TZ4, PK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)C2b::SMEM), B2_ERR_LAUNCH);
             using C2t = IsoTma2Cfg<R, T2::TY, T2::TZ4, 0, (PK != B2_PARAM_SCALAR ? 3 : 2)>;
             B2_CUDA(cudaFuncSetAttribute(k_iso_tma2<R, T2::TY, T2::TZ4, PK, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C2t::SMEM), B2_ERR_LAUNCH);
         }
         attr_set = true;
     }
-    const int v2 = T2::on ? p.v2 : 0;
-    const int TYeff = v2 == 3 ? Tile2bOf<R>::TY : v2 ? T2::TY : T::TY;
+    const int v2 = T2::on ? p.v2 : 0;           // 4: TMA tile ring (default at so=12), 1: LDG prefetch (experiment)
+    const int TYeff = v2 ? T2::TY : T::TY;
     IsoTK<R> k;
     k.u1 = p.u + (size_t)slot1 * p.slot_elems;
     k.sx = p.sx;
@@ -1034,10 +1028,8 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
         using C2t = IsoTma2Cfg<R, T2::TY, T2::TZ4, 0, (PK != B2_PARAM_SCALAR ? 3 : 2)>;
         const unsigned nth = (T2::TY / 2) * T2::TZ4 + 32;
         if (v2 == 1) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 2><<<grid, nth, C2::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
-        if (v2 == 2) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 1><<<grid, nth, C2::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
-        if (v2 == 3) k_iso_tma2<R, T2b::TY, T2b::TZ4, PK, 1><<<grid, (T2b::TY / 2) * T2b::TZ4 + 32, C2b::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
         if (v2 == 4) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 0><<<grid, nth, C2t::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
-        launched = v2 != 0;
+        launched = v2 == 1 || v2 == 4;
     }
     if (!launched)
         kern<<<grid, T::TY * T::TZ4 + 32, C::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
