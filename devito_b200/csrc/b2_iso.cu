@@ -1023,8 +1023,6 @@ static int launch_tma(const IsoPlan &p, int slot0, int slotm, int slot1, int xlo
     timing_begin();
     bool launched = false;
     if constexpr (T2::on) {
-        using T2b = Tile2bOf<R>;
-        using C2b = IsoTma2Cfg<R, T2b::TY, T2b::TZ4>;
         using C2t = IsoTma2Cfg<R, T2::TY, T2::TZ4, 0, (PK != B2_PARAM_SCALAR ? 3 : 2)>;
         const unsigned nth = (T2::TY / 2) * T2::TZ4 + 32;
         if (v2 == 1) k_iso_tma2<R, T2::TY, T2::TZ4, PK, 2><<<grid, nth, C2::SMEM, stream()>>>(p.tm_uh, p.tm_uc, p.tm_damp, p.tm_par, k);
