@@ -60,7 +60,10 @@ class LinearSystem:
         a.fields = farr
         if len(coefs) > L_.SYS_MAX_COEFS:
             raise InvalidArgument(f"{len(coefs)} coefficient arrays (at most {L_.SYS_MAX_COEFS})")
-        cobjs = [L_.make_dataobj(host=np.ascontiguousarray(c, dtype=np.float32)) for c in coefs]
+        # a coefficient array is a float32 ndarray (host-staged by the library) or a ready `struct dataobj` holder
+        # (e.g. device-resident: the plugin keeps the tabulated arrays on the GPU across applies)
+        cobjs = [c if hasattr(c, 'ptr') else L_.make_dataobj(host=np.ascontiguousarray(c, dtype=np.float32))
+                 for c in coefs]
         carr = (ctypes.POINTER(L_.Dataobj) * max(1, len(cobjs)))(*[c.ptr for c in cobjs])
         a.ncoefs, a.coefs = len(cobjs), carr
         st = (L_.SysStage * len(self.stages))()

@@ -132,6 +132,8 @@ def ffi():
             return b''
 
     L_.lib = lambda: Double()
+    # no device here: the tabulated coefficient arrays stay host arrays for the emulation
+    rp._coef_resident = lambda arr: L_.make_dataobj(host=np.ascontiguousarray(arr, dtype=np.float32))
     kw = dict(shape=(20, 20, 20), nbl=6, spacing=(20., 20., 20.), dtype=np.float32)
     # layered velocity (array parameter), free surface
     model = demo_model('layers-isotropic', space_order=4, fs=True, **kw)
