@@ -44,7 +44,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG = {'iso': 16.0, 'tti': 28.0}   # algorithmic bytes / point / step
+B_ALG = {'iso': 16.0, 'tti': 28.0,    # algorithmic bytes / point / step
+         'tti-arrays': 52.0}           # + cx, cy, cz, 1+2eps, sqrt(1+2delta), m/dt^2 tables
 
 
 def parse():
@@ -58,7 +59,7 @@ def parse():
     ap.add_argument('--nt', type=int, default=int(os.environ.get('B2_BENCH_NT', 256)),
                     help='time steps per Operator.apply')
     ap.add_argument('--space-order', type=int, default=8)
-    ap.add_argument('--workload', default='iso', choices=['iso', 'tti'],
+    ap.add_argument('--workload', default='iso', choices=['iso', 'tti', 'tti-arrays'],
                     help="iso: the headline metric; tti: BASELINE config 4 (not the driver's line)")
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help="strong: BASELINE config 5 as the headline (2048x1024x1024 fixed)")
@@ -313,10 +314,21 @@ class Bench:
                                          AnisotropicWaveSolver)
         nbl = 40
         shape = tuple(s - 2 * nbl for s in shape_total)
-        tti = kind == 'tti'
+        tti = kind.startswith('tti')
         extra = dict(epsilon=.3, delta=.2, theta=.7, phi=.35) if tti else {}
+        vp = 1.5
+        if kind == 'tti-arrays':
+            # array-valued vp / epsilon / delta / theta / phi (the reference's `layers-tti` shape of problem, here
+            # with lateral variation as well): per-point tables instead of scalars in the kernel
+            ax = [np.linspace(0., 1., n, dtype=np.float32) for n in shape]
+            gx, gy, gz = ax[0][:, None, None], ax[1][None, :, None], ax[2][None, None, :]
+            vp = (1.5 + 0.3 * gx + 0.2 * gy + 1.5 * gz).astype(np.float32)
+            extra = dict(epsilon=(0.05 + 0.25 * gz + 0.0 * gx + 0.0 * gy).astype(np.float32),
+                         delta=(0.02 + 0.1 * gz + 0.05 * gx + 0.0 * gy).astype(np.float32),
+                         theta=(0.2 + 0.5 * gz + 0.2 * gx * gy).astype(np.float32),
+                         phi=(0.1 + 0.3 * gy + 0.2 * gz + 0.0 * gx).astype(np.float32))
         model = SeismicModel(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=shape, space_order=so,
-                             vp=1.5, nbl=nbl, bcs="damp", topology=('*', 1, 1) if self.nranks > 1 else None,
+                             vp=vp, nbl=nbl, bcs="damp", topology=('*', 1, 1) if self.nranks > 1 else None,
                              **extra)
         dt = model.critical_dt
         tn = float(dt) * (NT + 0.5)                    # geometry.nt = NT + 2, NT time steps per apply
@@ -373,7 +385,7 @@ class Bench:
             ach = B_ALG[w['kind']] * pts_launch / (k_ms_max * 1e-3) / 1e9
             out['roofline'] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                               "kernel": "k_tti_*" if w['kind'] == 'tti' else "k_iso_tma",
+                               "kernel": "k_tti_*" if w['kind'].startswith('tti') else "k_iso_tma",
                                "launch_ms": k_ms_max, "launches_timed": int(nl.value),
                                "timed_in": "a second pass of %d applies with CUDA events around every stencil launch "
                                            "(%.1f ms per apply with the events, %.1f ms without)"
@@ -523,7 +535,7 @@ def main():
     if nranks > 1:
         halo_path = ("NCCL send/recv" if not getattr(w['u'].storage, 'p2p_registered', False) else
                      "peer-memory copies over NVLink (CUDA IPC + device flags)"
-                     if os.environ.get('B2_HALO_FUSED') == '0' or a.workload == 'tti' else
+                     if os.environ.get('B2_HALO_FUSED') == '0' or a.workload.startswith('tti') else
                      "fused into the sweep kernel: boundary planes stored into the neighbour's halo over NVLink "
                      "(CUDA IPC) by the CTAs that produce them, release/acquire flags")
     nvlink = None
@@ -554,7 +566,7 @@ def main():
         def side(kind, so_, total_, nt_, reps=3):
             ww = b.workload(kind, so_, total_, nt_)
             r = b.run_resident(ww, reps, 3)
-            r['config'] = (f"{'TTI' if kind == 'tti' else 'iso acoustic'} so={so_}, grid {'x'.join(map(str, total_))}, "
+            r['config'] = (f"{ {'tti': 'TTI', 'tti-arrays': 'TTI, array-valued vp/eps/delta/theta/phi'}.get(kind, 'iso acoustic')} so={so_}, grid {'x'.join(map(str, total_))}, "
                            f"{ww['nt_steps']} time steps per apply, {reps} applies after 3 warm-up")
             r['unit'] = 'GPts/s'
             b.release(ww)
@@ -562,6 +574,7 @@ def main():
         if nranks == 1:
             extra['C3_iso_so12_1024'] = side('iso', 12, (G, G, G), 64)
             extra['C4_tti_so8_768'] = side('tti', 8, (768, 768, 768), 64)
+            extra['C4b_tti_arrays_so8_512'] = side('tti-arrays', 8, (512, 512, 512), 32, reps=2)
         c5 = side('iso', 8, (2 * G, G, G), 96)
         c5['scaling'] = 'strong'
         extra['C5_iso_so8_2048x1024x1024_strong'] = c5
@@ -576,7 +589,7 @@ def main():
             cpu = {"value": None, "unit": "GPts/s", "cores": None, "kind": "port", "sample": f"failed: {e}"}
 
     if rank == 0:
-        tti = a.workload == 'tti'
+        tti = a.workload.startswith('tti')
         gx = total[0]
         line = {"metric": "GPts/s (3D %s forward, so=%d, %d^3 per GPU)" % ("TTI" if tti else "isotropic acoustic", so, G),
                 "value": res['value'], "unit": "GPts/s", "n_gpus": nranks, "steps": a.steps, "warmup": a.warmup,

@@ -175,6 +175,14 @@ struct TtiFK {
     // {w, w} pairs for the packed fp32x2 arithmetic of k_tti_ws (they sit in uniform registers)
     float2 p_w2x[5], p_w2y[5], p_w1x[4], p_w1y[4];
     float2 p_wc, p_e2, p_sd, p_mdt2;
+    // array-valued parameters (k_tti_fused<.., ARR = true>): per-point tables; w1x/w1y/w1z then hold the RAW weights
+    const float *__restrict__ tCx;
+    const float *__restrict__ tCy;
+    const float *__restrict__ tCz;
+    const float *__restrict__ tE2;
+    const float *__restrict__ tSD;
+    const float *__restrict__ tMD;
+    int ay, az;                // allocated extents of dims 1, 2 (bounds of the table reads on the extended tile)
 };
 
 template <int R, int TY>
@@ -197,7 +205,13 @@ struct TtiCfg {
     static constexpr size_t SMEM = (size_t)((NUU + NUV) * PLANE + 2 * NG * GPLANE) * 4 + 2 * NB * 8 + 128;
 };
 
-template <int R, int TY>
+// ARR = true: array-valued vp / epsilon / delta / theta / phi (`layers-tti`). The rotation factors are sampled where
+// the reference samples them — at the Gz point inside Gz, at the shifted point in the outer derivative — from the
+// per-point tables of k_tti_tables, read through L1 (`ld.global.nc`): stage A loads cx, cy, cz of its float4 group,
+// stage B keeps cx of its own column in a register queue along x and loads cy of the R rows / cz of the z segment
+// around its four points; (1+2eps), sqrt(1+2delta), m/dt^2 and A come with u[t-1], v[t-1] at the top of the
+// iteration. 52 B/point instead of 28.
+template <int R, int TY, bool ARR>
 __global__ void __launch_bounds__(TY * 16 + 32, 1)
 k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const TtiFK k) {
@@ -281,6 +295,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     // [-H, H-1], dealt round-robin; packed as poff | fv<<16 | has_left<<17 | has_right<<18 | valid<<19
     constexpr int NTASK = (2 * C::GGROUPS + NCT - 1) / NCT;
     int tdesc[NTASK];
+    int tcoff[ARR ? NTASK : 1];        // ARR: offset of the group inside an x plane of the tables, -1 = outside the array
 #pragma unroll
     for (int t = 0; t < NTASK; ++t) {
         const int task = tid + t * NCT;
@@ -291,6 +306,16 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const int poff = (gr + R - H) * BZ + 4 * gc;
         tdesc[t] = poff | (fv ? 1 << 16 : 0) | (gc > 0 ? 1 << 17 : 0) | (gc < BZ / 4 - 1 ? 1 << 18 : 0) |
                    (valid ? 1 << 19 : 0);
+        if constexpr (ARR) {
+            const int ay_ = k.oy + y0 - H + gr, az_ = k.oz + z0 - RZ + 4 * gc;
+            tcoff[t] = (valid && ay_ >= 0 && ay_ < k.ay && az_ >= 0 && az_ + 4 <= k.az)
+                           ? (int)((long long)ay_ * k.sy + az_) : -1;
+        }
+    }
+    float4 cxq[ARR ? R : 1];           // ARR: cx of the own column at planes x-H .. x+H-1
+    if constexpr (ARR) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) cxq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     long long gi = (long long)(k.ox + xs - PRE) * k.sx + gidx0;
 
@@ -317,6 +342,19 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 pa = make_float4(t[8], t[9], t[10], t[11]);
             }
         }
+        float4 pe2 = pu, psd = pu, pmd = pu;
+        if constexpr (ARR) {
+            // the 16-byte table reads stay inside the array for every gz < nz (az % 4 == 0, >= 4 cells of halo)
+            if (x >= xs && zcnt > 0) {
+                pe2 = __ldg(reinterpret_cast<const float4 *>(k.tE2 + gi));
+                psd = __ldg(reinterpret_cast<const float4 *>(k.tSD + gi));
+                pmd = __ldg(reinterpret_cast<const float4 *>(k.tMD + gi));
+            }
+#pragma unroll
+            for (int i = 0; i < R - 1; ++i) cxq[i] = cxq[i + 1];
+            if (x + H - 1 >= xs - H && zcnt > 0)
+                cxq[R - 1] = __ldg(reinterpret_cast<const float4 *>(k.tCx + gi + (long long)(H - 1) * k.sx));
+        }
         b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
 
         // queue: uq[i] = u plane x - R + i   (newest = x + R)
@@ -342,6 +380,15 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 const bool fv = d & (1 << 16);
                 const int poff = d & 0xffff;
                 float4 rr = make_float4(0, 0, 0, 0);
+                float4 c4x = rr, c4y = rr, c4z = rr, ry = rr, rz = rr;   // ARR: factors at the Gz point; D+y, D+z kept apart
+                if constexpr (ARR) {
+                    if (tcoff[t] >= 0) {
+                        const long long ci = (long long)(k.ox + x + H - 1) * k.sx + tcoff[t];
+                        c4x = __ldg(reinterpret_cast<const float4 *>(k.tCx + ci));
+                        c4y = __ldg(reinterpret_cast<const float4 *>(k.tCy + ci));
+                        c4z = __ldg(reinterpret_cast<const float4 *>(k.tCz + ci));
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < R; ++j) {                // x taps
                     const float4 a = b2ptx::lds128((fv ? vp[j] : up[j]) + poff);
@@ -351,19 +398,26 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < R; ++j) {                // y taps
                     const float4 a = b2ptx::lds128(fc + (j - H + 1) * BZ);
-                    f4fma_(rr, k.w1y[j], a);
+                    f4fma_(ARR ? ry : rr, k.w1y[j], a);
                 }
                 {                                            // z taps: segment [-4, 8) around the group
                     const float4 l = (d & (1 << 17)) ? b2ptx::lds128(fc - 4) : make_float4(0, 0, 0, 0);
                     const float4 c = b2ptx::lds128(fc);
                     const float4 r = (d & (1 << 18)) ? b2ptx::lds128(fc + 4) : make_float4(0, 0, 0, 0);
                     const float zz[12] = {l.x, l.y, l.z, l.w, c.x, c.y, c.z, c.w, r.x, r.y, r.z, r.w};
+                    float4 &az_ = ARR ? rz : rr;
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
                         const int o = 4 + j - H + 1;
-                        rr.x = fmaf(k.w1z[j], zz[o + 0], rr.x); rr.y = fmaf(k.w1z[j], zz[o + 1], rr.y);
-                        rr.z = fmaf(k.w1z[j], zz[o + 2], rr.z); rr.w = fmaf(k.w1z[j], zz[o + 3], rr.w);
+                        az_.x = fmaf(k.w1z[j], zz[o + 0], az_.x); az_.y = fmaf(k.w1z[j], zz[o + 1], az_.y);
+                        az_.z = fmaf(k.w1z[j], zz[o + 2], az_.z); az_.w = fmaf(k.w1z[j], zz[o + 3], az_.w);
                     }
+                }
+                if constexpr (ARR) {                         // Gz = cx D+x + cy D+y + cz D+z with the factors of this point
+                    rr.x = fmaf(c4z.x, rz.x, fmaf(c4y.x, ry.x, c4x.x * rr.x));
+                    rr.y = fmaf(c4z.y, rz.y, fmaf(c4y.y, ry.y, c4x.y * rr.y));
+                    rr.z = fmaf(c4z.z, rz.z, fmaf(c4y.z, ry.z, c4x.z * rr.z));
+                    rr.w = fmaf(c4z.w, rz.w, fmaf(c4y.w, ry.w, c4x.w * rr.w));
                 }
                 *reinterpret_cast<float4 *>((fv ? s_gv : s_gu) + sgz + poff - (R - H) * BZ) = rr;
             }
@@ -375,6 +429,26 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
 
         // ---- stage B: output plane x ----
         if (x >= xs) {
+            // ARR: cy at the R rows and cz on the z segment around the four points, issued ahead of their use
+            float4 cyq[ARR ? R : 1];
+            float czr[ARR ? 12 : 1];
+            if constexpr (ARR) {
+                if (zcnt > 0) {
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+                        cyq[j] = __ldg(reinterpret_cast<const float4 *>(k.tCy + gi + (long long)(j - H) * k.sy));
+                    const float4 l = __ldg(reinterpret_cast<const float4 *>(k.tCz + gi - 4));
+                    const float4 cc = __ldg(reinterpret_cast<const float4 *>(k.tCz + gi));
+                    const float4 r = __ldg(reinterpret_cast<const float4 *>(k.tCz + gi + 4));
+                    czr[0] = l.x; czr[1] = l.y; czr[2] = l.z; czr[3] = l.w; czr[4] = cc.x; czr[5] = cc.y; czr[6] = cc.z;
+                    czr[7] = cc.w; czr[8] = r.x; czr[9] = r.y; czr[10] = r.z; czr[11] = r.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < R; ++j) cyq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) czr[j] = 0.f;
+                }
+            }
             const float *cpl = s_u + iu * PLANE + my_off;   // u plane x, own column
             const float4 c = uq[R];
             const float4 vcn = b2ptx::lds128(s_v + iv * PLANE + my_off);
@@ -412,8 +486,15 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 const int so_ = sl_ * GPLANE + my_goff;
                 const float4 a = b2ptx::lds128(s_gu + so_), bb = b2ptx::lds128(s_gv + so_);
                 const float w = k.w1x[j];
-                zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
-                zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
+                if constexpr (ARR) {
+                    const float4 q = cxq[j];
+                    const float wx = q.x * w, wy = q.y * w, wz = q.z * w, ww = q.w * w;
+                    zu4.x = fmaf(wx, a.x, zu4.x); zu4.y = fmaf(wy, a.y, zu4.y); zu4.z = fmaf(wz, a.z, zu4.z); zu4.w = fmaf(ww, a.w, zu4.w);
+                    zv4.x = fmaf(wx, bb.x, zv4.x); zv4.y = fmaf(wy, bb.y, zv4.y); zv4.z = fmaf(wz, bb.z, zv4.z); zv4.w = fmaf(ww, bb.w, zv4.w);
+                } else {
+                    zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
+                    zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
+                }
             }
             const float *gpu_ = s_gu + ig * GPLANE + my_goff;
             const float *gpv_ = s_gv + ig * GPLANE + my_goff;
@@ -421,8 +502,15 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             for (int j = 0; j < R; ++j) {                       // y direction: rows y-H+j
                 const float4 a = b2ptx::lds128(gpu_ + (j - H) * BZ), bb = b2ptx::lds128(gpv_ + (j - H) * BZ);
                 const float w = k.w1y[j];
-                zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
-                zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
+                if constexpr (ARR) {
+                    const float4 q = cyq[j];
+                    const float wx = q.x * w, wy = q.y * w, wz = q.z * w, ww = q.w * w;
+                    zu4.x = fmaf(wx, a.x, zu4.x); zu4.y = fmaf(wy, a.y, zu4.y); zu4.z = fmaf(wz, a.z, zu4.z); zu4.w = fmaf(ww, a.w, zu4.w);
+                    zv4.x = fmaf(wx, bb.x, zv4.x); zv4.y = fmaf(wy, bb.y, zv4.y); zv4.z = fmaf(wz, bb.z, zv4.z); zv4.w = fmaf(ww, bb.w, zv4.w);
+                } else {
+                    zu4.x = fmaf(w, a.x, zu4.x); zu4.y = fmaf(w, a.y, zu4.y); zu4.z = fmaf(w, a.z, zu4.z); zu4.w = fmaf(w, a.w, zu4.w);
+                    zv4.x = fmaf(w, bb.x, zv4.x); zv4.y = fmaf(w, bb.y, zv4.y); zv4.z = fmaf(w, bb.z, zv4.z); zv4.w = fmaf(w, bb.w, zv4.w);
+                }
             }
             {
                 const float4 lu = b2ptx::lds128(gpu_ - 4), cu = b2ptx::lds128(gpu_), ru_ = b2ptx::lds128(gpu_ + 4);
@@ -433,20 +521,29 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 for (int j = 0; j < R; ++j) {                   // z direction: offsets j-H
                     const float w = k.w1z[j];
                     const int o = 4 + j - H;
-                    zu4.x = fmaf(w, au[o + 0], zu4.x); zu4.y = fmaf(w, au[o + 1], zu4.y);
-                    zu4.z = fmaf(w, au[o + 2], zu4.z); zu4.w = fmaf(w, au[o + 3], zu4.w);
-                    zv4.x = fmaf(w, av[o + 0], zv4.x); zv4.y = fmaf(w, av[o + 1], zv4.y);
-                    zv4.z = fmaf(w, av[o + 2], zv4.z); zv4.w = fmaf(w, av[o + 3], zv4.w);
+                    if constexpr (ARR) {
+                        zu4.x = fmaf(czr[o + 0] * w, au[o + 0], zu4.x); zu4.y = fmaf(czr[o + 1] * w, au[o + 1], zu4.y);
+                        zu4.z = fmaf(czr[o + 2] * w, au[o + 2], zu4.z); zu4.w = fmaf(czr[o + 3] * w, au[o + 3], zu4.w);
+                        zv4.x = fmaf(czr[o + 0] * w, av[o + 0], zv4.x); zv4.y = fmaf(czr[o + 1] * w, av[o + 1], zv4.y);
+                        zv4.z = fmaf(czr[o + 2] * w, av[o + 2], zv4.z); zv4.w = fmaf(czr[o + 3] * w, av[o + 3], zv4.w);
+                    } else {
+                        zu4.x = fmaf(w, au[o + 0], zu4.x); zu4.y = fmaf(w, au[o + 1], zu4.y);
+                        zu4.z = fmaf(w, au[o + 2], zu4.z); zu4.w = fmaf(w, au[o + 3], zu4.w);
+                        zv4.x = fmaf(w, av[o + 0], zv4.x); zv4.y = fmaf(w, av[o + 1], zv4.y);
+                        zv4.z = fmaf(w, av[o + 2], zv4.z); zv4.w = fmaf(w, av[o + 3], zv4.w);
+                    }
                 }
             }
             float4 ou, ov;
 #define B2_TTI_UPD(F)                                                              \
             {                                                                      \
                 const float gh = lap.F - zu4.F;                                    \
-                const float H0 = fmaf(k.e2, gh, k.sd * zv4.F);                     \
-                const float Hz = fmaf(k.sd, gh, zv4.F);                            \
-                ou.F = fmaf(pa.F, fmaf(k.m_dt2, c.F - pu.F, H0), c.F);             \
-                ov.F = fmaf(pa.F, fmaf(k.m_dt2, vcn.F - pv.F, Hz), vcn.F);         \
+                const float e2_ = ARR ? pe2.F : k.e2, sd_ = ARR ? psd.F : k.sd;    \
+                const float md_ = ARR ? pmd.F : k.m_dt2;                           \
+                const float H0 = fmaf(e2_, gh, sd_ * zv4.F);                       \
+                const float Hz = fmaf(sd_, gh, zv4.F);                             \
+                ou.F = fmaf(pa.F, fmaf(md_, c.F - pu.F, H0), c.F);                 \
+                ov.F = fmaf(pa.F, fmaf(md_, vcn.F - pv.F, Hz), vcn.F);             \
             }
             B2_TTI_UPD(x) B2_TTI_UPD(y) B2_TTI_UPD(z) B2_TTI_UPD(w)
 #undef B2_TTI_UPD
@@ -834,6 +931,13 @@ k_tti_ws(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUten
 }
 
 __global__ void __launch_bounds__(256)
+k_tti_coef_arr(const float *__restrict__ damp, const float *__restrict__ md, float inv_dt, float *__restrict__ A, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) A[i] = 1.0f / (md[i] + (damp ? damp[i] * inv_dt : 0.f));
+}
+
+__global__ void __launch_bounds__(256)
 k_tti_coef(const float *__restrict__ damp, float m_dt2, float inv_dt, float *__restrict__ A, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -873,6 +977,12 @@ constexpr int kTtiWsTY = 24;
 template <int R> struct TtiTile;
 template <> struct TtiTile<2> { static constexpr int TY = 32; };
 template <> struct TtiTile<4> { static constexpr int TY = 28; };
+// array-parameter variant: more live registers per thread (factor queue, per-point tables). Warps are allocated in
+// fours, so 22 rows (11 + 1 warps -> 168 registers) and 30 rows (15 + 1 warps -> 128) are the sizes below 16 / 20 warps
+template <int R> struct TtiTileArr;
+template <> struct TtiTileArr<2> { static constexpr int TY = 30; };
+template <> struct TtiTileArr<4> { static constexpr int TY = 22; };
+static int env_int_tti(const char *name, int dflt);
 
 // scratch cached across calls
 static float *g_tti_scratch[9] = {};
@@ -896,31 +1006,23 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         return B2_ERR_INVALID;
     }
     p.has_arrays = p.vp_a || p.eps_a || p.delta_a || p.theta_a || p.phi_a;
-    bool ok = !p.has_arrays && (p.R == 2 || p.R == 4) && (p.a[2] % 4 == 0) && (p.o[2] % 4 == 0) &&
+    bool ok = (p.R == 2 || p.R == 4) && (p.a[2] % 4 == 0) && (p.o[2] % 4 == 0) &&
               ((uintptr_t)p.u % 16 == 0) && ((uintptr_t)p.v % 16 == 0) && (p.slot_elems % 4 == 0) &&
               p.n[1] >= 8 && p.n[2] >= 16;
+    // array-valued parameters: the fused kernel reads the per-point tables with 16-byte loads one group left and
+    // right of its points and with 32-bit in-plane offsets
+    if (p.has_arrays)
+        ok = ok && env_int_tti("B2_TTI_ARR_FUSED", 1) != 0 && p.o[2] >= 4 && p.a[2] - (p.o[2] + p.n[2]) >= 4 &&
+             p.o[1] >= p.R && p.a[1] - (p.o[1] + p.n[1]) >= p.R && (long long)p.a[1] * p.a[2] < (1ll << 31);
     if (kernel == 1) ok = false;
     if (kernel == 2 && !ok) {
         set_error("tti: fused kernel forced but layout does not qualify (radius=%d a2=%d o2=%d)", p.R, p.a[2], p.o[2]);
         return B2_ERR_INVALID;
     }
     p.use_fused = ok;
+    p.arr_fused = ok && p.has_arrays;
     int rc;
-    if (ok) {
-        if ((rc = tti_scratch(0, p.slot_elems, &p.coefA))) return rc;
-        const float inv_dt = 1.0f / p.dt;
-        const float md = (1.0f / (p.vp * p.vp)) * (1.0f / (p.dt * p.dt));
-        k_tti_coef<<<148 * 8, 256, 0, stream()>>>(p.damp, md, inv_dt, p.coefA, p.slot_elems);
-        count_launch();
-        B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
-        const int ty = p.R == 2 ? TtiTile<2>::TY : (tti_use_ws(4) ? kTtiWsTY : TtiTile<4>::TY);
-        if ((rc = tti_make_tmap(&p.tm_u, p.u, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
-        if ((rc = tti_make_tmap(&p.tm_v, p.v, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
-        return B2_OK;
-    }
-    if ((rc = tti_scratch(1, p.slot_elems, &p.gzu))) return rc;
-    if ((rc = tti_scratch(2, p.slot_elems, &p.gzv))) return rc;
-    if (p.has_arrays) {
+    auto tables = [&]() -> int {
         float **t[6] = {&p.tCx, &p.tCy, &p.tCz, &p.tE2, &p.tSD, &p.tMD};
         for (int i = 0; i < 6; ++i)
             if ((rc = tti_scratch(3 + i, p.slot_elems, t[i]))) return rc;
@@ -930,7 +1032,30 @@ int tti_plan_init(TtiPlan &p, int kernel) {
                                                      p.tSD, p.tMD, p.slot_elems);
         count_launch();
         B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+        return B2_OK;
+    };
+    if (ok) {
+        if ((rc = tti_scratch(0, p.slot_elems, &p.coefA))) return rc;
+        const float inv_dt = 1.0f / p.dt;
+        int ty;
+        if (p.arr_fused) {
+            if ((rc = tables())) return rc;
+            k_tti_coef_arr<<<148 * 8, 256, 0, stream()>>>(p.damp, p.tMD, inv_dt, p.coefA, p.slot_elems);
+            ty = p.R == 2 ? TtiTileArr<2>::TY : TtiTileArr<4>::TY;
+        } else {
+            const float md = (1.0f / (p.vp * p.vp)) * (1.0f / (p.dt * p.dt));
+            k_tti_coef<<<148 * 8, 256, 0, stream()>>>(p.damp, md, inv_dt, p.coefA, p.slot_elems);
+            ty = p.R == 2 ? TtiTile<2>::TY : (tti_use_ws(4) ? kTtiWsTY : TtiTile<4>::TY);
+        }
+        count_launch();
+        B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+        if ((rc = tti_make_tmap(&p.tm_u, p.u, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
+        if ((rc = tti_make_tmap(&p.tm_v, p.v, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
+        return B2_OK;
     }
+    if ((rc = tti_scratch(1, p.slot_elems, &p.gzu))) return rc;
+    if ((rc = tti_scratch(2, p.slot_elems, &p.gzv))) return rc;
+    if (p.has_arrays && (rc = tables())) return rc;
     return B2_OK;
 }
 
@@ -945,6 +1070,54 @@ static int env_int_tti(const char *name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// fused kernel with per-point parameter tables
+template <int R>
+static int tti_launch_fused_arr(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
+    constexpr int TY = TtiTileArr<R>::TY;
+    using C = TtiCfg<R, TY>;
+    auto kern = k_tti_fused<R, TY, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM), B2_ERR_LAUNCH);
+        attr_set = true;
+    }
+    TtiFK k;
+    memset(&k, 0, sizeof(k));
+    k.u1 = p.u + (size_t)slot1 * p.slot_elems;
+    k.v1 = p.v + (size_t)slot1 * p.slot_elems;
+    k.um = p.u + (size_t)slotm * p.slot_elems;
+    k.vm = p.v + (size_t)slotm * p.slot_elems;
+    k.A = p.coefA;
+    k.sx = p.sx;
+    k.sy = p.sy;
+    k.ny = p.n[1];
+    k.nz = p.n[2];
+    k.ox = p.o[0];
+    k.oy = p.o[1];
+    k.oz = p.o[2];
+    k.ay = p.a[1];
+    k.az = p.a[2];
+    k.xlo = xlo;
+    k.xcount = xcount;
+    k.ntz = (p.n[2] + C::TZ - 1) / C::TZ;
+    k.nty = (p.n[1] + TY - 1) / TY;
+    int lx = env_int_tti("B2_TTI_LX", 0);
+    if (lx <= 0) lx = choose_chunk_len(k.ntz * k.nty, xcount, 2 * R, 32);
+    lx = std::min(lx, xcount);
+    k.lx = lx;
+    const int ntx = (xcount + lx - 1) / lx;
+    k.slot0 = slot0;
+    k.tCx = p.tCx; k.tCy = p.tCy; k.tCz = p.tCz; k.tE2 = p.tE2; k.tSD = p.tSD; k.tMD = p.tMD;
+    for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
+    for (int i = 0; i < R; ++i) { k.w1x[i] = p.w1[0][i]; k.w1y[i] = p.w1[1][i]; k.w1z[i] = p.w1[2][i]; }
+    timing_begin();
+    kern<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
+    timing_end();
+    count_launch();
+    B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
+    return B2_OK;
+}
+
 static bool tti_use_ws(int R) { return R == 4 && env_int_tti("B2_TTI_KERNEL", 3) == 3; }
 template <int R>
 static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
@@ -953,7 +1126,7 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     const int TY = ws ? kTtiWsTY : TYF;
     using C = TtiCfg<R, TYF>;
     using CW = TtiWsCfg<kTtiWsTY>;
-    auto kern = k_tti_fused<R, TYF>;
+    auto kern = k_tti_fused<R, TYF, false>;
     static const int pf = env_int_tti("B2_TTI_PF", 1);   // measured: one-deep 2.94 ms, two-deep (spills) 3.83 ms at 768^3
     auto kern_ws = pf == 1 ? k_tti_ws<kTtiWsTY, 1> : k_tti_ws<kTtiWsTY, 2>;
     static bool attr_set = false;
@@ -1017,6 +1190,9 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
 
 int tti_step(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
     if (xcount <= 0) return B2_OK;
+    if (p.arr_fused)
+        return p.R == 2 ? tti_launch_fused_arr<2>(p, slot0, slotm, slot1, xlo, xcount)
+                        : tti_launch_fused_arr<4>(p, slot0, slotm, slot1, xlo, xcount);
     if (p.use_fused)
         return p.R == 2 ? tti_launch_fused<2>(p, slot0, slotm, slot1, xlo, xcount)
                         : tti_launch_fused<4>(p, slot0, slotm, slot1, xlo, xcount);

@@ -23,6 +23,7 @@ struct TtiPlan {
     int kernel = 0;
     // fused single-pass kernel
     bool use_fused = false;
+    bool arr_fused = false;      // fused kernel with per-point parameter tables (k_tti_fused<.., ARR = true>)
     CUtensorMap tm_u, tm_v;
     float *coefA = nullptr;
     // array-valued parameters (device pointers, nullptr -> scalar)

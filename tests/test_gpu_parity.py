@@ -284,6 +284,36 @@ def test_tti_array_parameters_vs_reference_golden():
     assert rel_linf(rec.data, g['rec']) < 1e-4
 
 
+@pytest.mark.parametrize('so,shape,nbl', [(8, (40, 52, 70), 10), (4, (44, 40, 60), 8)])
+def test_tti_array_parameters_fused_vs_two_pass(so, shape, nbl):
+    """`layers-tti` through the single-pass kernel (k_tti_fused<.., ARR>: per-point rotation factors read from the
+    tables at the Gz point and at the shifted point) against the two-pass generic kernels, which the reference golden
+    above pins: several tiles, partial tiles in y and z, several x-chunks."""
+    import os
+    from devito_b200.seismic import SeismicModel, setup_geometry, AnisotropicWaveSolver
+    # parameters varying along every axis (the layered preset varies along z only and would not see a factor sampled
+    # at the wrong x- or y-shifted point)
+    gx, gy, gz = np.meshgrid(*[np.linspace(0., 1., n, dtype=np.float32) for n in shape], indexing='ij')
+    v = (1.5 + 0.6 * gx + 0.5 * gy + 0.9 * gz).astype(np.float32)
+    model = SeismicModel(space_order=so, vp=v, origin=(0., 0., 0.), shape=shape, dtype=np.float32,
+                         spacing=(10., 10., 10.), nbl=nbl, epsilon=(0.25 * gx * gz + 0.05).astype(np.float32),
+                         delta=(0.12 * gy + 0.02).astype(np.float32),
+                         theta=(0.2 + 0.9 * gx * gy + 0.3 * gz).astype(np.float32),
+                         phi=(0.1 + 0.8 * gy * gz - 0.4 * gx).astype(np.float32), bcs="damp")
+    geometry = setup_geometry(model, 90.0)
+    solver = AnisotropicWaveSolver(model, geometry, space_order=so)
+    r1, u1, v1, _ = solver.forward(kernel=1)
+    os.environ['B2_TTI_LX'] = '24'
+    try:
+        r2, u2, v2, _ = solver.forward(kernel=2)
+    finally:
+        del os.environ['B2_TTI_LX']
+    assert float(np.max(np.abs(u1.data))) > 0
+    assert rel_linf(u2.data_with_halo, u1.data_with_halo) < 1e-4
+    assert rel_linf(v2.data_with_halo, v1.data_with_halo) < 1e-4
+    assert rel_linf(r2.data, r1.data) < 1e-4
+
+
 def test_saved_wavefield():
     """`save=nt` (time slot == time index, no modulo): the saved history ends with the same three
     time levels as the buffered run."""
