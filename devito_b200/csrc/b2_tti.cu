@@ -183,6 +183,7 @@ struct TtiFK {
     const float *__restrict__ tSD;
     const float *__restrict__ tMD;
     int ay, az;                // allocated extents of dims 1, 2 (bounds of the table reads on the extended tile)
+    int pfc;                   // != 0: prefetch next iteration's stage-A factor groups into L2
 };
 
 template <int R, int TY>
@@ -349,6 +350,17 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 pe2 = __ldg(reinterpret_cast<const float4 *>(k.tE2 + gi));
                 psd = __ldg(reinterpret_cast<const float4 *>(k.tSD + gi));
                 pmd = __ldg(reinterpret_cast<const float4 *>(k.tMD + gi));
+            }
+            // stage A of the NEXT iteration reads cx, cy, cz of plane x+H for the first time: ask L2 for them now
+            if (k.pfc && x + H >= xs - H) {
+                const long long cb = (long long)(k.ox + x + H) * k.sx;
+#pragma unroll
+                for (int t = 0; t < NTASK; ++t)
+                    if (tcoff[t] >= 0 && !(tdesc[t] & (1 << 16))) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCx + cb + tcoff[t]));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCy + cb + tcoff[t]));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCz + cb + tcoff[t]));
+                    }
             }
 #pragma unroll
             for (int i = 0; i < R - 1; ++i) cxq[i] = cxq[i + 1];
@@ -1108,6 +1120,7 @@ static int tti_launch_fused_arr(const TtiPlan &p, int slot0, int slotm, int slot
     const int ntx = (xcount + lx - 1) / lx;
     k.slot0 = slot0;
     k.tCx = p.tCx; k.tCy = p.tCy; k.tCz = p.tCz; k.tE2 = p.tE2; k.tSD = p.tSD; k.tMD = p.tMD;
+    k.pfc = env_int_tti("B2_TTI_ARR_PREFETCH", 1);
     for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
     for (int i = 0; i < R; ++i) { k.w1x[i] = p.w1[0][i]; k.w1y[i] = p.w1[1][i]; k.w1z[i] = p.w1[2][i]; }
     timing_begin();

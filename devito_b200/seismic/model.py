@@ -229,10 +229,23 @@ class SeismicModel:
         """CFL time step, rounded through "%.3e" to the model dtype (model.py:370-382)."""
         if self._dt:
             return self._dt
+        # the maxima are full-array reductions (80 ms per apply for vp and epsilon at 512^3, more than a third of a
+        # 32-step propagation): recomputed only after somebody obtained write access to the parameter arrays
+        pars = [self.vp] + ([self.epsilon] if 'epsilon' in self._physical_parameters else [])
+        key = tuple((id(p), getattr(getattr(p, 'storage', None), 'version', None) if hasattr(p, 'storage')
+                     else float(getattr(p, 'data', p))) for p in pars) + (self.dt_scale,)
+        cached = getattr(self, '_critical_dt_cache', None)
+        if cached is not None and cached[0] == key and None not in [k[1] for k in key[:-1]]:
+            return cached[1]
         vmax = mmax(self.vp)
         aniso = np.sqrt(1 + 2 * mmax(self.epsilon)) if 'epsilon' in self._physical_parameters else 1
         dt = self._cfl_coeff * np.min(self.spacing) / (aniso * vmax)
-        return self.dtype("%.3e" % (self.dt_scale * dt))
+        out = self.dtype("%.3e" % (self.dt_scale * dt))
+        # the key is taken again AFTER the reductions: `data` accessors used by a reduction may count as accesses
+        key = tuple((id(p), getattr(getattr(p, 'storage', None), 'version', None) if hasattr(p, 'storage')
+                     else float(getattr(p, 'data', p))) for p in pars) + (self.dt_scale,)
+        self._critical_dt_cache = (key, out)
+        return out
 
 
 Model = SeismicModel

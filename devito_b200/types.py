@@ -367,6 +367,7 @@ class FieldStorage:
         self.dev = None            # torch tensor (allocation only)
         self.host_valid = True
         self.dev_valid = False
+        self.version = 0           # bumped whenever somebody obtains write access (host) or a kernel writes (device)
 
     def _alloc_host(self):
         if self._host is not None:
@@ -398,6 +399,7 @@ class FieldStorage:
         if not self.host_valid:
             self.sync_to_host()
         self.dev_valid = False
+        self.version += 1
         return self._host
 
     @property
@@ -496,6 +498,7 @@ class FieldStorage:
     def mark_device_written(self):
         self.dev_valid = True
         self.host_valid = False
+        self.version += 1
 
     def drop_device(self):
         if self.dev is not None and not self.host_valid:

@@ -284,7 +284,7 @@ def test_tti_array_parameters_vs_reference_golden():
     assert rel_linf(rec.data, g['rec']) < 1e-4
 
 
-@pytest.mark.parametrize('so,shape,nbl', [(8, (40, 52, 70), 10), (4, (44, 40, 60), 8)])
+@pytest.mark.parametrize('so,shape,nbl', [(8, (40, 52, 72), 10), (4, (44, 40, 60), 8)])
 def test_tti_array_parameters_fused_vs_two_pass(so, shape, nbl):
     """`layers-tti` through the single-pass kernel (k_tti_fused<.., ARR>: per-point rotation factors read from the
     tables at the Gz point and at the shifted point) against the two-pass generic kernels, which the reference golden
