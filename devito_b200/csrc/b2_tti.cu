@@ -184,17 +184,21 @@ struct TtiFK {
     const float *__restrict__ tMD;
     int ay, az;                // allocated extents of dims 1, 2 (bounds of the table reads on the extended tile)
     int pfc;                   // != 0: prefetch next iteration's stage-A factor groups into L2
+    int hint;                  // != 0: once-per-CTA table reads bypass L1 allocation
 };
 
-template <int R, int TY>
+// D = how many batches the producer may run ahead of the slowest consumer (ring depths follow); CT = the array-
+// parameter variant that stages the rotation-factor tiles of stage A through shared memory by TMA (two planes of
+// three tables, paid for with one batch less of u / v prefetch)
+template <int R, int TY, int D = 3, bool CT = false>
 struct TtiCfg {
     static constexpr int H = R / 2;
     static constexpr int TZ4 = 16, TZ = 64, RZ = 4;
     static constexpr int PR = TY + 2 * R;            // rows of a u/v plane box
     static constexpr int BZ = TZ + 2 * RZ;           // 72
     static constexpr int GR = TY + R;                // rows of a Gz plane: [-H, TY+H-1] (+pad)
-    static constexpr int NUU = R + 1 + 2;            // u planes x..x+R, +2 prefetch
-    static constexpr int NUV = R + 2;                // v planes x..x+R-1, +2 prefetch
+    static constexpr int NUU = R + D;                // u planes x..x+R, + (D-1) in flight
+    static constexpr int NUV = R + D - 1;            // v planes x..x+R-1, + (D-1) in flight
     static constexpr int NG = R + 1;                 // Gz planes x-H..x+H-1, +1 so that stage A of the
                                                      // next iteration never overwrites a plane still read
     static constexpr int NB = 4;                     // barrier ring
@@ -203,7 +207,8 @@ struct TtiCfg {
     static constexpr int NCT = TY * TZ4;             // consumer threads
     static constexpr int NCW = NCT / 32;
     static constexpr int GGROUPS = (TY + R - 1) * (BZ / 4);   // float4 groups of the extended tile
-    static constexpr size_t SMEM = (size_t)((NUU + NUV) * PLANE + 2 * NG * GPLANE) * 4 + 2 * NB * 8 + 128;
+    static constexpr int NCT_PLANES = CT ? 2 : 0;    // factor-tile ring: planes x+H-1 of this and the next iteration
+    static constexpr size_t SMEM = (size_t)((NUU + NUV) * PLANE + (2 * NG + 3 * NCT_PLANES) * GPLANE) * 4 + 2 * NB * 8 + 128;
 };
 
 // ARR = true: array-valued vp / epsilon / delta / theta / phi (`layers-tti`). The rotation factors are sampled where
@@ -212,11 +217,16 @@ struct TtiCfg {
 // stage B keeps cx of its own column in a register queue along x and loads cy of the R rows / cz of the z segment
 // around its four points; (1+2eps), sqrt(1+2delta), m/dt^2 and A come with u[t-1], v[t-1] at the top of the
 // iteration. 52 B/point instead of 28.
-template <int R, int TY, bool ARR>
+// CT = true (needs ARR): cx, cy, cz of stage A's plane arrive by TMA with the u / v batch instead (boxes of the
+// extended tile, zero-filled outside the array), so stage A has no global loads at all.
+template <int R, int TY, bool ARR, bool CT>
 __global__ void __launch_bounds__(TY * 16 + 32, 1)
 k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
-            const TtiFK k) {
-    using C = TtiCfg<R, TY>;
+            const __grid_constant__ CUtensorMap tm_cx, const __grid_constant__ CUtensorMap tm_cy,
+            const __grid_constant__ CUtensorMap tm_cz, const TtiFK k) {
+    static_assert(!CT || ARR, "factor tiles exist only with array-valued parameters");
+    constexpr int D = CT ? 2 : 3;
+    using C = TtiCfg<R, TY, D, CT>;
     constexpr int H = C::H, TZ = C::TZ, RZ = C::RZ, BZ = C::BZ, PR = C::PR, GR = C::GR;
     constexpr int NUU = C::NUU, NUV = C::NUV, NG = C::NG, NB = C::NB;
     constexpr int PLANE = C::PLANE, GPLANE = C::GPLANE, NCT = C::NCT, NCW = C::NCW;
@@ -227,7 +237,8 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     float *s_v = s_u + NUU * PLANE;
     float *s_gu = s_v + NUV * PLANE;
     float *s_gv = s_gu + NG * GPLANE;
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_gv + NG * GPLANE);
+    float *s_c = s_gv + NG * GPLANE;                // CT: [plane & 1][cx, cy, cz][GPLANE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_c + 3 * C::NCT_PLANES * GPLANE);
     uint64_t *empty = full + NB;
 
     int b = blockIdx.x;
@@ -258,21 +269,37 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             b2ptx::tma_prefetch_desc(&tm_v);
             // batch `it` carries u plane (x+R) and v plane (x+R-1) of iteration x = xs-PRE+it.
             // Its slots were last read in iteration it-3 (u plane x-3+R... see DESIGN.md §3.3).
+            if constexpr (CT) {
+                b2ptx::tma_prefetch_desc(&tm_cx);
+                b2ptx::tma_prefetch_desc(&tm_cy);
+                b2ptx::tma_prefetch_desc(&tm_cz);
+            }
             for (int it = 0; it < NIT; ++it) {
                 const int x = xs - PRE + it;
-                if (it >= 3) {
-                    const int w = it - 3;
+                if (it >= D) {
+                    const int w = it - D;
                     b2ptx::mbar_wait(&empty[w % NB], (w / NB) & 1);
                 }
                 const int pu = x + R;                    // u plane index (relative to origin)
                 const int pv = x + R - 1;
                 const bool hv = pv >= xs - (R - 1);      // v planes below xs-R+1 are never used
-                b2ptx::mbar_arrive_expect_tx(&full[it % NB], (uint32_t)(PR * BZ * 4) * (hv ? 2u : 1u));
+                // CT: factor tiles of stage A's plane x+H-1; their slot held plane x+H-3, last read in iteration it-2
+                const bool hc = CT && (x + H - 1 >= xs - H);
+                b2ptx::mbar_arrive_expect_tx(&full[it % NB], (uint32_t)(PR * BZ * 4) * (hv ? 2u : 1u) +
+                                                                 (hc ? (uint32_t)(3 * C::GR * BZ * 4) : 0u));
                 b2ptx::tma_load_4d(s_u + ((pu % NUU + NUU) % NUU) * PLANE, &tm_u, &full[it % NB],
                                    k.oz + z0 - RZ, k.oy + y0 - R, k.ox + pu, k.slot0);
                 if (hv)
                     b2ptx::tma_load_4d(s_v + ((pv % NUV + NUV) % NUV) * PLANE, &tm_v, &full[it % NB],
                                        k.oz + z0 - RZ, k.oy + y0 - R, k.ox + pv, k.slot0);
+                if constexpr (CT) {
+                    if (hc) {
+                        float *dst = s_c + ((x + H - 1) & 1) * 3 * GPLANE;
+                        b2ptx::tma_load_4d(dst, &tm_cx, &full[it % NB], k.oz + z0 - RZ, k.oy + y0 - H, k.ox + x + H - 1, 0);
+                        b2ptx::tma_load_4d(dst + GPLANE, &tm_cy, &full[it % NB], k.oz + z0 - RZ, k.oy + y0 - H, k.ox + x + H - 1, 0);
+                        b2ptx::tma_load_4d(dst + 2 * GPLANE, &tm_cz, &full[it % NB], k.oz + z0 - RZ, k.oy + y0 - H, k.ox + x + H - 1, 0);
+                    }
+                }
             }
         }
         return;
@@ -296,7 +323,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     // [-H, H-1], dealt round-robin; packed as poff | fv<<16 | has_left<<17 | has_right<<18 | valid<<19
     constexpr int NTASK = (2 * C::GGROUPS + NCT - 1) / NCT;
     int tdesc[NTASK];
-    int tcoff[ARR ? NTASK : 1];        // ARR: offset of the group inside an x plane of the tables, -1 = outside the array
+    int tcoff[(ARR && !CT) ? NTASK : 1];        // ARR without CT: offset of the group inside an x plane of the tables, -1 = outside the array
 #pragma unroll
     for (int t = 0; t < NTASK; ++t) {
         const int task = tid + t * NCT;
@@ -307,7 +334,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         const int poff = (gr + R - H) * BZ + 4 * gc;
         tdesc[t] = poff | (fv ? 1 << 16 : 0) | (gc > 0 ? 1 << 17 : 0) | (gc < BZ / 4 - 1 ? 1 << 18 : 0) |
                    (valid ? 1 << 19 : 0);
-        if constexpr (ARR) {
+        if constexpr (ARR && !CT) {
             const int ay_ = k.oy + y0 - H + gr, az_ = k.oz + z0 - RZ + 4 * gc;
             tcoff[t] = (valid && ay_ >= 0 && ay_ < k.ay && az_ >= 0 && az_ + 4 <= k.az)
                            ? (int)((long long)ay_ * k.sy + az_) : -1;
@@ -324,6 +351,17 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
         ig = ((xs - PRE) % NG + NG) % NG;
     auto wrap = [](int v, int n) { return v >= n ? v - n : v; };
+    // per-point tables read once per CTA: optionally kept out of L1, which the row / segment reads of cy, cz reuse
+    const bool stream_hint = ARR && k.hint != 0;
+    auto ldt = [&](const float *q) -> float4 {
+        float4 r;
+        if (stream_hint)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(q));
+        else
+            r = __ldg(reinterpret_cast<const float4 *>(q));
+        return r;
+    };
 
     for (int it = 0; it < NIT; ++it) {
         const int x = xs - PRE + it;
@@ -332,9 +370,13 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         float4 pu = make_float4(0, 0, 0, 0), pv = pu, pa = pu;
         if (x >= xs && zcnt > 0) {
             if (zcnt == 4) {
-                pu = *reinterpret_cast<const float4 *>(k.um + gi);
-                pv = *reinterpret_cast<const float4 *>(k.vm + gi);
-                pa = *reinterpret_cast<const float4 *>(k.A + gi);
+                if constexpr (ARR) {
+                    pu = ldt(k.um + gi); pv = ldt(k.vm + gi); pa = ldt(k.A + gi);
+                } else {
+                    pu = *reinterpret_cast<const float4 *>(k.um + gi);
+                    pv = *reinterpret_cast<const float4 *>(k.vm + gi);
+                    pa = *reinterpret_cast<const float4 *>(k.A + gi);
+                }
             } else {
                 float t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
                 for (int i = 0; i < zcnt; ++i) { t[i] = k.um[gi + i]; t[4 + i] = k.vm[gi + i]; t[8 + i] = k.A[gi + i]; }
@@ -347,25 +389,27 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         if constexpr (ARR) {
             // the 16-byte table reads stay inside the array for every gz < nz (az % 4 == 0, >= 4 cells of halo)
             if (x >= xs && zcnt > 0) {
-                pe2 = __ldg(reinterpret_cast<const float4 *>(k.tE2 + gi));
-                psd = __ldg(reinterpret_cast<const float4 *>(k.tSD + gi));
-                pmd = __ldg(reinterpret_cast<const float4 *>(k.tMD + gi));
+                pe2 = ldt(k.tE2 + gi);
+                psd = ldt(k.tSD + gi);
+                pmd = ldt(k.tMD + gi);
             }
             // stage A of the NEXT iteration reads cx, cy, cz of plane x+H for the first time: ask L2 for them now
-            if (k.pfc && x + H >= xs - H) {
-                const long long cb = (long long)(k.ox + x + H) * k.sx;
+            if constexpr (!CT) {
+                if (k.pfc && x + H >= xs - H) {
+                    const long long cb = (long long)(k.ox + x + H) * k.sx;
 #pragma unroll
-                for (int t = 0; t < NTASK; ++t)
-                    if (tcoff[t] >= 0 && !(tdesc[t] & (1 << 16))) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCx + cb + tcoff[t]));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCy + cb + tcoff[t]));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCz + cb + tcoff[t]));
-                    }
+                    for (int t = 0; t < NTASK; ++t)
+                        if (tcoff[t] >= 0 && !(tdesc[t] & (1 << 16))) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCx + cb + tcoff[t]));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCy + cb + tcoff[t]));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(k.tCz + cb + tcoff[t]));
+                        }
+                }
             }
 #pragma unroll
             for (int i = 0; i < R - 1; ++i) cxq[i] = cxq[i + 1];
             if (x + H - 1 >= xs - H && zcnt > 0)
-                cxq[R - 1] = __ldg(reinterpret_cast<const float4 *>(k.tCx + gi + (long long)(H - 1) * k.sx));
+                cxq[R - 1] = ldt(k.tCx + gi + (long long)(H - 1) * k.sx);
         }
         b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
 
@@ -393,7 +437,12 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 const int poff = d & 0xffff;
                 float4 rr = make_float4(0, 0, 0, 0);
                 float4 c4x = rr, c4y = rr, c4z = rr, ry = rr, rz = rr;   // ARR: factors at the Gz point; D+y, D+z kept apart
-                if constexpr (ARR) {
+                if constexpr (CT) {
+                    const float *cs = s_c + ((x + H - 1) & 1) * 3 * GPLANE + poff - (R - H) * BZ;
+                    c4x = b2ptx::lds128(cs);
+                    c4y = b2ptx::lds128(cs + GPLANE);
+                    c4z = b2ptx::lds128(cs + 2 * GPLANE);
+                } else if constexpr (ARR) {
                     if (tcoff[t] >= 0) {
                         const long long ci = (long long)(k.ox + x + H - 1) * k.sx + tcoff[t];
                         c4x = __ldg(reinterpret_cast<const float4 *>(k.tCx + ci));
@@ -1063,6 +1112,13 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
         if ((rc = tti_make_tmap(&p.tm_u, p.u, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
         if ((rc = tti_make_tmap(&p.tm_v, p.v, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
+        p.tm_cx = p.tm_cy = p.tm_cz = p.tm_u;
+        p.arr_ct = p.arr_fused && env_int_tti("B2_TTI_ARR_CT", 0) != 0;
+        if (p.arr_ct) {     // boxes of the Gz tile (TY + R rows) over the factor tables
+            if ((rc = tti_make_tmap(&p.tm_cx, p.tCx, p.a, 1, 72, ty + p.R))) return rc;
+            if ((rc = tti_make_tmap(&p.tm_cy, p.tCy, p.a, 1, 72, ty + p.R))) return rc;
+            if ((rc = tti_make_tmap(&p.tm_cz, p.tCz, p.a, 1, 72, ty + p.R))) return rc;
+        }
         return B2_OK;
     }
     if ((rc = tti_scratch(1, p.slot_elems, &p.gzu))) return rc;
@@ -1086,11 +1142,15 @@ static int env_int_tti(const char *name, int dflt) {
 template <int R>
 static int tti_launch_fused_arr(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
     constexpr int TY = TtiTileArr<R>::TY;
-    using C = TtiCfg<R, TY>;
-    auto kern = k_tti_fused<R, TY, true>;
+    using C = TtiCfg<R, TY, 3, false>;
+    using CC = TtiCfg<R, TY, 2, true>;
+    auto kern = k_tti_fused<R, TY, true, false>;
+    auto kern_ct = k_tti_fused<R, TY, true, true>;
+    static_assert(CC::SMEM <= 232448 && C::SMEM <= 232448, "shared memory per CTA");
     static bool attr_set = false;
     if (!attr_set) {
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM), B2_ERR_LAUNCH);
+        B2_CUDA(cudaFuncSetAttribute(kern_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC::SMEM), B2_ERR_LAUNCH);
         attr_set = true;
     }
     TtiFK k;
@@ -1121,10 +1181,14 @@ static int tti_launch_fused_arr(const TtiPlan &p, int slot0, int slotm, int slot
     k.slot0 = slot0;
     k.tCx = p.tCx; k.tCy = p.tCy; k.tCz = p.tCz; k.tE2 = p.tE2; k.tSD = p.tSD; k.tMD = p.tMD;
     k.pfc = env_int_tti("B2_TTI_ARR_PREFETCH", 1);
+    k.hint = env_int_tti("B2_TTI_ARR_HINT", 0);
     for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
     for (int i = 0; i < R; ++i) { k.w1x[i] = p.w1[0][i]; k.w1y[i] = p.w1[1][i]; k.w1z[i] = p.w1[2][i]; }
     timing_begin();
-    kern<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
+    if (p.arr_ct)
+        kern_ct<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, CC::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_cx, p.tm_cy, p.tm_cz, k);
+    else
+        kern<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_cx, p.tm_cy, p.tm_cz, k);
     timing_end();
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
@@ -1139,7 +1203,7 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     const int TY = ws ? kTtiWsTY : TYF;
     using C = TtiCfg<R, TYF>;
     using CW = TtiWsCfg<kTtiWsTY>;
-    auto kern = k_tti_fused<R, TYF, false>;
+    auto kern = k_tti_fused<R, TYF, false, false>;
     static const int pf = env_int_tti("B2_TTI_PF", 1);   // measured: one-deep 2.94 ms, two-deep (spills) 3.83 ms at 768^3
     auto kern_ws = pf == 1 ? k_tti_ws<kTtiWsTY, 1> : k_tti_ws<kTtiWsTY, 2>;
     static bool attr_set = false;
@@ -1194,7 +1258,7 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     if (ws)
         kern_ws<<<(unsigned)(k.ntz * k.nty * ntx), kTtiWsTY * 16 + 128, CW::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
     else
-        kern<<<(unsigned)(k.ntz * k.nty * ntx), TYF * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, k);
+        kern<<<(unsigned)(k.ntz * k.nty * ntx), TYF * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_u, p.tm_u, p.tm_u, k);
     timing_end();
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
