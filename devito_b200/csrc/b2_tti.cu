@@ -1113,7 +1113,7 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         if ((rc = tti_make_tmap(&p.tm_u, p.u, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
         if ((rc = tti_make_tmap(&p.tm_v, p.v, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
         p.tm_cx = p.tm_cy = p.tm_cz = p.tm_u;
-        p.arr_ct = p.arr_fused && env_int_tti("B2_TTI_ARR_CT", 0) != 0;
+        p.arr_ct = p.arr_fused && env_int_tti("B2_TTI_ARR_CT", 1) != 0;
         if (p.arr_ct) {     // boxes of the Gz tile (TY + R rows) over the factor tables
             if ((rc = tti_make_tmap(&p.tm_cx, p.tCx, p.a, 1, 72, ty + p.R))) return rc;
             if ((rc = tti_make_tmap(&p.tm_cy, p.tCy, p.a, 1, 72, ty + p.R))) return rc;
@@ -1181,7 +1181,7 @@ static int tti_launch_fused_arr(const TtiPlan &p, int slot0, int slotm, int slot
     k.slot0 = slot0;
     k.tCx = p.tCx; k.tCy = p.tCy; k.tCz = p.tCz; k.tE2 = p.tE2; k.tSD = p.tSD; k.tMD = p.tMD;
     k.pfc = env_int_tti("B2_TTI_ARR_PREFETCH", 1);
-    k.hint = env_int_tti("B2_TTI_ARR_HINT", 0);
+    k.hint = env_int_tti("B2_TTI_ARR_HINT", 1);
     for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
     for (int i = 0; i < R; ++i) { k.w1x[i] = p.w1[0][i]; k.w1y[i] = p.w1[1][i]; k.w1z[i] = p.w1[2][i]; }
     timing_begin();
