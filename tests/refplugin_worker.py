@@ -220,6 +220,18 @@ def ffi():
             assert err < (5e-4 if 'tti' in tag else 5e-5), (tag, name, err)
             assert float(np.abs(ref[name]).max()) > 0, (tag, name)
             errs[(tag, name)] = err
+    # the tabulated coefficient arrays of a system are cached across applies and re-tabulated when a parameter changes
+    ntab = []
+    real_eval = rp._eval_coef
+    rp._eval_coef = lambda *a, **k: (ntab.append(1), real_eval(*a, **k))[1]
+    try:
+        se.forward()
+        assert not ntab, "same parameters: the cached coefficient arrays must be reused"
+        me.vp.data[:] = me.vp.data * 1.01
+        se.forward()
+        assert ntab, "a changed parameter array must trigger a new tabulation"
+    finally:
+        rp._eval_coef = real_eval
     # the set-up operators stayed on the reference's CPU path (and ran: the damping profile is there)
     assert float(np.max(model.damp.data)) > 0
     print('REFPLUGIN-FFI-OK', len(calls), {k: float(f'{v:.2e}') for k, v in errs.items() if v > 2e-5})
