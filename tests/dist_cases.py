@@ -28,6 +28,17 @@ def run_case(kind, nranks, topology=None):
         if kind == 'tti':
             res['v'] = out[2].data
         return res, model
+    if kind == 'ttiarr':                                   # array-valued vp / eps / delta / theta / phi, varying along every axis
+        from devito_b200.seismic import SeismicModel
+        gx, gy, gz = np.meshgrid(*[np.linspace(0., 1., m, dtype=np.float32) for m in n], indexing='ij')
+        model = SeismicModel(space_order=SO, vp=(1.5 + 0.6 * gx + 0.5 * gy + 0.9 * gz).astype(np.float32),
+                             origin=(0., 0., 0.), shape=n, dtype=np.float32, spacing=(10., 10., 10.), nbl=NBL,
+                             epsilon=(0.25 * gx * gz + 0.05).astype(np.float32), delta=(0.12 * gy + 0.02).astype(np.float32),
+                             theta=(0.2 + 0.9 * gx * gy + 0.3 * gz).astype(np.float32),
+                             phi=(0.1 + 0.8 * gy * gz - 0.4 * gx).astype(np.float32), bcs="damp",
+                             **({'topology': topology} if topology is not None else {}))
+        out = AnisotropicWaveSolver(model, setup_geometry(model, TN), space_order=SO).forward()
+        return {'rec': out[0].data, 'u': out[1].data, 'v': out[2].data}, model
     if kind == 'iso12':                                    # so=12: the two-row sweep kernel with the fused halo step
         kw12 = dict(kw, space_order=12, nbl=14)
         model = demo_model('constant-isotropic', **kw12)
@@ -92,4 +103,4 @@ def run_case(kind, nranks, topology=None):
     raise ValueError(kind)
 
 
-TOL = {'iso12': 1e-5, 'stream': 1e-5, 'iso': 1e-5, 'tti': 1e-4, 'fs': 1e-5, 'ot4': 1e-5, 'born': 1e-4, 'grad': 1e-4, 'snap': 1e-5}
+TOL = {'ttiarr': 1e-4, 'iso12': 1e-5, 'stream': 1e-5, 'iso': 1e-5, 'tti': 1e-4, 'fs': 1e-5, 'ot4': 1e-5, 'born': 1e-4, 'grad': 1e-4, 'snap': 1e-5}

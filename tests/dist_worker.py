@@ -58,6 +58,16 @@ def host_mode():
     assert np.array_equal(np.asarray(fsm.damp.data), fs_full[lo:hi])
     fs_op = AcousticWaveSolver(fsm, setup_geometry(fsm, 30.0), space_order=so).op_fwd()
     assert fs_op.backend == 'cuda-sm100a' and fs_op._plan['free_surface']
+    # array-valued TTI parameters: every rank holds its slab of each table's source array with valid halo planes
+    # (the factor tables of k_tti_fused<.., ARR> are built from them, halo included), operator recognised
+    th = (0.2 + 0.5 * vp / 3.0).astype(np.float32)
+    tm = SeismicModel(origin=(0., 0., 0.), spacing=(10., 10., 10.), shape=n, space_order=so, vp=vp, nbl=nbl, bcs="damp",
+                      epsilon=(0.1 * (vp - 1.5)).astype(np.float32), delta=(0.05 * (vp - 1.5)).astype(np.float32),
+                      theta=th, phi=(0.5 * th).astype(np.float32), topology=('*', 1, 1))
+    th_full = np.pad(np.pad(th, nbl, mode='edge'), so, mode='edge')
+    assert np.array_equal(np.asarray(tm.theta.data_with_halo), th_full[lo:hi + 2 * so])
+    t_op = AnisotropicWaveSolver(tm, setup_geometry(tm, 30.0), space_order=so).op_fwd()
+    assert t_op.backend == 'cuda-sm100a'
     dist.barrier()
     if w.rank == 0:
         print('DIST-HOST-OK')

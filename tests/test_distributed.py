@@ -81,8 +81,9 @@ def test_four_gpu_halo_exchange_matches_single_gpu(kind, tol, path, env):
 
 
 # the schemes that ride on the isotropic update: free surface (copy path: the surface rows are redone after the
-# sweep), OT4 (halo of 2*radius planes), Born (two wavefields), gradient (adjoint + imaging), snapshots
-_SCHEMES = [('iso12', {}), ('stream', {}), ('fs', {}), ('ot4', {}), ('born', {}), ('grad', {}), ('snap', {}), ('ot4', {'B2_HALO': 'nccl'}),
+# sweep), OT4 (halo of 2*radius planes), Born (two wavefields), gradient (adjoint + imaging), snapshots; and the
+# array-parameter TTI kernel (per-point factor tables whose halo planes come with each rank's slab of the model)
+_SCHEMES = [('ttiarr', {}), ('ttiarr', {'B2_HALO': 'nccl'}), ('iso12', {}), ('stream', {}), ('fs', {}), ('ot4', {}), ('born', {}), ('grad', {}), ('snap', {}), ('ot4', {'B2_HALO': 'nccl'}),
             ('born', {'B2_HALO': 'nccl'}), ('fs', {'B2_HALO': 'nccl'})]
 
 
