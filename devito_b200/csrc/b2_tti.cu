@@ -190,7 +190,7 @@ struct TtiFK {
 // D = how many batches the producer may run ahead of the slowest consumer (ring depths follow); CT = the array-
 // parameter variant that stages the rotation-factor tiles of stage A through shared memory by TMA (two planes of
 // three tables, paid for with one batch less of u / v prefetch)
-template <int R, int TY, int D = 3, bool CT = false>
+template <int R, int TY, int D = 3, int CT = 0>
 struct TtiCfg {
     static constexpr int H = R / 2;
     static constexpr int TZ4 = 16, TZ = 64, RZ = 4;
@@ -207,7 +207,9 @@ struct TtiCfg {
     static constexpr int NCT = TY * TZ4;             // consumer threads
     static constexpr int NCW = NCT / 32;
     static constexpr int GGROUPS = (TY + R - 1) * (BZ / 4);   // float4 groups of the extended tile
-    static constexpr int NCT_PLANES = CT ? 2 : 0;    // factor-tile ring: planes x+H-1 of this and the next iteration
+    // factor-tile ring: CT = 1 holds stage A's plane x+H-1 and the one in flight; CT = 2 also keeps the planes down to x
+    // for stage B (H live planes + the one in flight)
+    static constexpr int NCT_PLANES = CT == 0 ? 0 : (CT == 1 ? 2 : H + 1);
     static constexpr size_t SMEM = (size_t)((NUU + NUV) * PLANE + (2 * NG + 3 * NCT_PLANES) * GPLANE) * 4 + 2 * NB * 8 + 128;
 };
 
@@ -219,13 +221,14 @@ struct TtiCfg {
 // iteration. 52 B/point instead of 28.
 // CT = true (needs ARR): cx, cy, cz of stage A's plane arrive by TMA with the u / v batch instead (boxes of the
 // extended tile, zero-filled outside the array), so stage A has no global loads at all.
-template <int R, int TY, bool ARR, bool CT>
+template <int R, int TY, bool ARR, int CT>
 __global__ void __launch_bounds__(TY * 16 + 32, 1)
 k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_v,
             const __grid_constant__ CUtensorMap tm_cx, const __grid_constant__ CUtensorMap tm_cy,
             const __grid_constant__ CUtensorMap tm_cz, const TtiFK k) {
     static_assert(!CT || ARR, "factor tiles exist only with array-valued parameters");
     constexpr int D = CT ? 2 : 3;
+    constexpr int NCP = (CT == 0 ? 1 : (CT == 1 ? 2 : R / 2 + 1));   // planes of the factor-tile ring
     using C = TtiCfg<R, TY, D, CT>;
     constexpr int H = C::H, TZ = C::TZ, RZ = C::RZ, BZ = C::BZ, PR = C::PR, GR = C::GR;
     constexpr int NUU = C::NUU, NUV = C::NUV, NG = C::NG, NB = C::NB;
@@ -237,7 +240,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     float *s_v = s_u + NUU * PLANE;
     float *s_gu = s_v + NUV * PLANE;
     float *s_gv = s_gu + NG * GPLANE;
-    float *s_c = s_gv + NG * GPLANE;                // CT: [plane & 1][cx, cy, cz][GPLANE]
+    float *s_c = s_gv + NG * GPLANE;                // CT: [plane mod NCP][cx, cy, cz][GPLANE]
     uint64_t *full = reinterpret_cast<uint64_t *>(s_c + 3 * C::NCT_PLANES * GPLANE);
     uint64_t *empty = full + NB;
 
@@ -283,7 +286,8 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 const int pu = x + R;                    // u plane index (relative to origin)
                 const int pv = x + R - 1;
                 const bool hv = pv >= xs - (R - 1);      // v planes below xs-R+1 are never used
-                // CT: factor tiles of stage A's plane x+H-1; their slot held plane x+H-3, last read in iteration it-2
+                // CT: factor tiles of stage A's plane x+H-1; their slot held plane x+H-1-NCP, last read (stage A with CT = 1,
+                // stage B with CT = 2) in iteration it-2
                 const bool hc = CT && (x + H - 1 >= xs - H);
                 b2ptx::mbar_arrive_expect_tx(&full[it % NB], (uint32_t)(PR * BZ * 4) * (hv ? 2u : 1u) +
                                                                  (hc ? (uint32_t)(3 * C::GR * BZ * 4) : 0u));
@@ -294,7 +298,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                                        k.oz + z0 - RZ, k.oy + y0 - R, k.ox + pv, k.slot0);
                 if constexpr (CT) {
                     if (hc) {
-                        float *dst = s_c + ((x + H - 1) & 1) * 3 * GPLANE;
+                        float *dst = s_c + (((x + H - 1) % NCP + NCP) % NCP) * 3 * GPLANE;
                         b2ptx::tma_load_4d(dst, &tm_cx, &full[it % NB], k.oz + z0 - RZ, k.oy + y0 - H, k.ox + x + H - 1, 0);
                         b2ptx::tma_load_4d(dst + GPLANE, &tm_cy, &full[it % NB], k.oz + z0 - RZ, k.oy + y0 - H, k.ox + x + H - 1, 0);
                         b2ptx::tma_load_4d(dst + 2 * GPLANE, &tm_cz, &full[it % NB], k.oz + z0 - RZ, k.oy + y0 - H, k.ox + x + H - 1, 0);
@@ -350,6 +354,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
     // ring positions of plane x (updated incrementally; x starts at xs - PRE)
     int iu = ((xs - PRE) % NUU + NUU) % NUU, iv = ((xs - PRE) % NUV + NUV) % NUV,
         ig = ((xs - PRE) % NG + NG) % NG;
+    int ic = ((xs - PRE) % NCP + NCP) % NCP;        // CT: ring slot of factor plane x
     auto wrap = [](int v, int n) { return v >= n ? v - n : v; };
     // per-point tables read once per CTA: optionally kept out of L1, which the row / segment reads of cy, cz reuse
     const bool stream_hint = ARR && k.hint != 0;
@@ -408,10 +413,16 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             }
 #pragma unroll
             for (int i = 0; i < R - 1; ++i) cxq[i] = cxq[i + 1];
-            if (x + H - 1 >= xs - H && zcnt > 0)
-                cxq[R - 1] = ldt(k.tCx + gi + (long long)(H - 1) * k.sx);
+            if constexpr (CT != 2) {
+                if (x + H - 1 >= xs - H && zcnt > 0)
+                    cxq[R - 1] = ldt(k.tCx + gi + (long long)(H - 1) * k.sx);
+            }
         }
         b2ptx::mbar_wait(&full[it % NB], (it / NB) & 1);
+        if constexpr (CT == 2) {                     // own column of the cx tile that just landed (plane x+H-1)
+            if (x + H - 1 >= xs - H)
+                cxq[R - 1] = b2ptx::lds128(s_c + wrap(ic + H - 1, NCP) * 3 * GPLANE + my_goff);
+        }
 
         // queue: uq[i] = u plane x - R + i   (newest = x + R)
 #pragma unroll
@@ -438,7 +449,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
                 float4 rr = make_float4(0, 0, 0, 0);
                 float4 c4x = rr, c4y = rr, c4z = rr, ry = rr, rz = rr;   // ARR: factors at the Gz point; D+y, D+z kept apart
                 if constexpr (CT) {
-                    const float *cs = s_c + ((x + H - 1) & 1) * 3 * GPLANE + poff - (R - H) * BZ;
+                    const float *cs = s_c + wrap(ic + H - 1, NCP) * 3 * GPLANE + poff - (R - H) * BZ;
                     c4x = b2ptx::lds128(cs);
                     c4y = b2ptx::lds128(cs + GPLANE);
                     c4z = b2ptx::lds128(cs + 2 * GPLANE);
@@ -493,7 +504,15 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
             // ARR: cy at the R rows and cz on the z segment around the four points, issued ahead of their use
             float4 cyq[ARR ? R : 1];
             float czr[ARR ? 12 : 1];
-            if constexpr (ARR) {
+            if constexpr (CT == 2) {               // plane x of the factor ring: rows y-H+j of cy, z segment of cz
+                const float *cb = s_c + ic * 3 * GPLANE + my_goff;
+#pragma unroll
+                for (int j = 0; j < R; ++j) cyq[j] = b2ptx::lds128(cb + GPLANE + (j - H) * BZ);
+                const float4 l = b2ptx::lds128(cb + 2 * GPLANE - 4), cc = b2ptx::lds128(cb + 2 * GPLANE),
+                             r = b2ptx::lds128(cb + 2 * GPLANE + 4);
+                czr[0] = l.x; czr[1] = l.y; czr[2] = l.z; czr[3] = l.w; czr[4] = cc.x; czr[5] = cc.y; czr[6] = cc.z;
+                czr[7] = cc.w; czr[8] = r.x; czr[9] = r.y; czr[10] = r.z; czr[11] = r.w;
+            } else if constexpr (ARR) {
                 if (zcnt > 0) {
 #pragma unroll
                     for (int j = 0; j < R; ++j)
@@ -618,6 +637,7 @@ k_tti_fused(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CU
         }
         __syncwarp();
         if (lane == 0) b2ptx::mbar_arrive(&empty[it % NB]);
+        ic = wrap(ic + 1, NCP);
         iu = wrap(iu + 1, NUU);
         iv = wrap(iv + 1, NUV);
         ig = wrap(ig + 1, NG);
@@ -1043,6 +1063,10 @@ template <> struct TtiTile<4> { static constexpr int TY = 28; };
 template <int R> struct TtiTileArr;
 template <> struct TtiTileArr<2> { static constexpr int TY = 30; };
 template <> struct TtiTileArr<4> { static constexpr int TY = 22; };
+// ... and with the three-plane factor ring of CT = 2 (shared memory: 220 KB at 20 rows)
+template <int R> struct TtiTileArr2;
+template <> struct TtiTileArr2<2> { static constexpr int TY = 30; };
+template <> struct TtiTileArr2<4> { static constexpr int TY = 20; };
 static int env_int_tti(const char *name, int dflt);
 
 // scratch cached across calls
@@ -1102,7 +1126,10 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         if (p.arr_fused) {
             if ((rc = tables())) return rc;
             k_tti_coef_arr<<<148 * 8, 256, 0, stream()>>>(p.damp, p.tMD, inv_dt, p.coefA, p.slot_elems);
-            ty = p.R == 2 ? TtiTileArr<2>::TY : TtiTileArr<4>::TY;
+            p.arr_ct = env_int_tti("B2_TTI_ARR_CT", 1);
+            if (p.arr_ct < 0 || p.arr_ct > 2) p.arr_ct = 1;
+            ty = p.arr_ct == 2 ? (p.R == 2 ? TtiTileArr2<2>::TY : TtiTileArr2<4>::TY)
+                               : (p.R == 2 ? TtiTileArr<2>::TY : TtiTileArr<4>::TY);
         } else {
             const float md = (1.0f / (p.vp * p.vp)) * (1.0f / (p.dt * p.dt));
             k_tti_coef<<<148 * 8, 256, 0, stream()>>>(p.damp, md, inv_dt, p.coefA, p.slot_elems);
@@ -1113,7 +1140,7 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         if ((rc = tti_make_tmap(&p.tm_u, p.u, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
         if ((rc = tti_make_tmap(&p.tm_v, p.v, p.a, p.tsize, 72, ty + 2 * p.R))) return rc;
         p.tm_cx = p.tm_cy = p.tm_cz = p.tm_u;
-        p.arr_ct = p.arr_fused && env_int_tti("B2_TTI_ARR_CT", 1) != 0;
+        if (!p.arr_fused) p.arr_ct = 0;
         if (p.arr_ct) {     // boxes of the Gz tile (TY + R rows) over the factor tables
             if ((rc = tti_make_tmap(&p.tm_cx, p.tCx, p.a, 1, 72, ty + p.R))) return rc;
             if ((rc = tti_make_tmap(&p.tm_cy, p.tCy, p.a, 1, 72, ty + p.R))) return rc;
@@ -1141,18 +1168,23 @@ static int env_int_tti(const char *name, int dflt) {
 // fused kernel with per-point parameter tables
 template <int R>
 static int tti_launch_fused_arr(const TtiPlan &p, int slot0, int slotm, int slot1, int xlo, int xcount) {
-    constexpr int TY = TtiTileArr<R>::TY;
-    using C = TtiCfg<R, TY, 3, false>;
-    using CC = TtiCfg<R, TY, 2, true>;
-    auto kern = k_tti_fused<R, TY, true, false>;
-    auto kern_ct = k_tti_fused<R, TY, true, true>;
-    static_assert(CC::SMEM <= 232448 && C::SMEM <= 232448, "shared memory per CTA");
+    constexpr int TY1 = TtiTileArr<R>::TY, TY2 = TtiTileArr2<R>::TY;
+    using C0 = TtiCfg<R, TY1, 3, 0>;
+    using C1 = TtiCfg<R, TY1, 2, 1>;
+    using C2 = TtiCfg<R, TY2, 2, 2>;
+    auto kern0 = k_tti_fused<R, TY1, true, 0>;
+    auto kern1 = k_tti_fused<R, TY1, true, 1>;
+    auto kern2 = k_tti_fused<R, TY2, true, 2>;
+    static_assert(C0::SMEM <= 232448 && C1::SMEM <= 232448 && C2::SMEM <= 232448, "shared memory per CTA");
     static bool attr_set = false;
     if (!attr_set) {
-        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM), B2_ERR_LAUNCH);
-        B2_CUDA(cudaFuncSetAttribute(kern_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC::SMEM), B2_ERR_LAUNCH);
+        B2_CUDA(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C0::SMEM), B2_ERR_LAUNCH);
+        B2_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::SMEM), B2_ERR_LAUNCH);
+        B2_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::SMEM), B2_ERR_LAUNCH);
         attr_set = true;
     }
+    const int TY = p.arr_ct == 2 ? TY2 : TY1;
+    using C = C0;      // TZ is common to the three configurations
     TtiFK k;
     memset(&k, 0, sizeof(k));
     k.u1 = p.u + (size_t)slot1 * p.slot_elems;
@@ -1185,10 +1217,13 @@ static int tti_launch_fused_arr(const TtiPlan &p, int slot0, int slotm, int slot
     for (int i = 0; i <= R; ++i) { k.w2x[i] = p.w2[0][i]; k.w2y[i] = p.w2[1][i]; k.w2z[i] = p.w2[2][i]; }
     for (int i = 0; i < R; ++i) { k.w1x[i] = p.w1[0][i]; k.w1y[i] = p.w1[1][i]; k.w1z[i] = p.w1[2][i]; }
     timing_begin();
-    if (p.arr_ct)
-        kern_ct<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, CC::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_cx, p.tm_cy, p.tm_cz, k);
+    const unsigned nblk = (unsigned)(k.ntz * k.nty * ntx);
+    if (p.arr_ct == 2)
+        kern2<<<nblk, TY2 * 16 + 32, C2::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_cx, p.tm_cy, p.tm_cz, k);
+    else if (p.arr_ct == 1)
+        kern1<<<nblk, TY1 * 16 + 32, C1::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_cx, p.tm_cy, p.tm_cz, k);
     else
-        kern<<<(unsigned)(k.ntz * k.nty * ntx), TY * 16 + 32, C::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_cx, p.tm_cy, p.tm_cz, k);
+        kern0<<<nblk, TY1 * 16 + 32, C0::SMEM, stream()>>>(p.tm_u, p.tm_v, p.tm_cx, p.tm_cy, p.tm_cz, k);
     timing_end();
     count_launch();
     B2_CUDA(cudaGetLastError(), B2_ERR_LAUNCH);
@@ -1203,7 +1238,7 @@ static int tti_launch_fused(const TtiPlan &p, int slot0, int slotm, int slot1, i
     const int TY = ws ? kTtiWsTY : TYF;
     using C = TtiCfg<R, TYF>;
     using CW = TtiWsCfg<kTtiWsTY>;
-    auto kern = k_tti_fused<R, TYF, false, false>;
+    auto kern = k_tti_fused<R, TYF, false, 0>;
     static const int pf = env_int_tti("B2_TTI_PF", 1);   // measured: one-deep 2.94 ms, two-deep (spills) 3.83 ms at 768^3
     auto kern_ws = pf == 1 ? k_tti_ws<kTtiWsTY, 1> : k_tti_ws<kTtiWsTY, 2>;
     static bool attr_set = false;
