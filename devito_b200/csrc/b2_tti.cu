@@ -1126,8 +1126,8 @@ int tti_plan_init(TtiPlan &p, int kernel) {
         if (p.arr_fused) {
             if ((rc = tables())) return rc;
             k_tti_coef_arr<<<148 * 8, 256, 0, stream()>>>(p.damp, p.tMD, inv_dt, p.coefA, p.slot_elems);
-            p.arr_ct = env_int_tti("B2_TTI_ARR_CT", 1);
-            if (p.arr_ct < 0 || p.arr_ct > 2) p.arr_ct = 1;
+            p.arr_ct = env_int_tti("B2_TTI_ARR_CT", 2);
+            if (p.arr_ct < 0 || p.arr_ct > 2) p.arr_ct = 2;
             ty = p.arr_ct == 2 ? (p.R == 2 ? TtiTileArr2<2>::TY : TtiTileArr2<4>::TY)
                                : (p.R == 2 ? TtiTileArr<2>::TY : TtiTileArr<4>::TY);
         } else {
