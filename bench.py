@@ -16,8 +16,9 @@ A "step" = one `Operator.apply` of the Forward operator over NT time steps.
   parity_check : outside the timed region, a short propagation on a small grid (decomposed over the
              same N ranks, sources on the slab boundaries) compared with the CPU oracle on the
              undecomposed grid: every halo data path; a failure makes the run exit non-zero
-  configs  : short runs of the other BASELINE configs — C3 (so=12, 1024^3), C4 (TTI so=8, 768^3) at
-             N=1, C5 (so=8, 2048x1024x1024 FIXED, x-slabs = strong scaling) at every N
+  configs  : short runs of the other BASELINE configs — C3 (so=12, 1024^3), C4 (TTI so=8, 768^3), C4b (TTI so=8
+             with array-valued vp/eps/delta/theta/phi, 512^3) at N=1, C5 (so=8, 2048x1024x1024 FIXED, x-slabs =
+             strong scaling) at every N
 
 `--impl reference` times the reference's own CPU code path (oracle/_ref = C code emitted by the
 reference's code generator for this operator, compiled here with its flags; else the oracle
@@ -45,7 +46,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_ALG = {'iso': 16.0, 'tti': 28.0,    # algorithmic bytes / point / step
-         'tti-arrays': 52.0}           # + cx, cy, cz, 1+2eps, sqrt(1+2delta), m/dt^2 tables (DESIGN §3.3d)
+         'tti-arrays': 52.0}           # + cx, cy, cz, 1+2eps, sqrt(1+2delta), m/dt^2 tables (DESIGN §3.3a2)
 
 
 def parse():
