@@ -200,6 +200,35 @@ def tti(name, so, n, nbl, tn, preset='constant-tti', **kw):
          vp=np.array(model.vp.data, dtype=np.float32))
 
 
+def tti_varying(name, so, n, nbl, tn):
+    """TTI with vp, epsilon, delta, theta, phi varying along EVERY axis (the `layers-tti` preset varies along z only):
+    pins where the reference samples the rotation factors (at the Gz point inside Gz, at the shifted point in the
+    outer derivative) in all three directions."""
+    from devito import norm
+    from examples.seismic import SeismicModel, setup_geometry
+    from examples.seismic.tti import AnisotropicWaveSolver
+    shape = (n, n, n)
+    gx, gy, gz = np.meshgrid(*[np.linspace(0., 1., m, dtype=np.float32) for m in shape], indexing='ij')
+    par = dict(vp=(1.5 + 0.6 * gx + 0.5 * gy + 0.9 * gz).astype(np.float32),
+               epsilon=(0.25 * gx * gz + 0.05).astype(np.float32), delta=(0.12 * gy + 0.02).astype(np.float32),
+               theta=(0.2 + 0.9 * gx * gy + 0.3 * gz).astype(np.float32),
+               phi=(0.1 + 0.8 * gy * gz - 0.4 * gx).astype(np.float32))
+    model = SeismicModel(space_order=so, origin=(0., 0., 0.), shape=shape, dtype=np.float32, spacing=(10., 10., 10.),
+                         nbl=nbl, bcs="damp", **par)
+    geometry = setup_geometry(model, tn)
+    solver = AnisotropicWaveSolver(model, geometry, space_order=so)
+    rec, u, v, _ = solver.forward()
+    # the parameter arrays follow the formulas above (tests/helpers.py::varying_tti_parameters restates them); the model
+    # pads them with edge values over the absorbing layers, which the fixture records for vp only as a cross-check
+    save(name, so=so, n=n, nbl=nbl, tn=tn, dt=np.float32(model.critical_dt), nt=geometry.nt,
+         src_coords=np.array(geometry.src.coordinates.data), rec=np.array(rec.data),
+         slot=(geometry.nt - 1) % 3, u_last=np.array(u.data[(geometry.nt - 1) % 3]),
+         v_last=np.array(v.data[(geometry.nt - 1) % 3]), norm_rec=np.float32(norm(rec)),
+         norm_u=np.float32(norm(u)), norm_v=np.float32(norm(v)),
+         vp_line=np.array(model.vp.data[:, n // 2 + nbl, n // 3 + nbl], dtype=np.float32),
+         theta_line=np.array(model.theta.data[n // 3 + nbl, :, n // 2 + nbl], dtype=np.float32))
+
+
 def coefficients():
     """FD weights and CFL numbers straight from the reference's machinery."""
     from devito import Grid, TimeFunction
@@ -217,7 +246,7 @@ def coefficients():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'born', 'snap', 'adjvar', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'coef']
+    which = sys.argv[1:] or ['kat2d', 'fs', 'ot4', 'born', 'snap', 'adjvar', 'iso8', 'iso12', 'iso4layers', 'iso8sinc', 'adj8', 'grad8', 'tti8', 'tti4', 'tti4layers', 'tti8varying', 'coef']
     if 'kat2d' in which:
         kat2d()
     if 'fs' in which:
@@ -251,6 +280,8 @@ if __name__ == '__main__':
         gradient('grad3d_so8', so=8, n=20, nbl=8, tn=150.0)
     if 'tti8' in which:
         tti('tti3d_so8', so=8, n=20, nbl=8, tn=150.0)
+    if 'tti8varying' in which:
+        tti_varying('tti3d_so8_varying', so=8, n=24, nbl=8, tn=90.0)
     if 'tti4layers' in which:
         tti('tti3d_so4_layers', so=4, n=20, nbl=8, tn=100.0, preset='layers-tti', nlayers=3)
     if 'tti4' in which:

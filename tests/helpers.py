@@ -88,3 +88,13 @@ def fs_problem(n, nbl, so, tn, h=10.0, nlayers=3, interpolation='linear', f0=0.0
                 vp=np.pad(vp_dom, so, mode='edge').astype(np.float32),
                 src=dict(data=src, gp=sgp, w=sw, r=rr), rec=dict(data=rec, gp=rgp, w=rw, r=rr),
                 src_coords=src_c, rec_coords=rec_c, origin=origin, spacing=spacing)
+
+
+def varying_tti_parameters(n):
+    """vp, epsilon, delta, theta, phi of the fixture `tti3d_so8_varying` on the physical n^3 grid (the formulas of
+    oracle/make_golden.py::tti_varying): every parameter varies along every axis."""
+    gx, gy, gz = np.meshgrid(*[np.linspace(0., 1., n, dtype=np.float32)] * 3, indexing='ij')
+    return dict(vp=(1.5 + 0.6 * gx + 0.5 * gy + 0.9 * gz).astype(np.float32),
+                epsilon=(0.25 * gx * gz + 0.05).astype(np.float32), delta=(0.12 * gy + 0.02).astype(np.float32),
+                theta=(0.2 + 0.9 * gx * gy + 0.3 * gz).astype(np.float32),
+                phi=(0.1 + 0.8 * gy * gz - 0.4 * gx).astype(np.float32))

@@ -284,6 +284,29 @@ def test_tti_array_parameters_vs_reference_golden():
     assert rel_linf(rec.data, g['rec']) < 1e-4
 
 
+@pytest.mark.parametrize('kernel', [0, 1])
+def test_tti_array_parameters_varying_along_every_axis_vs_reference_golden(kernel):
+    """The reference's own run with vp / epsilon / delta / theta / phi varying along x, y and z (fixture
+    `tti3d_so8_varying`, oracle/make_golden.py::tti_varying): single-pass kernel with the TMA-staged factor tiles
+    (kernel=0, the default) and the two-pass generic kernels (kernel=1)."""
+    from helpers import varying_tti_parameters
+    from devito_b200.seismic import SeismicModel, setup_geometry, AnisotropicWaveSolver
+    g = load_golden('tti3d_so8_varying')
+    n, nbl = int(g['n']), int(g['nbl'])
+    model = SeismicModel(space_order=8, origin=(0., 0., 0.), shape=(n, n, n), dtype=np.float32,
+                         spacing=(10., 10., 10.), nbl=nbl, bcs="damp", **varying_tti_parameters(n))
+    assert np.float32(model.critical_dt) == g['dt']
+    geometry = setup_geometry(model, float(g['tn']))
+    assert geometry.nt == int(g['nt'])
+    solver = AnisotropicWaveSolver(model, geometry, space_order=8)
+    assert solver.op_fwd().backend == 'cuda-sm100a'
+    rec, u, v, _ = solver.forward(kernel=kernel)
+    slot = int(g['slot'])
+    assert rel_linf(u.data[slot], g['u_last']) < 1e-4
+    assert rel_linf(v.data[slot], g['v_last']) < 1e-4
+    assert rel_linf(rec.data, g['rec']) < 1e-4
+
+
 @pytest.mark.parametrize('so,shape,nbl', [(8, (40, 52, 72), 10), (4, (44, 40, 60), 8)])
 def test_tti_array_parameters_fused_vs_two_pass(so, shape, nbl):
     """`layers-tti` through the single-pass kernel (k_tti_fused<.., ARR>: per-point rotation factors read from the
