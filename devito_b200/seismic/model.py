@@ -235,7 +235,10 @@ class SeismicModel:
         key = tuple((id(p), getattr(getattr(p, 'storage', None), 'version', None) if hasattr(p, 'storage')
                      else float(getattr(p, 'data', p))) for p in pars) + (self.dt_scale,)
         cached = getattr(self, '_critical_dt_cache', None)
-        if cached is not None and cached[0] == key and None not in [k[1] for k in key[:-1]]:
+        # under decomposition the maxima are collectives: every rank must take the same branch, so no rank-local
+        # shortcut there
+        parallel = self.grid.distributor.is_parallel
+        if not parallel and cached is not None and cached[0] == key and None not in [k[1] for k in key[:-1]]:
             return cached[1]
         vmax = mmax(self.vp)
         aniso = np.sqrt(1 + 2 * mmax(self.epsilon)) if 'epsilon' in self._physical_parameters else 1
